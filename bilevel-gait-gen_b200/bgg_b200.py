@@ -1,0 +1,300 @@
+"""ctypes binding over libbgg_b200.so (include/bgg.h) -- the product's Python entry point used by tests and bench.py.
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is present, construction raises.
+Nothing here imports or calls anything under oracle/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbgg_b200.so")
+
+NX, NX_MAN, NUM_EE = 12, 13, 4
+MAX_KNOTS, MAX_NODES = 28, 64
+STATUS_NAMES = ["Solved", "SolvedInacc", "MaxIter", "PrimalInfeasible", "DualInfeasible", "PrimalInfeasibleInacc",
+                "DualInfeasibleInacc", "Unsolved", "Other"]
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class BggError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32), ("max_spline_vars", C.c_int32), ("device", C.c_int32), ("ipm_max_iter", C.c_int32),
+                ("ipm_refine", C.c_int32), ("reserved_", C.c_int32), ("integrator_dt", C.c_double), ("friction_coef", C.c_double),
+                ("force_bound", C.c_double), ("swing_height", C.c_double), ("foot_offset", C.c_double),
+                ("ee_box_size", C.c_double * 2), ("force_cost", C.c_double), ("ipm_tol_feas", C.c_double),
+                ("ipm_tol_gap", C.c_double), ("ipm_eq_delta", C.c_double)]
+
+
+class Robot(C.Structure):
+    _fields_ = [("mass", C.c_double), ("Ir", C.c_double * 9), ("Ir_inv", C.c_double * 9), ("hip_xy", C.c_double * 8),
+                ("gravity", C.c_double * 3)]
+
+
+class Sizes(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n", "nu", "nf", "np", "n_samples", "n_eebox", "n_eq", "n_td", "m_ineq", "status",
+                                         "iters", "ls_iters", "error")] + \
+               [("nfv", C.c_int32 * 4), ("npv", C.c_int32 * 4), ("fbase", C.c_int32 * 4), ("pbase", C.c_int32 * 4)] + \
+               [(n, C.c_double) for n in ("t0", "alpha", "cost", "prim_res", "dual_res", "gap", "eq_violation", "step_norm",
+                                          "merit", "merit_dd")] + [("ee_box", C.c_double * 2)]
+
+
+# numpy view of the POD bgg::Instance / bgg::FootSpline (csrc/bgg_types.cuh)
+FOOT_DTYPE = np.dtype([("n", np.int32), ("ttype", np.uint8, MAX_KNOTS), ("ftype", np.uint8, MAX_KNOTS),
+                       ("ptype", np.uint8, MAX_KNOTS), ("ztype", np.uint8, MAX_KNOTS), ("t", np.float64, MAX_KNOTS),
+                       ("f", np.float64, (3, MAX_KNOTS, 2)), ("p", np.float64, (3, MAX_KNOTS, 2))], align=True)
+INSTANCE_DTYPE = np.dtype([("states", np.float64, (MAX_NODES + 1, NX_MAN)), ("foot", FOOT_DTYPE, NUM_EE),
+                           ("ee_box", np.float64, 2), ("init_time", np.float64), ("run_count", np.int32),
+                           ("pad_", np.int32)], align=True)
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BggError(f"{LIB_PATH} is missing: build it with bilevel-gait-gen_b200/build.sh (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        L.bgg_last_error.restype = C.c_char_p
+        L.bgg_create.argtypes = [C.POINTER(Config), C.POINTER(Robot), C.POINTER(C.c_void_p)]
+        L.bgg_destroy.argtypes = [C.c_void_p]
+        L.bgg_set_costs.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+        L.bgg_batch_reset.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int]
+        L.bgg_set_warm_states.argtypes = [C.c_void_p, _dp, C.c_int]
+        L.bgg_set_contact_times.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, C.c_int]
+        L.bgg_solve_batch.argtypes = [C.c_void_p, _dp, _dp, _dp, _ip, _ip, _dp, _dp]
+        L.bgg_upload_inputs.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.bgg_solve_resident.argtypes = [C.c_void_p]
+        L.bgg_download_results.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp]
+        L.bgg_synchronize.argtypes = [C.c_void_p]
+        L.bgg_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.bgg_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.bgg_kernel_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.bgg_get_sizes.argtypes = [C.c_void_p, C.c_int, C.POINTER(Sizes)]
+        L.bgg_get_dynamics.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int]
+        L.bgg_get_condensed.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
+        L.bgg_get_solution.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.bgg_instance_bytes.restype = C.c_size_t
+        L.bgg_get_instance.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.bgg_set_instance.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.bgg_get_states.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.bgg_eval_splines.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _dp, _dp]
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    """Names include/bgg.h declares; used by the CPU-side ABI test."""
+    return ["bgg_last_error", "bgg_device_count", "bgg_create", "bgg_destroy", "bgg_set_costs", "bgg_batch_reset",
+            "bgg_set_warm_states", "bgg_set_contact_times", "bgg_solve_batch", "bgg_upload_inputs", "bgg_solve_resident",
+            "bgg_download_results", "bgg_synchronize", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count",
+            "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_get_solution", "bgg_instance_bytes",
+            "bgg_get_instance", "bgg_set_instance", "bgg_get_states", "bgg_eval_splines"]
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class BatchedMPC:
+    """A batch of independent mpc::MPCSingleRigidBody instances living on one B200.
+
+    Method names follow the reference class (mpc/include/mpc.h, mpc_single_rigid_body.h); every array argument has a
+    leading batch dimension.
+    """
+
+    def __init__(self, num_nodes, integrator_dt, robot, friction_coef=0.5, force_bound=150.0, swing_height=0.075,
+                 foot_offset=0.015, ee_box_size=(0.15, 0.15), force_cost=0.0, device=0, max_spline_vars=0,
+                 ipm_tol=0.0, ipm_max_iter=0, ipm_refine=0):
+        self.L = lib()
+        self.N = num_nodes
+        cfg = Config()
+        cfg.num_nodes = num_nodes
+        cfg.max_spline_vars = max_spline_vars
+        cfg.device = device
+        cfg.ipm_max_iter = ipm_max_iter
+        cfg.ipm_refine = ipm_refine
+        cfg.integrator_dt = integrator_dt
+        cfg.friction_coef = friction_coef
+        cfg.force_bound = force_bound
+        cfg.swing_height = swing_height
+        cfg.foot_offset = foot_offset
+        cfg.ee_box_size[0], cfg.ee_box_size[1] = ee_box_size
+        cfg.force_cost = force_cost
+        cfg.ipm_tol_feas = ipm_tol
+        cfg.ipm_tol_gap = ipm_tol
+        cfg.ipm_eq_delta = 0.0
+        rb = Robot()
+        rb.mass = robot["mass"]
+        rb.Ir[:] = np.asarray(robot["Ir"], float).ravel().tolist()
+        rb.Ir_inv[:] = np.asarray(robot["Ir_inv"], float).ravel().tolist()
+        rb.hip_xy[:] = np.asarray(robot["hip_offsets_xy"], float).ravel().tolist()
+        rb.gravity[:] = list(robot["gravity"])
+        self.h = C.c_void_p()
+        self._chk(self.L.bgg_create(C.byref(cfg), C.byref(rb), C.byref(self.h)))
+        self.B = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise BggError(f"bgg error {rc}: {self.L.bgg_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.bgg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- reference-named setters ---------------------------------------------------------------------------------
+    def AddQuadraticTrackingCost(self, state_des_tangent, Q_diag, Phi_diag=None, Phi_w=None):
+        q = np.ascontiguousarray(Q_diag, np.float64)
+        d = np.ascontiguousarray(state_des_tangent, np.float64)
+        phi = None if Phi_diag is None else np.ascontiguousarray(Phi_diag, np.float64)
+        pw = None if Phi_w is None else np.ascontiguousarray(Phi_w, np.float64)
+        self._chk(self.L.bgg_set_costs(self.h, _d(q), _d(d), None if phi is None else _d(phi), None if pw is None else _d(pw)))
+
+    def Reset(self, batch, contact_times=None):
+        self.B = batch
+        if contact_times is None:
+            self._chk(self.L.bgg_batch_reset(self.h, batch, None, 0))
+        else:
+            ct = np.ascontiguousarray(contact_times, np.float64)
+            assert ct.shape[0] == NUM_EE
+            self._chk(self.L.bgg_batch_reset(self.h, batch, _d(ct), ct.shape[1]))
+
+    def SetStateTrajectoryWarmStart(self, states):
+        s = np.ascontiguousarray(states, np.float64)
+        if s.ndim == 2:
+            assert s.shape == (self.B, NX_MAN)
+            self._chk(self.L.bgg_set_warm_states(self.h, _d(s), 0))
+        else:
+            assert s.shape == (self.B, self.N + 1, NX_MAN)
+            self._chk(self.L.bgg_set_warm_states(self.h, _d(s), 1))
+
+    def UpdateContactTimes(self, times, first=0):
+        t = np.ascontiguousarray(times, np.float64)
+        assert t.ndim == 3 and t.shape[1] == NUM_EE
+        self._chk(self.L.bgg_set_contact_times(self.h, first, t.shape[0], _d(t), t.shape[2]))
+
+    # --- solves ---------------------------------------------------------------------------------------------------
+    def GetRealTimeUpdate(self, state, init_time, ee_start_locations):
+        """One RTI solve per instance. Returns dict(status, iters, alpha, cost) of numpy arrays [B]."""
+        s, t, e = self._inputs(state, init_time, ee_start_locations)
+        st, it = np.zeros(self.B, np.int32), np.zeros(self.B, np.int32)
+        al, co = np.zeros(self.B), np.zeros(self.B)
+        self._chk(self.L.bgg_solve_batch(self.h, _d(s), _d(t), _d(e), _i(st), _i(it), _d(al), _d(co)))
+        return dict(status=st, iters=it, alpha=al, cost=co)
+
+    Solve = GetRealTimeUpdate
+
+    def CreateInitialRun(self, state, ee_start_locations, num_solves=10):
+        out = None
+        for _ in range(num_solves):   # mpc.cpp:78-90: ten solves at t = 0
+            out = self.GetRealTimeUpdate(state, np.zeros(self.B), ee_start_locations)
+        return out
+
+    def _inputs(self, state, init_time, ee):
+        s = np.ascontiguousarray(state, np.float64)
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(init_time, np.float64), (self.B,)))
+        e = np.ascontiguousarray(ee, np.float64)
+        if s.shape != (self.B, NX_MAN) or e.shape != (self.B, NUM_EE, 3):
+            raise BggError("state must be [B][13] and ee_start_locations [B][4][3]")
+        return s, t, e
+
+    def upload(self, state, init_time, ee):
+        s, t, e = self._inputs(state, init_time, ee)
+        self._chk(self.L.bgg_upload_inputs(self.h, _d(s), _d(t), _d(e)))
+
+    def solve_resident(self):
+        self._chk(self.L.bgg_solve_resident(self.h))
+
+    def download(self):
+        st, it = np.zeros(self.B, np.int32), np.zeros(self.B, np.int32)
+        al, co = np.zeros(self.B), np.zeros(self.B)
+        self._chk(self.L.bgg_download_results(self.h, _i(st), _i(it), _d(al), _d(co)))
+        return dict(status=st, iters=it, alpha=al, cost=co)
+
+    def synchronize(self):
+        self._chk(self.L.bgg_synchronize(self.h))
+
+    def set_profiling(self, on):
+        self._chk(self.L.bgg_set_profiling(self.h, int(on)))
+
+    def last_kernel_ms(self):
+        ms = (C.c_float * 4)()
+        self._chk(self.L.bgg_last_kernel_ms(self.h, ms))
+        return dict(zip(("prepare", "condense", "ipm", "finish"), (float(v) for v in ms)))
+
+    def launch_count(self):
+        v = C.c_int64()
+        self._chk(self.L.bgg_kernel_launch_count(self.h, C.byref(v)))
+        return v.value
+
+    # --- accessors ------------------------------------------------------------------------------------------------
+    def sizes(self, b=0):
+        s = Sizes()
+        self._chk(self.L.bgg_get_sizes(self.h, b, C.byref(s)))
+        out = {}
+        for name, _t in Sizes._fields_:
+            v = getattr(s, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        return out
+
+    def dynamics(self, first=0, count=1, nu=None):
+        nu = nu or self.sizes(first)["nu"]
+        Ad = np.zeros((count, self.N, 12, 12))
+        Bd = np.zeros((count, self.N, 12, nu))
+        cd = np.zeros((count, self.N, 12))
+        self._chk(self.L.bgg_get_dynamics(self.h, first, count, _d(Ad), _d(Bd), _d(cd), nu))
+        return Ad, Bd, cd
+
+    def condensed(self, b=0):
+        nu = self.sizes(b)["nu"]
+        H, g = np.zeros((nu, nu)), np.zeros(nu)
+        pp, xo = np.zeros((2 * (self.N - 3), nu)), np.zeros((self.N + 1, 12))
+        self._chk(self.L.bgg_get_condensed(self.h, b, _d(H), _d(g), _d(pp), _d(xo)))
+        return dict(H=H, g=g, phipos=pp, xoff=xo)
+
+    def solution(self, b=0):
+        sz = self.sizes(b)
+        qp, z = np.zeros(sz["n"]), np.zeros(sz["n"])
+        lam, sl, nu = np.zeros(sz["m_ineq"]), np.zeros(sz["m_ineq"]), np.zeros(sz["n_eq"])
+        self._chk(self.L.bgg_get_solution(self.h, b, _d(qp), _d(z), _d(lam), _d(sl), _d(nu)))
+        return dict(qp_sol=qp, z=z, lam=lam, slack=sl, nu_eq=nu, sizes=sz)
+
+    def get_instance(self, b=0):
+        assert self.L.bgg_instance_bytes() == INSTANCE_DTYPE.itemsize, (self.L.bgg_instance_bytes(), INSTANCE_DTYPE.itemsize)
+        buf = np.zeros(1, dtype=INSTANCE_DTYPE)
+        self._chk(self.L.bgg_get_instance(self.h, b, buf.ctypes.data_as(C.c_void_p)))
+        return buf[0]
+
+    def set_instance(self, b, inst):
+        buf = np.zeros(1, dtype=INSTANCE_DTYPE)
+        buf[0] = inst
+        self._chk(self.L.bgg_set_instance(self.h, b, buf.ctypes.data_as(C.c_void_p)))
+
+    def GetStates(self, b=0):
+        s = np.zeros((self.N + 1, NX_MAN))
+        self._chk(self.L.bgg_get_states(self.h, b, _d(s)))
+        return s
+
+    def eval_splines(self, b, times):
+        t = np.ascontiguousarray(times, np.float64)
+        f, p = np.zeros((len(t), NUM_EE, 3)), np.zeros((len(t), NUM_EE, 3))
+        self._chk(self.L.bgg_eval_splines(self.h, b, _d(t), len(t), _d(f), _d(p)))
+        return f, p

@@ -1,0 +1,16 @@
+#!/usr/bin/env bash
+# Builds libbgg_b200.so (the C-ABI library of include/bgg.h) in-tree for sm_100a.
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -v"
+mkdir -p build
+# bgg_prepare.cu is compiled without FMA contraction so that exact zeros stay exact (sparsity parity).
+$NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_prepare.o csrc/bgg_prepare.cu 2> build/ptxas_prepare.log
+$NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_condense.o csrc/bgg_condense.cu 2> build/ptxas_condense.log
+$NVCC $ARCH $COMMON -dc -o build/bgg_ipm.o csrc/bgg_ipm.cu 2> build/ptxas_ipm.log
+$NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_finish.o csrc/bgg_finish.cu 2> build/ptxas_finish.log
+$NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_capi.o csrc/bgg_capi.cu 2> build/ptxas_capi.log
+$NVCC $ARCH -shared -o libbgg_b200.so build/bgg_prepare.o build/bgg_condense.o build/bgg_ipm.o build/bgg_finish.o build/bgg_capi.o -lcudart
+echo "built $(pwd)/libbgg_b200.so"

@@ -1,0 +1,475 @@
+// bilevel-gait-gen_b200 -- the C ABI (include/bgg.h) over the CUDA kernels.  No torch types, no exceptions across
+// the boundary.  There is no CPU fallback: without a CUDA device bgg_create fails with BGG_ECUDA.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bgg.h"
+#include "bgg_kernels.cuh"
+
+using namespace bgg;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(BGG_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct bgg_handle {
+    Params P{};
+    WsLayout L{};
+    int device = 0;
+    int batch = 0;
+    cudaStream_t stream = nullptr;
+    Instance* d_inst = nullptr;
+    char* d_ws = nullptr;
+    double *d_state = nullptr, *d_t0 = nullptr, *d_ee = nullptr;
+    // pinned staging
+    double *h_state = nullptr, *h_t0 = nullptr, *h_ee = nullptr;
+    WsHeader* h_hdr = nullptr;   // pinned [batch]
+    WsHeader* d_hdr = nullptr;   // compact copy of the headers [batch]
+    bool profiling = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float last_ms[4] = {0, 0, 0, 0};
+    int64_t launches = 0;
+    bool costs_set = false;
+};
+
+__global__ void k_gather_headers(WsLayout L, const char* __restrict__ ws, WsHeader* __restrict__ out, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) out[b] = *reinterpret_cast<const WsHeader*>(ws + static_cast<size_t>(b) * L.stride + L.hdr);
+}
+
+__global__ void k_reset(Params P, Instance* inst, int B, const double* __restrict__ ct, int nct) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    Instance& I = inst[b];
+    for (int k = 0; k <= kMaxNodes; ++k)
+        for (int c = 0; c < kNxMan; ++c) I.states[k][c] = 0.0;
+    const double def[5] = {0.0, 0.3, 0.6, 0.9, 1.2};
+    for (int e = 0; e < kNumEE; ++e) {
+        double t[16];
+        const int n = ct ? nct : 5;
+        for (int i = 0; i < n; ++i) t[i] = ct ? ct[e * nct + i] : def[i];
+        init_foot(I.foot[e], t, n, e == 1 || e == 2);            // trajectory.cpp:25-28
+        set_swing_pos_z(I.foot[e], P.swing_height, P.foot_offset);
+    }
+    I.ee_box[0] = P.ee_box_nominal[0];
+    I.ee_box[1] = P.ee_box_nominal[1];
+    I.init_time = 0.0;
+    I.run_count = 0;
+    I.pad_ = 0;
+}
+
+__global__ void k_warm_states(Instance* inst, int B, int N, const double* __restrict__ states, int per_node) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * (N + 1)) return;
+    const int b = i / (N + 1), k = i % (N + 1);
+    const double* src = per_node ? states + static_cast<size_t>(i) * kNxMan : states + static_cast<size_t>(b) * kNxMan;
+    for (int c = 0; c < kNxMan; ++c) inst[b].states[k][c] = src[c];
+}
+
+__global__ void k_set_contact_times(Instance* inst, int first, int count, const double* __restrict__ times, int nct) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count * kNumEE) return;
+    const int b = first + i / kNumEE, e = i % kNumEE;
+    set_contact_times(inst[b].foot[e], times + static_cast<size_t>(i) * nct, nct);
+}
+
+__global__ void k_eval_splines(const Instance* inst, int b, const double* __restrict__ times, int T, double* __restrict__ force,
+                               double* __restrict__ pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * kNumEE) return;
+    const int e = i % kNumEE;
+    const double t = times[i / kNumEE];
+    for (int c = 0; c < 3; ++c) {
+        force[i * 3 + c] = value_at(inst[b].foot[e], true, c, t);
+        pos[i * 3 + c] = value_at(inst[b].foot[e], false, c, t);
+    }
+}
+
+extern "C" {
+
+const char* bgg_last_error(void) { return g_err.c_str(); }
+
+int bgg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) {
+    if (!cfg || !robot || !out) return fail(BGG_EINVAL, "null argument");
+    if (cfg->num_nodes <= kEENodeStart || cfg->num_nodes > kMaxNodes) return fail(BGG_EINVAL, "num_nodes must be in (4, 64]");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(BGG_ECUDA, "no CUDA device: this library has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(BGG_EINVAL, "bad device ordinal");
+    CU(cudaSetDevice(cfg->device));
+    bgg_handle* h = new bgg_handle;
+    h->device = cfg->device;
+    Params& P = h->P;
+    P.N = cfg->num_nodes;
+    P.max_nu = cfg->max_spline_vars > 0 ? cfg->max_spline_vars : 160;
+    if (P.max_nu < P.N + 1 || P.max_nu % 8) {
+        delete h;
+        return fail(BGG_EINVAL, "max_spline_vars must be a multiple of 8 and >= num_nodes + 1");
+    }
+    P.dt = cfg->integrator_dt;
+    P.mass = robot->mass;
+    std::memcpy(P.Ir, robot->Ir, sizeof P.Ir);
+    std::memcpy(P.Ir_inv, robot->Ir_inv, sizeof P.Ir_inv);
+    std::memcpy(P.gravity, robot->gravity, sizeof P.gravity);
+    std::memcpy(P.hip_xy, robot->hip_xy, sizeof P.hip_xy);
+    P.friction_coef = cfg->friction_coef;
+    P.force_bound = cfg->force_bound;
+    P.swing_height = cfg->swing_height;
+    P.foot_offset = cfg->foot_offset;
+    P.force_cost = cfg->force_cost;
+    P.ee_box_nominal[0] = cfg->ee_box_size[0];
+    P.ee_box_nominal[1] = cfg->ee_box_size[1];
+    for (int i = 0; i < kNx; ++i) P.Q[i] = P.w[i] = P.Phi[i] = P.Phi_w[i] = 0.0;
+    P.merit_mu = 5000.0;      // mpc.cpp:65
+    P.td_fraction = 0.75;     // mpc.cpp:73
+    P.ipm_tol_feas = cfg->ipm_tol_feas > 0 ? cfg->ipm_tol_feas : 1e-8;
+    P.ipm_tol_gap = cfg->ipm_tol_gap > 0 ? cfg->ipm_tol_gap : 1e-8;
+    P.ipm_eq_delta = cfg->ipm_eq_delta > 0 ? cfg->ipm_eq_delta : 1e-8;
+    P.ipm_max_iter = cfg->ipm_max_iter > 0 ? cfg->ipm_max_iter : 50;
+    P.ipm_refine = cfg->ipm_refine < 0 ? 0 : (cfg->ipm_refine == 0 ? 1 : cfg->ipm_refine);
+    h->L = make_layout(P.N, P.max_nu);
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+    if (ipm_smem_bytes(h->L) > static_cast<size_t>(max_smem) || condense_smem_bytes(h->L) > static_cast<size_t>(max_smem)) {
+        delete h;
+        return fail(BGG_EINVAL, "num_nodes / max_spline_vars need more shared memory than the device offers");
+    }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return fail(BGG_ECUDA, "cudaStreamCreate failed");
+    }
+    for (auto& e : h->ev) cudaEventCreate(&e);
+    *out = h;
+    return BGG_OK;
+}
+
+static void free_batch(bgg_handle* h) {
+    cudaFree(h->d_inst);
+    cudaFree(h->d_ws);
+    cudaFree(h->d_state);
+    cudaFree(h->d_t0);
+    cudaFree(h->d_ee);
+    cudaFree(h->d_hdr);
+    cudaFreeHost(h->h_state);
+    cudaFreeHost(h->h_t0);
+    cudaFreeHost(h->h_ee);
+    cudaFreeHost(h->h_hdr);
+    h->d_inst = nullptr;
+    h->d_ws = nullptr;
+    h->d_state = h->d_t0 = h->d_ee = nullptr;
+    h->h_state = h->h_t0 = h->h_ee = nullptr;
+    h->d_hdr = nullptr;
+    h->h_hdr = nullptr;
+    h->batch = 0;
+}
+
+void bgg_destroy(bgg_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_batch(h);
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int bgg_set_costs(bgg_handle* h, const double Q[BGG_NX], const double x_des[BGG_NX], const double Phi[BGG_NX],
+                  const double Phi_w[BGG_NX]) {
+    if (!h || !Q || !x_des) return fail(BGG_EINVAL, "null argument");
+    for (int i = 0; i < kNx; ++i) {
+        h->P.Q[i] = Q[i];
+        h->P.w[i] = (-1 * Q[i]) * x_des[i];             // w_ = -1*Q*state_des, mpc.cpp:539
+        h->P.Phi[i] = Phi ? Phi[i] : Q[i];
+        h->P.Phi_w[i] = Phi_w ? Phi_w[i] : h->P.w[i];
+    }
+    h->costs_set = true;
+    return BGG_OK;
+}
+
+int bgg_batch_reset(bgg_handle* h, int batch, const double* contact_times, int num_contacts) {
+    if (!h || batch <= 0) return fail(BGG_EINVAL, "bad batch");
+    if (contact_times && (num_contacts < 2 || num_contacts > 8)) return fail(BGG_EINVAL, "num_contacts must be in [2, 8]");
+    CU(cudaSetDevice(h->device));
+    if (batch != h->batch) {
+        cudaStreamSynchronize(h->stream);
+        free_batch(h);
+        CU(cudaMalloc(&h->d_inst, sizeof(Instance) * static_cast<size_t>(batch)));
+        CU(cudaMalloc(&h->d_ws, h->L.stride * static_cast<size_t>(batch)));
+        CU(cudaMalloc(&h->d_state, 8 * kNxMan * static_cast<size_t>(batch)));
+        CU(cudaMalloc(&h->d_t0, 8 * static_cast<size_t>(batch)));
+        CU(cudaMalloc(&h->d_ee, 8 * 12 * static_cast<size_t>(batch)));
+        CU(cudaMalloc(&h->d_hdr, sizeof(WsHeader) * static_cast<size_t>(batch)));
+        CU(cudaMallocHost(&h->h_state, 8 * kNxMan * static_cast<size_t>(batch)));
+        CU(cudaMallocHost(&h->h_t0, 8 * static_cast<size_t>(batch)));
+        CU(cudaMallocHost(&h->h_ee, 8 * 12 * static_cast<size_t>(batch)));
+        CU(cudaMallocHost(&h->h_hdr, sizeof(WsHeader) * static_cast<size_t>(batch)));
+        CU(cudaMemsetAsync(h->d_ws, 0, h->L.stride * static_cast<size_t>(batch), h->stream));
+        h->batch = batch;
+    }
+    double* d_ct = nullptr;
+    if (contact_times) {
+        CU(cudaMalloc(&d_ct, 8 * kNumEE * num_contacts));
+        CU(cudaMemcpyAsync(d_ct, contact_times, 8 * kNumEE * num_contacts, cudaMemcpyHostToDevice, h->stream));
+    }
+    k_reset<<<(batch + 127) / 128, 128, 0, h->stream>>>(h->P, h->d_inst, batch, d_ct, num_contacts);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    if (d_ct) cudaFree(d_ct);
+    return BGG_OK;
+}
+
+int bgg_set_warm_states(bgg_handle* h, const double* states, int per_node) {
+    if (!h || !states || !h->batch) return fail(BGG_EINVAL, "no batch");
+    CU(cudaSetDevice(h->device));
+    const size_t cnt = static_cast<size_t>(h->batch) * (per_node ? (h->P.N + 1) : 1) * kNxMan;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, 8 * cnt));
+    CU(cudaMemcpyAsync(d, states, 8 * cnt, cudaMemcpyHostToDevice, h->stream));
+    const int tot = h->batch * (h->P.N + 1);
+    k_warm_states<<<(tot + 127) / 128, 128, 0, h->stream>>>(h->d_inst, h->batch, h->P.N, d, per_node);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    return BGG_OK;
+}
+
+int bgg_set_contact_times(bgg_handle* h, int first, int count, const double* times, int nct) {
+    if (!h || !times || first < 0 || count <= 0 || first + count > h->batch) return fail(BGG_EINVAL, "bad range");
+    CU(cudaSetDevice(h->device));
+    const size_t cnt = static_cast<size_t>(count) * kNumEE * nct;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, 8 * cnt));
+    CU(cudaMemcpyAsync(d, times, 8 * cnt, cudaMemcpyHostToDevice, h->stream));
+    k_set_contact_times<<<(count * kNumEE + 127) / 128, 128, 0, h->stream>>>(h->d_inst, first, count, d, nct);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    return BGG_OK;
+}
+
+int bgg_upload_inputs(bgg_handle* h, const double* state, const double* t0, const double* ee_start) {
+    if (!h || !state || !t0 || !ee_start || !h->batch) return fail(BGG_EINVAL, "null argument / no batch");
+    CU(cudaSetDevice(h->device));
+    const size_t B = h->batch;
+    std::memcpy(h->h_state, state, 8 * kNxMan * B);
+    std::memcpy(h->h_t0, t0, 8 * B);
+    std::memcpy(h->h_ee, ee_start, 8 * 12 * B);
+    CU(cudaMemcpyAsync(h->d_state, h->h_state, 8 * kNxMan * B, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_t0, h->h_t0, 8 * B, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_ee, h->h_ee, 8 * 12 * B, cudaMemcpyHostToDevice, h->stream));
+    return BGG_OK;
+}
+
+int bgg_solve_resident(bgg_handle* h) {
+    if (!h || !h->batch) return fail(BGG_EINVAL, "no batch");
+    if (!h->costs_set) return fail(BGG_ESTATE, "bgg_set_costs has not been called");
+    CU(cudaSetDevice(h->device));
+    const int B = h->batch;
+    if (h->profiling) cudaEventRecord(h->ev[0], h->stream);
+    launch_prepare(h->P, h->d_inst, h->d_state, h->d_t0, h->d_ee, h->L, h->d_ws, B, h->stream);
+    if (h->profiling) cudaEventRecord(h->ev[1], h->stream);
+    launch_condense(h->P, h->L, h->d_ws, B, h->stream);
+    if (h->profiling) cudaEventRecord(h->ev[2], h->stream);
+    launch_ipm(h->P, h->L, h->d_ws, B, h->stream);
+    if (h->profiling) cudaEventRecord(h->ev[3], h->stream);
+    launch_finish(h->P, h->d_inst, h->L, h->d_ws, B, h->stream);
+    if (h->profiling) cudaEventRecord(h->ev[4], h->stream);
+    h->launches += 4;
+    CU(cudaGetLastError());
+    return BGG_OK;
+}
+
+int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double* alpha, double* cost) {
+    if (!h || !h->batch) return fail(BGG_EINVAL, "no batch");
+    CU(cudaSetDevice(h->device));
+    const int B = h->batch;
+    k_gather_headers<<<(B + 127) / 128, 128, 0, h->stream>>>(h->L, h->d_ws, h->d_hdr, B);
+    h->launches += 1;
+    CU(cudaMemcpyAsync(h->h_hdr, h->d_hdr, sizeof(WsHeader) * static_cast<size_t>(B), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < B; ++b) {
+        const WsHeader& w = h->h_hdr[b];
+        if (status) status[b] = w.error ? BGG_OTHER : w.status;
+        if (iters) iters[b] = w.iters;
+        if (alpha) alpha[b] = w.alpha;
+        if (cost) cost[b] = w.cost;
+    }
+    if (h->profiling)
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&h->last_ms[i], h->ev[i], h->ev[i + 1]);
+    return BGG_OK;
+}
+
+int bgg_solve_batch(bgg_handle* h, const double* state, const double* t0, const double* ee_start, int32_t* status,
+                    int32_t* iters, double* alpha, double* cost) {
+    int rc = bgg_upload_inputs(h, state, t0, ee_start);
+    if (rc) return rc;
+    rc = bgg_solve_resident(h);
+    if (rc) return rc;
+    return bgg_download_results(h, status, iters, alpha, cost);
+}
+
+int bgg_synchronize(bgg_handle* h) {
+    if (!h) return fail(BGG_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return BGG_OK;
+}
+
+int bgg_set_profiling(bgg_handle* h, int enable) {
+    if (!h) return fail(BGG_EINVAL, "null handle");
+    h->profiling = enable != 0;
+    return BGG_OK;
+}
+
+int bgg_last_kernel_ms(bgg_handle* h, float ms[4]) {
+    if (!h || !ms) return fail(BGG_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->profiling)
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&h->last_ms[i], h->ev[i], h->ev[i + 1]);
+    for (int i = 0; i < 4; ++i) ms[i] = h->last_ms[i];
+    return BGG_OK;
+}
+
+int bgg_kernel_launch_count(bgg_handle* h, int64_t* launches) {
+    if (!h || !launches) return fail(BGG_EINVAL, "null argument");
+    *launches = h->launches;
+    return BGG_OK;
+}
+
+static int fetch(bgg_handle* h, void* dst, const void* dsrc, size_t bytes) {
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(dst, dsrc, bytes, cudaMemcpyDeviceToHost));
+    return BGG_OK;
+}
+
+int bgg_get_sizes(bgg_handle* h, int b, bgg_sizes* out) {
+    if (!h || !out || b < 0 || b >= h->batch) return fail(BGG_EINVAL, "bad instance");
+    WsHeader w;
+    const int rc = fetch(h, &w, h->d_ws + static_cast<size_t>(b) * h->L.stride + h->L.hdr, sizeof w);
+    if (rc) return rc;
+    out->n = w.n; out->nu = w.nu; out->nf = w.nf; out->np = w.np; out->n_samples = w.n_samples; out->n_eebox = w.n_eebox;
+    out->n_eq = w.n_eq; out->n_td = w.n_td; out->m_ineq = w.m_ineq; out->status = w.status; out->iters = w.iters;
+    out->ls_iters = w.ls_iters; out->error = w.error;
+    for (int e = 0; e < kNumEE; ++e) {
+        out->nfv[e] = w.nfv[e]; out->npv[e] = w.npv[e]; out->fbase[e] = w.fbase[e]; out->pbase[e] = w.pbase[e];
+    }
+    out->t0 = w.t0; out->alpha = w.alpha; out->cost = w.cost; out->prim_res = w.prim_res; out->dual_res = w.dual_res;
+    out->gap = w.gap; out->eq_violation = w.eq_violation; out->step_norm = w.step_norm; out->merit = w.merit;
+    out->merit_dd = w.merit_dd; out->ee_box[0] = w.ee_box[0]; out->ee_box[1] = w.ee_box[1];
+    return BGG_OK;
+}
+
+int bgg_get_dynamics(bgg_handle* h, int first, int count, double* Ad, double* Bd, double* cd, int nu_stride) {
+    if (!h || !Ad || !Bd || !cd || first < 0 || count <= 0 || first + count > h->batch) return fail(BGG_EINVAL, "bad range");
+    CU(cudaSetDevice(h->device));
+    const size_t N = h->P.N;
+    double *dA, *dB, *dc;
+    CU(cudaMalloc(&dA, 8 * count * N * 144));
+    CU(cudaMalloc(&dB, 8 * count * N * kNx * nu_stride));
+    CU(cudaMalloc(&dc, 8 * count * N * kNx));
+    launch_export_dynamics(h->P, h->L, h->d_ws + static_cast<size_t>(first) * h->L.stride, count, dA, dB, dc, nu_stride, h->stream);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(Ad, dA, 8 * count * N * 144, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(Bd, dB, 8 * count * N * kNx * nu_stride, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cd, dc, 8 * count * N * kNx, cudaMemcpyDeviceToHost));
+    cudaFree(dA);
+    cudaFree(dB);
+    cudaFree(dc);
+    return BGG_OK;
+}
+
+int bgg_get_condensed(bgg_handle* h, int b, double* H, double* g, double* phipos, double* xoff) {
+    if (!h || b < 0 || b >= h->batch) return fail(BGG_EINVAL, "bad instance");
+    bgg_sizes sz;
+    int rc = bgg_get_sizes(h, b, &sz);
+    if (rc) return rc;
+    const char* ws = h->d_ws + static_cast<size_t>(b) * h->L.stride;
+    const int nu = sz.nu, N = h->P.N;
+    if (H && (rc = fetch(h, H, ws + h->L.H, 8 * static_cast<size_t>(nu) * nu))) return rc;
+    if (g && (rc = fetch(h, g, ws + h->L.g, 8 * static_cast<size_t>(nu)))) return rc;
+    if (phipos) {
+        std::vector<double> tmp(static_cast<size_t>(2 * (N - 3)) * h->L.max_nu);
+        if ((rc = fetch(h, tmp.data(), ws + h->L.phipos, 8 * tmp.size()))) return rc;
+        for (int r = 0; r < 2 * (N - 3); ++r)
+            for (int i = 0; i < nu; ++i) phipos[static_cast<size_t>(r) * nu + i] = tmp[static_cast<size_t>(r) * h->L.max_nu + i];
+    }
+    if (xoff && (rc = fetch(h, xoff, ws + h->L.xoff, 8 * static_cast<size_t>(kNx) * (N + 1)))) return rc;
+    return BGG_OK;
+}
+
+int bgg_get_solution(bgg_handle* h, int b, double* qp_sol, double* z, double* lam, double* slack, double* nu_eq) {
+    if (!h || b < 0 || b >= h->batch) return fail(BGG_EINVAL, "bad instance");
+    bgg_sizes sz;
+    int rc = bgg_get_sizes(h, b, &sz);
+    if (rc) return rc;
+    const char* ws = h->d_ws + static_cast<size_t>(b) * h->L.stride;
+    if (qp_sol && (rc = fetch(h, qp_sol, ws + h->L.zqp, 8 * static_cast<size_t>(sz.n)))) return rc;
+    if (z && (rc = fetch(h, z, ws + h->L.zprev, 8 * static_cast<size_t>(sz.n)))) return rc;
+    if (lam && (rc = fetch(h, lam, ws + h->L.lam, 8 * static_cast<size_t>(sz.m_ineq)))) return rc;
+    if (slack && (rc = fetch(h, slack, ws + h->L.slack, 8 * static_cast<size_t>(sz.m_ineq)))) return rc;
+    if (nu_eq && (rc = fetch(h, nu_eq, ws + h->L.nueq, 8 * static_cast<size_t>(sz.n_eq)))) return rc;
+    return BGG_OK;
+}
+
+size_t bgg_instance_bytes(void) { return sizeof(Instance); }
+
+int bgg_get_instance(bgg_handle* h, int b, void* out) {
+    if (!h || !out || b < 0 || b >= h->batch) return fail(BGG_EINVAL, "bad instance");
+    return fetch(h, out, h->d_inst + b, sizeof(Instance));
+}
+
+int bgg_set_instance(bgg_handle* h, int b, const void* in) {
+    if (!h || !in || b < 0 || b >= h->batch) return fail(BGG_EINVAL, "bad instance");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(h->d_inst + b, in, sizeof(Instance), cudaMemcpyHostToDevice));
+    return BGG_OK;
+}
+
+int bgg_get_states(bgg_handle* h, int b, double* states) {
+    if (!h || !states || b < 0 || b >= h->batch) return fail(BGG_EINVAL, "bad instance");
+    return fetch(h, states, reinterpret_cast<const char*>(h->d_inst + b) + offsetof(Instance, states),
+                 8 * static_cast<size_t>(kNxMan) * (h->P.N + 1));
+}
+
+int bgg_eval_splines(bgg_handle* h, int b, const double* times, int T, double* force, double* position) {
+    if (!h || !times || !force || !position || T <= 0 || b < 0 || b >= h->batch) return fail(BGG_EINVAL, "bad argument");
+    CU(cudaSetDevice(h->device));
+    double *dt, *df, *dp;
+    CU(cudaMalloc(&dt, 8 * T));
+    CU(cudaMalloc(&df, 8 * T * 12));
+    CU(cudaMalloc(&dp, 8 * T * 12));
+    CU(cudaMemcpyAsync(dt, times, 8 * T, cudaMemcpyHostToDevice, h->stream));
+    k_eval_splines<<<(T * kNumEE + 127) / 128, 128, 0, h->stream>>>(h->d_inst, b, dt, T, df, dp);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(force, df, 8 * T * 12, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(position, dp, 8 * T * 12, cudaMemcpyDeviceToHost));
+    cudaFree(dt);
+    cudaFree(df);
+    cudaFree(dp);
+    return BGG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,583 @@
+// bilevel-gait-gen_b200 -- kernel 4: the QP solve, one CTA per MPC instance, a primal-dual interior-point method
+// (Mehrotra predictor-corrector) on the condensed QP
+//      min 1/2 u'Hu + g'u   s.t.  C u <= d  (force box, friction pyramid, foot box),   E u = e  (touch-down, foot start)
+// The reference's live solver is Clarabel, an interior-point method run to 1e-8 (mpc.h:264, clarabel_interface.cpp:
+// 18-27,72-155); an ADMM at OSQP tolerances leaves this ill-conditioned QP 1e-2 away from the optimum,
+// so the kernel follows the live path.  Per iteration: K = H + C'WC + E'E/delta is assembled from the *structured*
+// rows (never a sparse matrix), factorised by an in-shared-memory packed Cholesky, and used for the predictor and the
+// corrector solve.  Equality rows are handled by the proximal (static-regularisation) term E'E/delta with their
+// multipliers accumulated, as Clarabel does with its static KKT regularisation.
+//
+// Inequality rows, internal order (m = 6 ns + 2 ne):
+//   6 j + 0 :  f_z(tau_j) <= force_bound          6 j + 1 : -f_z(tau_j) <= 0               (mpc.cpp:352-414)
+//   6 j + 2..5 : (+-e_x - mu e_z).f <= 0, (+-e_y - mu e_z).f <= 0                          (mpc.cpp:153-209)
+//   6 ns + 2 e + 0 : -p_c(k) + w.u_pos <=  hip_c + box_c/2     e = ((k-4)*4 + foot)*2 + c   (mpc_single_rigid_body.cpp:381-443)
+//   6 ns + 2 e + 1 :  p_c(k) - w.u_pos <= -(hip_c - box_c/2)
+#include "bgg_kernels.cuh"
+
+namespace bgg {
+
+namespace {
+
+struct Smem {
+    double* K;       // packed lower triangle nu(nu+1)/2
+    double *u, *du, *rd, *rhs, *g, *tmpn;            // nu
+    double *s, *lam, *ds, *dl, *rp, *wv, *d;         // m
+    double *tkc, *ckc;                               // 2(N-3)
+    double *nueq, *re, *dnu;                         // kMaxEq
+    double* red;                                     // 40
+};
+
+__device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
+
+}  // namespace
+
+size_t ipm_smem_bytes(const WsLayout& L) {
+    const size_t nu = L.max_nu, m = L.max_rows, kc = 2 * (L.N - 3);
+    return 8 * (nu * (nu + 1) / 2 + 6 * nu + 7 * m + 2 * kc + 3 * kMaxEq + 40) + 64;
+}
+
+__global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base) {
+    const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+    const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
+    char* ws = ws_base + static_cast<size_t>(b) * L.stride;
+    WsHeader* Hd = reinterpret_cast<WsHeader*>(ws + L.hdr);
+    if (Hd->error) {
+        if (tid == 0) Hd->status = kOther;
+        return;
+    }
+    const NodeLin* nodes = reinterpret_cast<const NodeLin*>(ws + L.nodes);
+    const Sample* samples = reinterpret_cast<const Sample*>(ws + L.samples);
+    const EqRow* eqs = reinterpret_cast<const EqRow*>(ws + L.eq);
+    const double* Hg = reinterpret_cast<const double*>(ws + L.H);       // full symmetric nu x nu
+    const double* gg = reinterpret_cast<const double*>(ws + L.g);
+    const double* phipos = reinterpret_cast<const double*>(ws + L.phipos);
+    const double* xoff = reinterpret_cast<const double*>(ws + L.xoff);
+
+    const int N = P.N, nu = Hd->nu, nf = Hd->nf, ns = Hd->n_samples, ne = Hd->n_eebox, neq = Hd->n_eq;
+    const int m = 6 * ns + 2 * ne, nkc = 2 * (N - 3), npk = nu * (nu + 1) / 2;
+    const double mu_f = P.friction_coef, delta = P.ipm_eq_delta, inv_delta = 1.0 / P.ipm_eq_delta;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem S;
+    {
+        double* p = reinterpret_cast<double*>(smem_raw);
+        S.K = p; p += L.max_nu * (L.max_nu + 1) / 2;
+        S.u = p; p += L.max_nu; S.du = p; p += L.max_nu; S.rd = p; p += L.max_nu;
+        S.rhs = p; p += L.max_nu; S.g = p; p += L.max_nu; S.tmpn = p; p += L.max_nu;
+        S.s = p; p += L.max_rows; S.lam = p; p += L.max_rows; S.ds = p; p += L.max_rows; S.dl = p; p += L.max_rows;
+        S.rp = p; p += L.max_rows; S.wv = p; p += L.max_rows; S.d = p; p += L.max_rows;
+        S.tkc = p; p += nkc; S.ckc = p; p += nkc;
+        S.nueq = p; p += kMaxEq; S.re = p; p += kMaxEq; S.dnu = p; p += kMaxEq;
+        S.red = p;
+    }
+    __shared__ int s_fbase[kNumEE], s_pbase[kNumEE], s_nfv[kNumEE], s_npv[kNumEE];
+    __shared__ int s_flag;
+    if (tid < kNumEE) {
+        s_fbase[tid] = Hd->fbase[tid];
+        s_pbase[tid] = Hd->pbase[tid];
+        s_nfv[tid] = Hd->nfv[tid];
+        s_npv[tid] = Hd->npv[tid];
+    }
+    for (int i = tid; i < nu; i += nth) S.g[i] = gg[i];
+
+    // ---- right-hand sides d (and the active mask: wv < 0 marks an inactive row while setting up)
+    const double box0 = Hd->ee_box[0] / 2, box1 = Hd->ee_box[1] / 2;
+    for (int j = tid; j < ns; j += nth) {
+        const bool act = samples[j].active != 0;
+        double* dj = S.d + 6 * j;
+        dj[0] = P.force_bound;
+        dj[1] = 0.0;
+        dj[2] = dj[3] = dj[4] = dj[5] = 0.0;
+        for (int r = 0; r < 6; ++r) S.wv[6 * j + r] = act ? 1.0 : 0.0;
+    }
+    for (int e = tid; e < ne; e += nth) {
+        const int c = e & 1, foot = (e >> 1) & 3, kk = e >> 3;   // node k = kk + 4
+        const double bx = c ? box1 : box0;
+        const double off = xoff[(kk + kEENodeStart) * kNx + c];
+        S.d[6 * ns + 2 * e + 0] = (bx + P.hip_xy[foot][c]) + off;
+        S.d[6 * ns + 2 * e + 1] = -(-bx + P.hip_xy[foot][c]) - off;
+        S.wv[6 * ns + 2 * e + 0] = 1.0;
+        S.wv[6 * ns + 2 * e + 1] = 1.0;
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------------------------------------ operators
+    // out[0..m) = C v   (v: nu-vector in shared memory)
+    auto apply_C = [&](const double* v, double* out) {
+        for (int q = wid; q < nkc; q += nwarp) {     // dense position rows: one warp per (node, coord)
+            const double* row = phipos + static_cast<size_t>(q) * L.max_nu;
+            double s = 0;
+            for (int i = lane; i < nf; i += 32) s += row[i] * v[i];
+            s = warp_sum(s);
+            if (lane == 0) S.tkc[q] = s;
+        }
+        for (int j = tid; j < ns; j += nth) {
+            const Sample& sp = samples[j];
+            double fv[3];
+            for (int c = 0; c < 3; ++c) {
+                const double* vv = v + s_fbase[sp.ee] + c * s_nfv[sp.ee] + sp.off;
+                double s = 0;
+                for (int i = 0; i < sp.cnt; ++i) s += sp.w[i] * vv[i];
+                fv[c] = s;
+            }
+            double* o = out + 6 * j;
+            o[0] = fv[2];
+            o[1] = -fv[2];
+            o[2] = fv[0] - mu_f * fv[2];
+            o[3] = -fv[0] - mu_f * fv[2];
+            o[4] = fv[1] - mu_f * fv[2];
+            o[5] = -fv[1] - mu_f * fv[2];
+        }
+        __syncthreads();
+        for (int e = tid; e < ne; e += nth) {
+            const int c = e & 1, foot = (e >> 1) & 3, kk = e >> 3;
+            const NodeLin& nl = nodes[kk + kEENodeStart];
+            const double* vv = v + nf + s_pbase[foot] + c * s_npv[foot] + nl.poff[foot];
+            double s = -S.tkc[kk * 2 + c];
+            for (int i = 0; i < nl.pcnt[foot]; ++i) s += nl.pw[foot][i] * vv[i];
+            out[6 * ns + 2 * e] = s;
+            out[6 * ns + 2 * e + 1] = -s;
+        }
+        __syncthreads();
+    };
+    // out[0..nu) += C' y   (y: m-vector; rows with wv == 0 contribute nothing)
+    auto add_Ct = [&](const double* y, double* out) {
+        // foot-box rows: per (node, coord) coefficient on the dense position row, gathered per column
+        for (int q = tid; q < nkc; q += nth) {
+            const int kk = q >> 1, c = q & 1;
+            double s = 0;
+            for (int foot = 0; foot < kNumEE; ++foot) {
+                const int e = (kk * 4 + foot) * 2 + c;
+                s += y[6 * ns + 2 * e] - y[6 * ns + 2 * e + 1];
+            }
+            S.ckc[q] = -s;
+        }
+        __syncthreads();
+        for (int i = tid; i < nf; i += nth) {
+            double s = 0;
+            for (int q = 0; q < nkc; ++q) s += S.ckc[q] * phipos[static_cast<size_t>(q) * L.max_nu + i];
+            out[i] += s;
+        }
+        __syncthreads();
+        // sparse parts, one thread per destination column block to stay free of atomics:
+        // force columns of foot e / coord c are touched only by that foot's samples
+        if (tid < kNumEE * 3) {
+            const int e = tid / 3, c = tid % 3;
+            double* o = out + s_fbase[e] + c * s_nfv[e];
+            for (int j = 0; j < ns; ++j) {
+                const Sample& sp = samples[j];
+                if (sp.ee != e || !sp.active) continue;
+                const double* yy = y + 6 * j;
+                double coef;
+                if (c == 2) coef = (yy[0] - yy[1]) - mu_f * (yy[2] + yy[3] + yy[4] + yy[5]);
+                else if (c == 0) coef = yy[2] - yy[3];
+                else coef = yy[4] - yy[5];
+                for (int i = 0; i < sp.cnt; ++i) o[sp.off + i] += coef * sp.w[i];
+            }
+        } else if (tid >= 32 && tid < 32 + kNumEE * 2) {
+            const int q = tid - 32, foot = q >> 1, c = q & 1;
+            double* o = out + nf + s_pbase[foot] + c * s_npv[foot];
+            for (int kk = 0; kk < N - 3; ++kk) {
+                const NodeLin& nl = nodes[kk + kEENodeStart];
+                const int e = (kk * 4 + foot) * 2 + c;
+                const double coef = y[6 * ns + 2 * e] - y[6 * ns + 2 * e + 1];
+                for (int i = 0; i < nl.pcnt[foot]; ++i) o[nl.poff[foot] + i] += coef * nl.pw[foot][i];
+            }
+        }
+        __syncthreads();
+    };
+    // out[0..nu) = H v, H full symmetric in HBM/L2, read column-wise (coalesced across threads)
+    auto apply_H = [&](const double* v, double* out) {
+        for (int i = tid; i < nu; i += nth) {
+            double s = 0;
+            for (int j = 0; j < nu; ++j) s += Hg[static_cast<size_t>(j) * nu + i] * v[j];
+            out[i] = s;
+        }
+        __syncthreads();
+    };
+    // re = E v - e (or E v when rhs == false) ; out += E' y
+    auto apply_E = [&](const double* v, double* out, bool with_rhs) {
+        if (tid < neq) {
+            const EqRow& q = eqs[tid];
+            double s = with_rhs ? -q.rhs : 0.0;
+            for (int i = 0; i < q.cnt; ++i) s += q.w[i] * v[q.col[i]];
+            out[tid] = s;
+        }
+        __syncthreads();
+    };
+    auto add_Et = [&](const double* y, double* out, double scale) {
+        if (tid == 0)
+            for (int r = 0; r < neq; ++r) {
+                const EqRow& q = eqs[r];
+                for (int i = 0; i < q.cnt; ++i) out[q.col[i]] += scale * y[r] * q.w[i];
+            }
+        __syncthreads();
+    };
+
+    // K = H + C' diag(wv) C + E'E/delta (packed lower triangle in shared memory), then in-place Cholesky.
+    auto build_and_factor = [&]() -> bool {
+        for (int p = tid; p < nu * nu; p += nth) {
+            const int i = p / nu, j = p % nu;
+            if (j <= i) S.K[pk(i, j)] = Hg[p];
+        }
+        // (node, coord) weights of the dense foot-box rows
+        for (int q = tid; q < nkc; q += nth) {
+            const int kk = q >> 1, c = q & 1;
+            double s = 0;
+            for (int foot = 0; foot < kNumEE; ++foot) {
+                const int e = (kk * 4 + foot) * 2 + c;
+                s += S.wv[6 * ns + 2 * e] + S.wv[6 * ns + 2 * e + 1];
+            }
+            S.ckc[q] = s;
+        }
+        __syncthreads();
+        // force-force block: sum_q ckc[q] phi_q phi_q'   (16 x 16 thread tiling)
+        {
+            const int ty = tid >> 4, tx = tid & 15;
+            for (int i = ty; i < nf; i += 16)
+                for (int j = tx; j <= i; j += 16) {
+                    double s = 0;
+                    for (int q = 0; q < nkc; ++q) {
+                        const double* row = phipos + static_cast<size_t>(q) * L.max_nu;
+                        s += S.ckc[q] * row[i] * row[j];
+                    }
+                    S.K[pk(i, j)] += s;
+                }
+        }
+        __syncthreads();
+        // position-force and position-position blocks of the foot-box rows: one thread per (foot, coord)
+        if (tid < kNumEE * 2) {
+            const int foot = tid >> 1, c = tid & 1;
+            const int pb = nf + s_pbase[foot] + c * s_npv[foot];
+            for (int kk = 0; kk < N - 3; ++kk) {
+                const NodeLin& nl = nodes[kk + kEENodeStart];
+                const int e = (kk * 4 + foot) * 2 + c;
+                const double om = S.wv[6 * ns + 2 * e] + S.wv[6 * ns + 2 * e + 1];
+                const double* row = phipos + static_cast<size_t>(kk * 2 + c) * L.max_nu;
+                for (int a = 0; a < nl.pcnt[foot]; ++a) {
+                    const int ca = pb + nl.poff[foot] + a;
+                    const double wa = om * nl.pw[foot][a];
+                    for (int j = 0; j < nf; ++j) S.K[pk(ca, j)] -= wa * row[j];
+                    for (int a2 = 0; a2 <= a; ++a2) S.K[pk(ca, pb + nl.poff[foot] + a2)] += wa * nl.pw[foot][a2];
+                }
+            }
+        }
+        // force samples: one thread per (foot, coord pair) owns a disjoint set of K entries
+        if (tid >= 32 && tid < 32 + kNumEE * 6) {
+            const int q = tid - 32, e = q / 6, cp = q % 6;
+            const int c1 = (cp < 3) ? cp : (cp == 3 ? 1 : 2);          // (0,0) (1,1) (2,2) (1,0) (2,0) (2,1)
+            const int c2 = (cp < 3) ? cp : (cp == 5 ? 1 : 0);
+            for (int j = 0; j < ns; ++j) {
+                const Sample& sp = samples[j];
+                if (sp.ee != e || !sp.active) continue;
+                const double* w6 = S.wv + 6 * j;
+                // M = sum_r w_r c_r c_r' over the rows' coefficient 3-vectors
+                double Mcc;
+                if (c1 == 2 && c2 == 2) Mcc = (w6[0] + w6[1]) + mu_f * mu_f * (w6[2] + w6[3] + w6[4] + w6[5]);
+                else if (c1 == 0 && c2 == 0) Mcc = w6[2] + w6[3];
+                else if (c1 == 1 && c2 == 1) Mcc = w6[4] + w6[5];
+                else if (c1 == 1 && c2 == 0) Mcc = 0.0;
+                else if (c1 == 2 && c2 == 0) Mcc = -mu_f * (w6[2] - w6[3]);
+                else Mcc = -mu_f * (w6[4] - w6[5]);
+                if (Mcc == 0.0) continue;
+                const int r0 = s_fbase[e] + c1 * s_nfv[e] + sp.off, q0 = s_fbase[e] + c2 * s_nfv[e] + sp.off;
+                for (int a = 0; a < sp.cnt; ++a)
+                    for (int a2 = 0; a2 < sp.cnt; ++a2) {
+                        if (c1 == c2 && a2 > a) continue;
+                        S.K[pk(r0 + a, q0 + a2)] += Mcc * sp.w[a] * sp.w[a2];
+                    }
+            }
+        }
+        __syncthreads();
+        if (tid == 0)
+            for (int r = 0; r < neq; ++r) {
+                const EqRow& q = eqs[r];
+                for (int a = 0; a < q.cnt; ++a)
+                    for (int a2 = 0; a2 <= a; ++a2) {
+                        const int ia = q.col[a], ib = q.col[a2];
+                        S.K[ia >= ib ? pk(ia, ib) : pk(ib, ia)] += inv_delta * q.w[a] * q.w[a2];
+                    }
+            }
+        __syncthreads();
+        // right-looking Cholesky, 16 x 16 thread tiling of the trailing update
+        if (tid == 0) s_flag = 0;
+        const int ty = tid >> 4, tx = tid & 15;
+        for (int j = 0; j < nu; ++j) {
+            __syncthreads();
+            const double djj = S.K[pk(j, j)];
+            if (!(djj > 0.0)) {
+                if (tid == 0) s_flag = 1;
+                break;
+            }
+            const double inv = 1.0 / sqrt(djj);
+            __syncthreads();
+            for (int i = j + tid; i < nu; i += nth) S.K[pk(i, j)] = (i == j) ? sqrt(djj) : S.K[pk(i, j)] * inv;
+            __syncthreads();
+            for (int i = j + 1 + ty; i < nu; i += 16) {
+                const double lij = S.K[pk(i, j)];
+                const int rb = i * (i + 1) / 2;
+                for (int l = j + 1 + tx; l <= i; l += 16) S.K[rb + l] -= lij * S.K[pk(l, j)];
+            }
+        }
+        __syncthreads();
+        return s_flag == 0;
+    };
+    // solve K x = rhs in place (x overwrites v) with the packed factor: one warp, shuffle reductions
+    auto chol_solve = [&](double* v) {
+        __syncthreads();
+        if (wid == 0) {
+            for (int i = 0; i < nu; ++i) {
+                const double* Li = S.K + i * (i + 1) / 2;
+                double s = 0;
+                for (int j = lane; j < i; j += 32) s += Li[j] * v[j];
+                s = warp_sum(s);
+                if (lane == 0) v[i] = (v[i] - s) / Li[i];
+                __syncwarp();
+            }
+            for (int i = nu - 1; i >= 0; --i) {
+                double s = 0;
+                for (int j = i + 1 + lane; j < nu; j += 32) s += S.K[pk(j, i)] * v[j];
+                s = warp_sum(s);
+                if (lane == 0) v[i] = (v[i] - s) / S.K[pk(i, i)];
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    };
+
+    // ------------------------------------------------------------------------------------------------ start point
+    // u0 = argmin of the equality/inequality-penalised quadratic: (H + C'C + E'E/delta) u = -g + C'd + E'e/delta
+    bool ok = build_and_factor();
+    for (int i = tid; i < nu; i += nth) S.rhs[i] = -S.g[i];
+    for (int i = tid; i < m; i += nth) S.rp[i] = (S.wv[i] != 0.0) ? S.d[i] : 0.0;
+    if (tid < neq) S.re[tid] = eqs[tid].rhs;
+    __syncthreads();
+    add_Ct(S.rp, S.rhs);
+    add_Et(S.re, S.rhs, inv_delta);
+    for (int i = tid; i < nu; i += nth) S.u[i] = S.rhs[i];
+    chol_solve(S.u);
+    apply_C(S.u, S.ds);
+    double mn = 1e300;
+    for (int i = tid; i < m; i += nth)
+        if (S.wv[i] != 0.0) {
+            S.s[i] = S.d[i] - S.ds[i];
+            mn = fmin(mn, S.s[i]);
+        }
+    mn = block_reduce<kMin>(mn, S.red);
+    const double shift = fmax(0.0, -1.5 * mn);
+    double sl = 0, ss = 0, xi = 0;
+    for (int i = tid; i < m; i += nth) {
+        if (S.wv[i] != 0.0) {
+            const double v = fmax(S.s[i] + shift, 1e-2);
+            S.s[i] = v;
+            S.lam[i] = v;
+            xi += v * v;
+            sl += v;
+        } else {
+            S.s[i] = 1.0;
+            S.lam[i] = 0.0;
+        }
+    }
+    xi = block_reduce<kSum>(xi, S.red);
+    sl = block_reduce<kSum>(sl, S.red);
+    for (int i = tid; i < m; i += nth)
+        if (S.wv[i] != 0.0) {
+            S.s[i] += 0.5 * xi / sl;
+            ss += S.s[i];
+        }
+    ss = block_reduce<kSum>(ss, S.red);
+    int m_act = 0;
+    for (int i = tid; i < m; i += nth)
+        if (S.wv[i] != 0.0) {
+            S.lam[i] += 0.5 * xi / ss;
+            m_act++;
+        }
+    m_act = static_cast<int>(block_reduce<kSum>(static_cast<double>(m_act), S.red) + 0.5);
+    if (tid < kMaxEq) S.nueq[tid] = 0.0;
+    __syncthreads();
+
+    double nrm_q = 1.0, nrm_d = 1.0;
+    for (int r = 0; r < kNx; ++r) nrm_q = fmax(nrm_q, fmax(fabs(P.w[r]), fabs(P.Phi_w[r])));
+    {
+        double v = 0;
+        for (int i = tid; i < m; i += nth)
+            if (S.wv[i] != 0.0) v = fmax(v, fabs(S.d[i]));
+        nrm_d = fmax(1.0, block_reduce<kMax>(v, S.red));
+    }
+
+    // ------------------------------------------------------------------------------------------------ main loop
+    int it = 0, status = kMaxIter;
+    double n_rd = 0, n_rp = 0, n_re = 0, mu = 0, gap_scale = 1;
+    for (it = 0; it <= P.ipm_max_iter; ++it) {
+        // residuals: rd = H u + g + C'lam + E'nu ; rp = C u + s - d ; re = E u - e
+        apply_H(S.u, S.rd);
+        double pobj = 0;
+        for (int i = tid; i < nu; i += nth) {
+            pobj += S.u[i] * (0.5 * S.rd[i] + S.g[i]);
+            S.rd[i] += S.g[i];
+        }
+        pobj = block_reduce<kSum>(pobj, S.red);
+        add_Ct(S.lam, S.rd);
+        add_Et(S.nueq, S.rd, 1.0);
+        apply_C(S.u, S.rp);
+        apply_E(S.u, S.re, true);
+        double a = 0, c = 0, dsum = 0;
+        for (int i = tid; i < nu; i += nth) a = fmax(a, fabs(S.rd[i]));
+        for (int i = tid; i < m; i += nth) {
+            if (S.lam[i] > 0.0) {   // active row (inactive rows keep lam == 0 exactly)
+                S.rp[i] = S.rp[i] + S.s[i] - S.d[i];
+                c = fmax(c, fabs(S.rp[i]));
+                dsum += S.s[i] * S.lam[i];
+            } else {
+                S.rp[i] = 0.0;
+            }
+        }
+        n_rd = block_reduce<kMax>(a, S.red);
+        n_rp = block_reduce<kMax>(c, S.red);
+        dsum = block_reduce<kSum>(dsum, S.red);
+        mu = dsum / m_act;
+        n_re = 0;
+        for (int r = 0; r < neq; ++r) n_re = fmax(n_re, fabs(S.re[r]));
+        gap_scale = fmax(1.0, fabs(pobj));
+        const bool nan_seen = !(n_rd == n_rd) || !(n_rp == n_rp) || !(mu == mu);
+        if (nan_seen || !ok) {
+            status = kOther;
+            break;
+        }
+        if (n_rd <= P.ipm_tol_feas * nrm_q && n_rp <= P.ipm_tol_feas * nrm_d && n_re <= P.ipm_tol_feas * nrm_d &&
+            dsum <= P.ipm_tol_gap * gap_scale) {
+            status = kSolved;
+            break;
+        }
+        if (it == P.ipm_max_iter) break;
+
+        // scaling W = lam / s (inactive rows keep 0), factorisation
+        for (int i = tid; i < m; i += nth) S.wv[i] = (S.lam[i] > 0.0) ? S.lam[i] / S.s[i] : 0.0;
+        __syncthreads();
+        ok = build_and_factor();
+        if (!ok) {
+            status = kOther;
+            break;
+        }
+
+        // one Newton solve for complementarity target rc (dl holds -rc on entry, see callers):
+        //   K du = -rd - C'((-rc + lam rp)/s) - E' re / delta ; ds = -rp - C du ; dl = (-rc - lam ds)/s
+        auto newton = [&](bool corrector, double sig_mu) {
+            for (int i = tid; i < m; i += nth) {
+                if (S.wv[i] == 0.0) {
+                    S.dl[i] = 0.0;
+                    continue;
+                }
+                double rc = S.s[i] * S.lam[i];
+                if (corrector) rc += S.ds[i] * S.dl[i] - sig_mu;
+                S.dl[i] = rc;                                           // keep rc
+            }
+            __syncthreads();
+            for (int i = tid; i < m; i += nth)
+                S.ds[i] = (S.wv[i] != 0.0) ? -(-S.dl[i] + S.lam[i] * S.rp[i]) / S.s[i] : 0.0;
+            for (int i = tid; i < nu; i += nth) S.rhs[i] = -S.rd[i];
+            __syncthreads();
+            add_Ct(S.ds, S.rhs);
+            add_Et(S.re, S.rhs, -inv_delta);
+            for (int i = tid; i < nu; i += nth) S.du[i] = S.rhs[i];
+            chol_solve(S.du);
+            for (int rf = 0; rf < P.ipm_refine; ++rf) {
+                // iterative refinement against K = H + C'WC + E'E/delta applied matrix-free
+                apply_H(S.du, S.tmpn);
+                apply_C(S.du, S.ds);
+                for (int i = tid; i < m; i += nth) S.ds[i] *= S.wv[i];
+                __syncthreads();
+                add_Ct(S.ds, S.tmpn);
+                apply_E(S.du, S.dnu, false);
+                add_Et(S.dnu, S.tmpn, inv_delta);
+                for (int i = tid; i < nu; i += nth) S.tmpn[i] = S.rhs[i] - S.tmpn[i];
+                chol_solve(S.tmpn);
+                for (int i = tid; i < nu; i += nth) S.du[i] += S.tmpn[i];
+                __syncthreads();
+            }
+            apply_C(S.du, S.ds);
+            for (int i = tid; i < m; i += nth) {
+                if (S.wv[i] == 0.0) {
+                    S.ds[i] = 0.0;
+                    S.dl[i] = 0.0;
+                    continue;
+                }
+                const double dsi = -S.rp[i] - S.ds[i];
+                S.dl[i] = (-S.dl[i] - S.lam[i] * dsi) / S.s[i];
+                S.ds[i] = dsi;
+            }
+            apply_E(S.du, S.dnu, false);
+            if (tid < neq) S.dnu[tid] = (S.dnu[tid] + S.re[tid]) * inv_delta;
+            __syncthreads();
+        };
+        auto max_step = [&]() -> double {
+            double al = 1e300;
+            for (int i = tid; i < m; i += nth)
+                if (S.wv[i] != 0.0) {
+                    if (S.ds[i] < 0.0) al = fmin(al, -S.s[i] / S.ds[i]);
+                    if (S.dl[i] < 0.0) al = fmin(al, -S.lam[i] / S.dl[i]);
+                }
+            return block_reduce<kMin>(al, S.red);
+        };
+        newton(false, 0.0);
+        const double a_aff = fmin(1.0, max_step());
+        double mu_aff = 0;
+        for (int i = tid; i < m; i += nth)
+            if (S.wv[i] != 0.0) mu_aff += (S.s[i] + a_aff * S.ds[i]) * (S.lam[i] + a_aff * S.dl[i]);
+        mu_aff = block_reduce<kSum>(mu_aff, S.red) / m_act;
+        const double sr = mu_aff / mu;
+        const double sigma = sr * sr * sr;
+        newton(true, sigma * mu);
+        const double alpha = fmin(1.0, 0.99 * max_step());
+        for (int i = tid; i < nu; i += nth) S.u[i] += alpha * S.du[i];
+        for (int i = tid; i < m; i += nth)
+            if (S.wv[i] != 0.0) {
+                S.s[i] += alpha * S.ds[i];
+                S.lam[i] += alpha * S.dl[i];
+            }
+        if (tid < neq) S.nueq[tid] += alpha * S.dnu[tid];
+        __syncthreads();
+    }
+    if (status == kMaxIter) {
+        const double loose = 1e3;
+        if (n_rd <= loose * P.ipm_tol_feas * nrm_q && n_rp <= loose * P.ipm_tol_feas * nrm_d &&
+            n_re <= loose * P.ipm_tol_feas * nrm_d && mu * m_act <= loose * P.ipm_tol_gap * gap_scale)
+            status = kSolvedInacc;
+        else if (n_rp > 1e-4 * nrm_d || n_re > 1e-4 * nrm_d)
+            status = kPrimalInfeasible;
+    }
+
+    // ------------------------------------------------------------------------------------------------ outputs
+    double* uo = reinterpret_cast<double*>(ws + L.u);
+    double* lo = reinterpret_cast<double*>(ws + L.lam);
+    double* so = reinterpret_cast<double*>(ws + L.slack);
+    double* no = reinterpret_cast<double*>(ws + L.nueq);
+    for (int i = tid; i < nu; i += nth) uo[i] = S.u[i];
+    for (int i = tid; i < m; i += nth) {
+        lo[i] = S.lam[i];
+        so[i] = (S.lam[i] > 0.0 || S.s[i] != 1.0) ? S.s[i] : S.d[i];   // inactive rows: slack = d (row is 0 <= d)
+    }
+    if (tid < neq) no[tid] = S.nueq[tid];
+    if (tid == 0) {
+        Hd->status = status;
+        Hd->iters = it;
+        Hd->prim_res = fmax(n_rp, n_re);
+        Hd->dual_res = n_rd;
+        Hd->gap = mu * m_act;
+    }
+    (void)delta;
+    (void)npk;
+}
+
+void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, cudaStream_t stream) {
+    const size_t smem = ipm_smem_bytes(L);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(k_ipm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        configured = smem;
+    }
+    k_ipm<<<B, 256, smem, stream>>>(P, L, ws);
+}
+
+}  // namespace bgg

@@ -1,0 +1,58 @@
+// bilevel-gait-gen_b200 -- kernel launchers and small device helpers shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "bgg_spline.cuh"
+#include "bgg_types.cuh"
+#include "bgg_ws.cuh"
+
+namespace bgg {
+
+__device__ void quat_log3(const double q[4], double out[3]);
+__device__ void quat_exp3(const double v[3], double q[4]);
+__device__ void quat_first_order_normalize(double q[4]);
+
+// block-wide reductions (result broadcast to every thread); `scratch` holds >= 33 doubles of shared memory
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+enum RedOp { kSum, kMax, kMin };
+template <int OP>
+__device__ __forceinline__ double block_reduce(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = (OP == kSum) ? warp_sum(v) : (OP == kMax ? warp_max(v) : warp_min(v));
+    __syncthreads();   // protect scratch from the previous use
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double x = (lane < nw) ? scratch[lane] : ((OP == kSum) ? 0.0 : (OP == kMax ? -1e300 : 1e300));
+        x = (OP == kSum) ? warp_sum(x) : (OP == kMax ? warp_max(x) : warp_min(x));
+        if (lane == 0) scratch[32] = x;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+// kernel launchers (each is asynchronous on `stream`)
+void launch_prepare(const Params& P, Instance* inst, const double* state, const double* t0, const double* ee_start,
+                    const WsLayout& L, char* ws, int B, cudaStream_t stream);
+void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, cudaStream_t stream);
+void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, cudaStream_t stream);
+void launch_finish(const Params& P, Instance* inst, const WsLayout& L, char* ws, int B, cudaStream_t stream);
+size_t ipm_smem_bytes(const WsLayout& L);
+size_t condense_smem_bytes(const WsLayout& L);
+
+// parity taps
+void launch_export_dynamics(const Params& P, const WsLayout& L, char* ws, int B, double* Ad, double* Bd, double* cd,
+                            int nu_stride, cudaStream_t stream);
+
+}  // namespace bgg

@@ -1,0 +1,93 @@
+// bilevel-gait-gen_b200 -- per-instance solve workspace (HBM, L2-resident while a wave of instances is in flight).
+//
+// The reference rebuilds triplets -> Eigen::SparseMatrix -> solver every Solve() (mpc_single_rigid_body.cpp:49-107,
+// qp_data.cpp:169-178).  Here one solve's QP lives in a *structured* form that is a deterministic function of the
+// contact schedule: per-node discretised dynamics (Ad, cd and the spline weights that make up Bd), per-sample force
+// rows, per-node foot-box rows and the few equality rows.  The CSC matrix of the reference (bit-identical sparsity)
+// is produced from this form only when a caller asks for it (bgg_export_qp_csc).
+#pragma once
+#include "bgg_types.cuh"
+
+namespace bgg {
+
+struct WsHeader {
+    int32_t nfv[kNumEE], npv[kNumEE];     // force / xy-position variables per foot and coordinate
+    int32_t fbase[kNumEE], pbase[kNumEE]; // start of the foot's block inside the force / position variables
+    int32_t nf, np, nu, n;                // spline variable counts and total decision variables 12(N+1)+nu
+    int32_t n_samples;                    // force samples = 10 * (stance segments)
+    int32_t n_eebox;                      // (N-3)*4*2 two-sided foot-box rows
+    int32_t n_eq;                         // touch-down rows + foot-start rows
+    int32_t n_td;                         // touch-down rows (0..8)
+    int32_t m_ineq;                       // one-sided inequality rows: 6*n_samples + 2*n_eebox
+    int32_t td_flag[kNumEE];
+    int32_t error;                        // bit 0: too many knots, bit 1: nu > max_nu, bit 2: too many samples
+    int32_t status, iters, ls_iters, pad0;
+    double t0;
+    double alpha, cost, qp_cost, prim_res, dual_res, gap, eq_violation, step_norm, merit, merit_dd;
+    double ee_box[2];
+};
+
+// Linearisation of one node: Ad = I + dt A, cd = dt C and the pieces Bd is made of.  Bd is never stored densely:
+//   Bd[3+c , fcol(e,c,i)] = dt * fw[e][i]
+//   Bd[9:12, fcol(e,c,i)] = dt * (rel[e] x e_c) * fw[e][i]
+//   Bd[9:12, pcol(e,c,i)] = dt * (e_c x f[e])  * pw[e][i]            (single_rigid_body_model.cpp:113-148)
+struct NodeLin {
+    double Ad[kNx * kNx];
+    double cd[kNx];
+    double rel[kNumEE][3];    // r_e(t_k) - p_k
+    double f[kNumEE][3];      // f_e(t_k)
+    double fw[kNumEE][4];     // force-spline weights (same for x, y, z)
+    double pw[kNumEE][2];     // xy-position-spline weights (same for x, y)
+    int32_t fcnt[kNumEE], foff[kNumEE], pcnt[kNumEE], poff[kNumEE];
+};
+
+struct Sample {               // one of the 10 constraint samples of a stance (mpc.cpp:166-209, 352-414)
+    double w[4];
+    double time;
+    int32_t ee, off, cnt, active;   // active == 0 when every weight is exactly 0 (the touch-down sample)
+};
+
+struct EqRow {                // touch-down / foot-start rows: w . u_pos[col] = rhs
+    double w[2];
+    double rhs;
+    int32_t col[2];           // column inside the spline variables (>= nf)
+    int32_t cnt, pad;
+};
+
+constexpr int kMaxEq = 16;
+constexpr int kMaxSamples = kNumEE * kMaxStances * kSamplesPerStance;
+
+struct WsLayout {             // byte offsets inside one instance's workspace
+    size_t stride;
+    size_t hdr, nodes, samples, eq, zprev, H, g, phipos, xoff, u, lam, slack, nueq, zqp, dualx;
+    int32_t N, max_nu, max_rows, pad;
+};
+
+inline WsLayout make_layout(int N, int max_nu) {
+    WsLayout L{};
+    L.N = N;
+    L.max_nu = max_nu;
+    L.max_rows = 6 * kMaxSamples + 2 * (N - 3) * 8;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 127) / 128 * 128; return r; };
+    const size_t n_max = static_cast<size_t>(kNx) * (N + 1) + max_nu;
+    L.hdr = take(sizeof(WsHeader));
+    L.nodes = take(sizeof(NodeLin) * (N + 1));
+    L.samples = take(sizeof(Sample) * kMaxSamples);
+    L.eq = take(sizeof(EqRow) * kMaxEq);
+    L.zprev = take(8 * n_max);
+    L.H = take(8 * static_cast<size_t>(max_nu) * (max_nu + 1) / 2);   // packed lower triangle, row-major
+    L.g = take(8 * static_cast<size_t>(max_nu));
+    L.phipos = take(8 * static_cast<size_t>(2 * (N - 3)) * max_nu);   // rows (k-4)*2+c of the condensed position map
+    L.xoff = take(8 * static_cast<size_t>(kNx) * (N + 1));            // phi_k : x_k = Phi_k u + phi_k
+    L.u = take(8 * static_cast<size_t>(max_nu));
+    L.lam = take(8 * static_cast<size_t>(L.max_rows));
+    L.slack = take(8 * static_cast<size_t>(L.max_rows));
+    L.nueq = take(8 * kMaxEq);
+    L.zqp = take(8 * n_max);
+    L.dualx = take(8 * static_cast<size_t>(kNx) * (N + 1));           // dynamics multipliers (adjoint recursion)
+    L.stride = o;
+    return L;
+}
+
+}  // namespace bgg

@@ -1,0 +1,146 @@
+/* bilevel-gait-gen_b200 -- C ABI of the B200-native RTI-MPC hot path.
+ *
+ * Plain pointers and sizes only; every pointer is HOST memory unless the name says device.  All arithmetic is FP64.
+ * The reference has no FFI seam -- its hot path is a set of C++ classes linked statically into the callers
+ *  -- so each entry point names the reference member function(s) it stands in for, for a
+ * whole batch of independent MPC instances at once.  The C++ shim in bilevel-gait-gen_b200/host/ (mpc::MPC /
+ * mpc::MPCSingleRigidBody with the reference's own signatures) and the ctypes binding used by the tests both sit on
+ * top of exactly these functions.
+ *
+ * Return value: 0 on success, a negative BGG_E* code otherwise (never throws across the boundary);
+ * bgg_last_error() gives the message of the last failure on the calling thread.
+ */
+#ifndef BGG_H_
+#define BGG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGG_OK 0
+#define BGG_EINVAL (-1)
+#define BGG_ECUDA (-2)
+#define BGG_ENOMEM (-3)
+#define BGG_ESTATE (-4)
+
+#define BGG_NX 12        /* tangent states, mpc/models/single_rigid_body_model.cpp:30 */
+#define BGG_NX_MAN 13    /* manifold states [p(3) l(3) quat xyzw(4) a(3)], single_rigid_body_model.h:87-92 */
+#define BGG_NUM_EE 4
+
+/* mpc::SolveQuality, mpc/include/qp/qp_interface.h:12-22 */
+enum bgg_status {
+    BGG_SOLVED = 0, BGG_SOLVED_INACC = 1, BGG_MAX_ITER = 2, BGG_PRIMAL_INFEASIBLE = 3, BGG_DUAL_INFEASIBLE = 4,
+    BGG_PRIMAL_INFEASIBLE_INACC = 5, BGG_DUAL_INFEASIBLE_INACC = 6, BGG_UNSOLVED = 7, BGG_OTHER = 8
+};
+
+/* mpc::MPCInfo (mpc/include/mpc.h:39-62): the fields that act on the live path, plus solver settings
+ * (ClarabelInterface ctor, mpc/qp/clarabel_interface.cpp:18-27). */
+typedef struct bgg_config {
+    int32_t num_nodes;        /* N, 4 < N <= 64 */
+    int32_t max_spline_vars;  /* cap on force+position spline variables per instance (0 = default 160) */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t ipm_max_iter;     /* 0 = default 50 */
+    int32_t ipm_refine;       /* iterative-refinement steps per Newton solve (default 1; negative = 0) */
+    int32_t reserved_;
+    double integrator_dt;
+    double friction_coef;
+    double force_bound;
+    double swing_height;
+    double foot_offset;
+    double ee_box_size[2];
+    double force_cost;
+    double ipm_tol_feas;      /* 0 = default 1e-8 */
+    double ipm_tol_gap;       /* 0 = default 1e-8 */
+    double ipm_eq_delta;      /* 0 = default 1e-8 (static regularisation of the equality rows) */
+} bgg_config;
+
+/* What the reference reads out of pinocchio at construction: mpc/models/model.cpp:27 (mass),
+ * mpc/models/single_rigid_body_model.cpp:33-37 (Ir_, Ir_inv_), :258-308 (GetCOMToHip offsets). Row-major 3x3. */
+typedef struct bgg_robot {
+    double mass;
+    double Ir[9];
+    double Ir_inv[9];
+    double hip_xy[BGG_NUM_EE * 2];
+    double gravity[3];
+} bgg_robot;
+
+typedef struct bgg_handle bgg_handle;
+
+const char* bgg_last_error(void);
+int bgg_device_count(void);
+
+/* MPCSingleRigidBody::MPCSingleRigidBody (mpc/mpc_single_rigid_body.cpp:8-23) + MPC::MPC (mpc/mpc.cpp:38-76). */
+int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out);
+void bgg_destroy(bgg_handle* h);
+
+/* MPC::AddQuadraticTrackingCost (mpc.cpp:533-540), SetQuadraticFinalCost / SetLinearFinalCost (:143-157).
+ * Q and Phi are the diagonals (every shipped configuration is diagonal); x_des is a tangent state. */
+int bgg_set_costs(bgg_handle* h, const double Q_diag[BGG_NX], const double x_des[BGG_NX], const double Phi_diag[BGG_NX],
+                  const double Phi_w[BGG_NX]);
+
+/* Create `batch` instances, each the trajectory the reference constructs by default: Trajectory ctor
+ * (mpc/trajectory.cpp:11-48) over CreateDefaultSwitchingTimes (mpc.cpp:566-588) = {0,.3,.6,.9,1.2}, feet 1 and 2
+ * starting in stance.  contact_times (optional, [4][num_contacts]) replaces the default switching times. */
+int bgg_batch_reset(bgg_handle* h, int batch, const double* contact_times, int num_contacts);
+
+/* MPC::SetStateTrajectoryWarmStart (mpc.cpp:660-666).  per_node != 0: states is [batch][N+1][13];
+ * per_node == 0: states is [batch][13] and is replicated over the nodes (what every driver does, test/mpc_test.cpp:91). */
+int bgg_set_warm_states(bgg_handle* h, const double* states, int per_node);
+
+/* MPC::UpdateContactTimes (mpc.cpp:1085-1088) for instances [first, first+count): times is [count][4][num_contacts]. */
+int bgg_set_contact_times(bgg_handle* h, int first, int count, const double* times, int num_contacts);
+
+/* One RTI solve for every instance: MPC::GetRealTimeUpdate -> MPCSingleRigidBody::Solve
+ * (mpc.cpp:92-108, mpc_single_rigid_body.cpp:25-216).  state [batch][13], t0 [batch], ee_start [batch][4][3].
+ * Output arrays may be NULL.  status/iters/ls_iters are int32 [batch]; alpha/cost are double [batch]. */
+int bgg_solve_batch(bgg_handle* h, const double* state, const double* t0, const double* ee_start, int32_t* status,
+                    int32_t* iters, double* alpha, double* cost);
+
+/* The same solve split for measurement: copy inputs to HBM once, run the kernels on resident data, fetch results. */
+int bgg_upload_inputs(bgg_handle* h, const double* state, const double* t0, const double* ee_start);
+int bgg_solve_resident(bgg_handle* h);
+int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double* alpha, double* cost);
+int bgg_synchronize(bgg_handle* h);
+/* device milliseconds of the four kernels of the last bgg_solve_resident (prepare, condense, ipm, finish),
+ * measured with CUDA events on the handle's stream; enable with bgg_set_profiling(h, 1). */
+int bgg_set_profiling(bgg_handle* h, int enable);
+int bgg_last_kernel_ms(bgg_handle* h, float ms[4]);
+int bgg_kernel_launch_count(bgg_handle* h, int64_t* launches);
+
+/* --- parity taps and accessors (all sizes are per instance) ------------------------------------------------------ */
+typedef struct bgg_sizes {
+    int32_t n, nu, nf, np, n_samples, n_eebox, n_eq, n_td, m_ineq, status, iters, ls_iters, error;
+    int32_t nfv[BGG_NUM_EE], npv[BGG_NUM_EE], fbase[BGG_NUM_EE], pbase[BGG_NUM_EE];
+    double t0, alpha, cost, prim_res, dual_res, gap, eq_violation, step_norm, merit, merit_dd, ee_box[2];
+} bgg_sizes;
+int bgg_get_sizes(bgg_handle* h, int instance, bgg_sizes* out);
+
+/* Discretised dynamics of the last solve, dense, as the reference holds them in A_, B_, C_
+ * (mpc_single_rigid_body.cpp:236-262): Ad [count][N][12][12], Bd [count][N][12][nu_stride], cd [count][N][12]. */
+int bgg_get_dynamics(bgg_handle* h, int first, int count, double* Ad, double* Bd, double* cd, int nu_stride);
+
+/* Condensed QP of the last solve: H [nu][nu], g [nu], phipos [2(N-3)][nu] (position rows of the state map for the
+ * foot-box rows, node-major from node 4), xoff [N+1][12] (state offsets).  Any pointer may be NULL. */
+int bgg_get_condensed(bgg_handle* h, int instance, double* H, double* g, double* phipos, double* xoff);
+
+/* Solution of the last solve.  qp_sol [n]: the QP optimum z* = [x_0..x_N | u] (MPC::Solve's `sol`);
+ * z [n]: prev_qp_sol after the line-search update (MPC::GetQPSolution, mpc.cpp:1071-1073);
+ * lam / slack [m_ineq] in the kernel's row order (see csrc/bgg_ipm.cu), nu_eq [n_eq]. */
+int bgg_get_solution(bgg_handle* h, int instance, double* qp_sol, double* z, double* lam, double* slack, double* nu_eq);
+
+/* Raw trajectory of one instance (the POD bgg::Instance of csrc/bgg_types.cuh). */
+size_t bgg_instance_bytes(void);
+int bgg_get_instance(bgg_handle* h, int instance, void* out);
+int bgg_set_instance(bgg_handle* h, int instance, const void* in);
+/* Trajectory::GetState / GetForce / GetEndEffectorLocation (mpc/trajectory.cpp:267-269,395-411) */
+int bgg_get_states(bgg_handle* h, int instance, double* states /* [N+1][13] */);
+int bgg_eval_splines(bgg_handle* h, int instance, const double* times, int num_times, double* force /* [T][4][3] */,
+                     double* position /* [T][4][3] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGG_H_ */
