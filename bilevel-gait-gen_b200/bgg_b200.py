@@ -42,7 +42,7 @@ class Sizes(C.Structure):
                                          "iters", "ls_iters", "error")] + \
                [("nfv", C.c_int32 * 4), ("npv", C.c_int32 * 4), ("fbase", C.c_int32 * 4), ("pbase", C.c_int32 * 4)] + \
                [(n, C.c_double) for n in ("t0", "alpha", "cost", "prim_res", "dual_res", "gap", "eq_violation", "step_norm",
-                                          "merit", "merit_dd")] + [("ee_box", C.c_double * 2)]
+                                          "merit", "merit_dd")] + [("ee_box", C.c_double * 2), ("qp_cost", C.c_double)]
 
 
 # numpy view of the POD bgg::Instance / bgg::FootSpline (csrc/bgg_types.cuh)
@@ -77,6 +77,8 @@ def lib():
         L.bgg_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.bgg_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.bgg_kernel_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.bgg_event_record.argtypes = [C.c_void_p, C.c_int]
+        L.bgg_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.bgg_get_sizes.argtypes = [C.c_void_p, C.c_int, C.POINTER(Sizes)]
         L.bgg_get_dynamics.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int]
         L.bgg_get_condensed.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
@@ -94,7 +96,7 @@ def exported_symbols():
     """Names include/bgg.h declares; used by the CPU-side ABI test."""
     return ["bgg_last_error", "bgg_device_count", "bgg_create", "bgg_destroy", "bgg_set_costs", "bgg_batch_reset",
             "bgg_set_warm_states", "bgg_set_contact_times", "bgg_solve_batch", "bgg_upload_inputs", "bgg_solve_resident",
-            "bgg_download_results", "bgg_synchronize", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count",
+            "bgg_download_results", "bgg_synchronize", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count", "bgg_event_record", "bgg_event_elapsed_ms",
             "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_get_solution", "bgg_instance_bytes",
             "bgg_get_instance", "bgg_set_instance", "bgg_get_states", "bgg_eval_splines"]
 
@@ -239,6 +241,14 @@ class BatchedMPC:
         ms = (C.c_float * 4)()
         self._chk(self.L.bgg_last_kernel_ms(self.h, ms))
         return dict(zip(("prepare", "condense", "ipm", "finish"), (float(v) for v in ms)))
+
+    def event_record(self, slot):
+        self._chk(self.L.bgg_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._chk(self.L.bgg_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return float(ms.value)
 
     def launch_count(self):
         v = C.c_int64()

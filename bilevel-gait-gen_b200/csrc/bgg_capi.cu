@@ -10,6 +10,8 @@
 
 using namespace bgg;
 
+static_assert(sizeof(WsHeader) == 248, "bench.py reports the per-instance result record as 248 bytes");
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -38,6 +40,7 @@ struct bgg_handle {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
     int64_t launches = 0;
+    cudaEvent_t user_ev[8] = {};
     bool costs_set = false;
 };
 
@@ -154,6 +157,7 @@ int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) 
         return fail(BGG_ECUDA, "cudaStreamCreate failed");
     }
     for (auto& e : h->ev) cudaEventCreate(&e);
+    for (auto& e : h->user_ev) cudaEventCreate(&e);
     *out = h;
     return BGG_OK;
 }
@@ -184,6 +188,8 @@ void bgg_destroy(bgg_handle* h) {
     cudaStreamSynchronize(h->stream);
     free_batch(h);
     for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : h->user_ev)
         if (e) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -353,6 +359,21 @@ int bgg_kernel_launch_count(bgg_handle* h, int64_t* launches) {
     return BGG_OK;
 }
 
+int bgg_event_record(bgg_handle* h, int slot) {
+    if (!h || slot < 0 || slot >= 8) return fail(BGG_EINVAL, "bad event slot");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->user_ev[slot], h->stream));
+    return BGG_OK;
+}
+
+int bgg_event_elapsed_ms(bgg_handle* h, int a, int b, float* ms) {
+    if (!h || !ms || a < 0 || a >= 8 || b < 0 || b >= 8) return fail(BGG_EINVAL, "bad event slot");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventSynchronize(h->user_ev[b]));
+    CU(cudaEventElapsedTime(ms, h->user_ev[a], h->user_ev[b]));
+    return BGG_OK;
+}
+
 static int fetch(bgg_handle* h, void* dst, const void* dsrc, size_t bytes) {
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
@@ -374,6 +395,7 @@ int bgg_get_sizes(bgg_handle* h, int b, bgg_sizes* out) {
     out->t0 = w.t0; out->alpha = w.alpha; out->cost = w.cost; out->prim_res = w.prim_res; out->dual_res = w.dual_res;
     out->gap = w.gap; out->eq_violation = w.eq_violation; out->step_norm = w.step_norm; out->merit = w.merit;
     out->merit_dd = w.merit_dd; out->ee_box[0] = w.ee_box[0]; out->ee_box[1] = w.ee_box[1];
+    out->qp_cost = w.qp_cost;
     return BGG_OK;
 }
 

@@ -28,7 +28,7 @@ size_t condense_smem_bytes(const WsLayout& L) {
 __global__ void __launch_bounds__(256) k_condense(Params P, WsLayout L, char* __restrict__ ws_base) {
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
-    const WsHeader* Hd = reinterpret_cast<const WsHeader*>(ws + L.hdr);
+    WsHeader* Hd = reinterpret_cast<WsHeader*>(ws + L.hdr);
     if (Hd->error) return;
     const NodeLin* nodes = reinterpret_cast<const NodeLin*>(ws + L.nodes);
     const double* zprev = reinterpret_cast<const double*>(ws + L.zprev);
@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(256) k_condense(Params P, WsLayout L, char* __
     double* pq = phi + 2 * kNx;                                // [2][12]: P_k (diag) and P_k phi_k + q_k
     NodeLin* nl = reinterpret_cast<NodeLin*>(pq + 2 * kNx);
     __shared__ int s_fbase[kNumEE], s_pbase[kNumEE], s_nfv[kNumEE], s_npv[kNumEE];
+    __shared__ double s_cc[kNx];
+    double cc = 0.0;   // this thread's share of the constant term of the condensed objective
 
     for (int i = tid; i < npk; i += nth) Hp[i] = 0.0;
     for (int i = tid; i < 2 * kNx * nu; i += nth) Phi[i] = 0.0;
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(256) k_condense(Params P, WsLayout L, char* __
             const double qk = (k < N) ? P.w[tid] : P.Phi_w[tid];
             pq[tid] = pk;
             pq[kNx + tid] = pk * fc[tid] + qk;
+            cc += 0.5 * pk * fc[tid] * fc[tid] + qk * fc[tid];
             xoff[k * kNx + tid] = fc[tid];
         }
         __syncthreads();
@@ -149,12 +152,18 @@ __global__ void __launch_bounds__(256) k_condense(Params P, WsLayout L, char* __
         }
         __syncthreads();
     }
+    if (tid < kNx) s_cc[tid] = cc;
     // P_u: force weight on force variables, +1e-3 on everything (AddForceCost / AddDiagonalCost)
     for (int i = tid; i < nu; i += nth) {
         Hp[i * (i + 1) / 2 + i] += ((i < nf) ? P.force_cost : 0.0) + 1e-3;
         gout[i] = gs[i];
     }
     __syncthreads();
+    if (tid == 0) {
+        double t = 0;
+        for (int r = 0; r < kNx; ++r) t += s_cc[r];
+        Hd->cost_const = t;
+    }
     // full symmetric H to HBM (the IPM reads it column-wise, coalesced)
     for (int p = tid; p < nu * nu; p += nth) {
         const int i = p / nu, j = p % nu;

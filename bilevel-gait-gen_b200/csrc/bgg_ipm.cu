@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
 
     const int N = P.N, nu = Hd->nu, nf = Hd->nf, ns = Hd->n_samples, ne = Hd->n_eebox, neq = Hd->n_eq;
     const int m = 6 * ns + 2 * ne, nkc = 2 * (N - 3), npk = nu * (nu + 1) / 2;
+    const double cost_const = Hd->cost_const;
     const double mu_f = P.friction_coef, delta = P.ipm_eq_delta, inv_delta = 1.0 / P.ipm_eq_delta;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
 
     // ------------------------------------------------------------------------------------------------ main loop
     int it = 0, status = kMaxIter;
-    double n_rd = 0, n_rp = 0, n_re = 0, mu = 0, gap_scale = 1;
+    double n_rd = 0, n_rp = 0, n_re = 0, mu = 0, gap_scale = 1, qp_obj = 0, last_rp = 0, last_re = 0;
     for (it = 0; it <= P.ipm_max_iter; ++it) {
         // residuals: rd = H u + g + C'lam + E'nu ; rp = C u + s - d ; re = E u - e
         apply_H(S.u, S.rd);
@@ -418,6 +419,7 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
             S.rd[i] += S.g[i];
         }
         pobj = block_reduce<kSum>(pobj, S.red);
+        qp_obj = pobj;
         add_Ct(S.lam, S.rd);
         add_Et(S.nueq, S.rd, 1.0);
         apply_C(S.u, S.rp);
@@ -439,12 +441,16 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         mu = dsum / m_act;
         n_re = 0;
         for (int r = 0; r < neq; ++r) n_re = fmax(n_re, fabs(S.re[r]));
-        gap_scale = fmax(1.0, fabs(pobj));
+        gap_scale = fmax(1.0, fabs(pobj + cost_const));   // full objective, as Clarabel's relative gap
         const bool nan_seen = !(n_rd == n_rd) || !(n_rp == n_rp) || !(mu == mu);
         if (nan_seen || !ok) {
             status = kOther;
+            n_rp = last_rp;
+            n_re = last_re;
             break;
         }
+        last_rp = n_rp;
+        last_re = n_re;
         if (n_rd <= P.ipm_tol_feas * nrm_q && n_rp <= P.ipm_tol_feas * nrm_d && n_re <= P.ipm_tol_feas * nrm_d &&
             dsum <= P.ipm_tol_gap * gap_scale) {
             status = kSolved;
@@ -539,6 +545,8 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         if (tid < neq) S.nueq[tid] += alpha * S.dnu[tid];
         __syncthreads();
     }
+    // a diverging iteration on a problem whose primal residual never came down: infeasible (no homogeneous embedding)
+    if (status == kOther && (n_rp > 1e-4 * nrm_d || n_re > 1e-4 * nrm_d)) status = kPrimalInfeasible;
     if (status == kMaxIter) {
         const double loose = 1e3;
         if (n_rd <= loose * P.ipm_tol_feas * nrm_q && n_rp <= loose * P.ipm_tol_feas * nrm_d &&
@@ -565,6 +573,7 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         Hd->prim_res = fmax(n_rp, n_re);
         Hd->dual_res = n_rd;
         Hd->gap = mu * m_act;
+        Hd->qp_cost = qp_obj + cost_const;
     }
     (void)delta;
     (void)npk;

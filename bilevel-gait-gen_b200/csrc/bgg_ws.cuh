@@ -23,6 +23,7 @@ struct WsHeader {
     int32_t error;                        // bit 0: too many knots, bit 1: nu > max_nu, bit 2: too many samples
     int32_t status, iters, ls_iters, pad0;
     double t0;
+    double cost_const;                    // 1/2 phi'P phi + q'phi: condensed objective + cost_const = full objective
     double alpha, cost, qp_cost, prim_res, dual_res, gap, eq_violation, step_norm, merit, merit_dd;
     double ee_box[2];
 };
@@ -76,7 +77,7 @@ inline WsLayout make_layout(int N, int max_nu) {
     L.samples = take(sizeof(Sample) * kMaxSamples);
     L.eq = take(sizeof(EqRow) * kMaxEq);
     L.zprev = take(8 * n_max);
-    L.H = take(8 * static_cast<size_t>(max_nu) * (max_nu + 1) / 2);   // packed lower triangle, row-major
+    L.H = take(8 * static_cast<size_t>(max_nu) * max_nu);             // full symmetric nu x nu (row stride nu)
     L.g = take(8 * static_cast<size_t>(max_nu));
     L.phipos = take(8 * static_cast<size_t>(2 * (N - 3)) * max_nu);   // rows (k-4)*2+c of the condensed position map
     L.xoff = take(8 * static_cast<size_t>(kNx) * (N + 1));            // phi_k : x_k = Phi_k u + phi_k

@@ -109,12 +109,17 @@ int bgg_synchronize(bgg_handle* h);
 int bgg_set_profiling(bgg_handle* h, int enable);
 int bgg_last_kernel_ms(bgg_handle* h, float ms[4]);
 int bgg_kernel_launch_count(bgg_handle* h, int64_t* launches);
+/* CUDA events on the handle's stream for whole-step timing: record event `slot` (0..7); elapsed ms between two slots
+ * (synchronises on the later one). */
+int bgg_event_record(bgg_handle* h, int slot);
+int bgg_event_elapsed_ms(bgg_handle* h, int slot_start, int slot_end, float* ms);
 
 /* --- parity taps and accessors (all sizes are per instance) ------------------------------------------------------ */
 typedef struct bgg_sizes {
     int32_t n, nu, nf, np, n_samples, n_eebox, n_eq, n_td, m_ineq, status, iters, ls_iters, error;
     int32_t nfv[BGG_NUM_EE], npv[BGG_NUM_EE], fbase[BGG_NUM_EE], pbase[BGG_NUM_EE];
     double t0, alpha, cost, prim_res, dual_res, gap, eq_violation, step_norm, merit, merit_dd, ee_box[2];
+    double qp_cost; /* objective of the QP optimum, 1/2 z'Pz + q'z */
 } bgg_sizes;
 int bgg_get_sizes(bgg_handle* h, int instance, bgg_sizes* out);
 

@@ -8,6 +8,7 @@
 
 #include "foot_spline.hpp"
 #include "qp_admm.hpp"
+#include "qp_ipm.hpp"
 #include "srb_mpc.hpp"
 
 using namespace oracle;
@@ -221,7 +222,8 @@ struct OrcRobotConsts {
     double mass, Ir[9], Ir_inv[9], hip_xy[8], gravity[3];
 };
 struct MpcHandle {
-    std::shared_ptr<AdmmQpSolver> solver;
+    std::shared_ptr<AdmmQpSolver> solver;     // OSQP restatement (the reference's test-only OSQPInterface)
+    std::shared_ptr<IpmQpSolver> ipm;         // interior point (the reference's live ClarabelInterface)
     std::unique_ptr<SrbMpc> mpc;
 };
 
@@ -239,7 +241,8 @@ void* orc_mpc_create(const OrcMpcInfo* ci, const OrcRobotConsts* cr) {
     std::memcpy(rc.gravity, cr->gravity, sizeof rc.gravity);
     auto* h = new MpcHandle;
     h->solver = std::make_shared<AdmmQpSolver>();
-    h->mpc.reset(new SrbMpc(info, rc, h->solver));
+    h->ipm = std::make_shared<IpmQpSolver>();
+    h->mpc.reset(new SrbMpc(info, rc, h->ipm));   // the live path: interior point
     return h;
     ORC_CATCH(nullptr)
 }
@@ -248,11 +251,45 @@ void* orc_mpc_clone(void* h) {
     auto* src = static_cast<MpcHandle*>(h);
     auto* dst = new MpcHandle;
     dst->solver = std::make_shared<AdmmQpSolver>(*src->solver);
+    dst->ipm = std::make_shared<IpmQpSolver>(*src->ipm);
     dst->mpc.reset(new SrbMpc(*src->mpc));
-    dst->mpc->SetSolver(dst->solver);
+    dst->mpc->SetSolver(dst->ipm);
     return dst;
 }
 static SrbMpc& M(void* h) { return *static_cast<MpcHandle*>(h)->mpc; }
+
+// which: 0 = interior point (default, the reference's live Clarabel path), 1 = ADMM (its OSQPInterface)
+void orc_mpc_select_solver(void* h, int which) {
+    auto* mh = static_cast<MpcHandle*>(h);
+    if (which == 1) mh->mpc->SetSolver(mh->solver);
+    else mh->mpc->SetSolver(mh->ipm);
+}
+void orc_mpc_set_ipm(void* h, double tol_feas, double tol_gap, int max_iter, int refine) {
+    auto* mh = static_cast<MpcHandle*>(h);
+    if (tol_feas > 0) mh->ipm->settings.tol_feas = tol_feas;
+    if (tol_gap > 0) mh->ipm->settings.tol_gap = tol_gap;
+    if (max_iter > 0) mh->ipm->settings.max_iter = max_iter;
+    if (refine >= 0) mh->ipm->settings.refine = refine;
+}
+// generic Clarabel-form interior-point solve; info = [iters, prim_res, dual_res, gap]
+int orc_ipm_solve(int n, int m, const int* Pcolptr, const int* Prowidx, const double* Pval, const double* q,
+                  const int* Acolptr, const int* Arowidx, const double* Aval, const double* b, const char* is_eq,
+                  double tol, int max_iter, double* x, double* y, double* s, double* info) {
+    ORC_TRY
+    const Csc P = MakeCsc(n, n, Pcolptr, Prowidx, Pval), A = MakeCsc(m, n, Acolptr, Arowidx, Aval);
+    IpmSettings st;
+    if (tol > 0) st.tol_feas = st.tol_gap = tol;
+    if (max_iter > 0) st.max_iter = max_iter;
+    const IpmResult r = IpmSolve(P, Vec(q, q + n), A, Vec(b, b + m), std::vector<char>(is_eq, is_eq + m), {}, st);
+    if (!r.x.empty()) {
+        std::copy(r.x.begin(), r.x.end(), x);
+        std::copy(r.y.begin(), r.y.end(), y);
+        std::copy(r.s.begin(), r.s.end(), s);
+    }
+    info[0] = r.iters; info[1] = r.prim_res; info[2] = r.dual_res; info[3] = r.gap;
+    return r.status;
+    ORC_CATCH(-1)
+}
 
 void orc_mpc_set_admm(void* h, const OrcAdmmSettings* initial, const OrcAdmmSettings* real_time) {
     auto* mh = static_cast<MpcHandle*>(h);

@@ -254,6 +254,10 @@ def _bind_mpc_api(lib):
     lib.orc_mpc_destroy.argtypes = [C.c_void_p]
     lib.orc_mpc_clone.restype = C.c_void_p
     lib.orc_mpc_clone.argtypes = [C.c_void_p]
+    lib.orc_mpc_select_solver.argtypes = [C.c_void_p, C.c_int]
+    lib.orc_mpc_set_ipm.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.orc_ipm_solve.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, _dp, _ip, _ip, _dp, _dp, C.c_char_p, C.c_double, C.c_int,
+                                  _dp, _dp, _dp, _dp]
     lib.orc_mpc_set_admm.argtypes = [C.c_void_p, C.POINTER(AdmmSettings), C.POINTER(AdmmSettings)]
     lib.orc_mpc_get_admm.argtypes = [C.c_void_p, C.POINTER(AdmmSettings), C.POINTER(AdmmSettings)]
     lib.orc_mpc_set_costs.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
@@ -319,6 +323,29 @@ def admm_solve(P, q, A, l, u, x0=None, y0=None, settings=None):
                 rho_updates=int(info[4]))
 
 
+def ipm_solve(P, q, A, b, is_eq, tol=0.0, max_iter=0):
+    """Interior-point solve of min 1/2 x'Px+q'x, Ax + s = b, s = 0 on is_eq rows and s >= 0 elsewhere."""
+    import scipy.sparse as sp
+    lib = load()
+    P = sp.csc_matrix(P, dtype=np.float64)
+    A = sp.csc_matrix(A, dtype=np.float64)
+    P.sort_indices()
+    A.sort_indices()
+    n, m = P.shape[0], A.shape[0]
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    eq = np.ascontiguousarray(is_eq, dtype=np.uint8).tobytes()
+    x, y, s, info = np.zeros(n), np.zeros(m), np.zeros(m), np.zeros(4)
+    pc, pr = P.indptr.astype(np.int32), P.indices.astype(np.int32)
+    ac, ar = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    pv, av = np.ascontiguousarray(P.data), np.ascontiguousarray(A.data)
+    st = lib.orc_ipm_solve(n, m, _iptr(pc), _iptr(pr), _dptr(pv), _dptr(q), _iptr(ac), _iptr(ar), _dptr(av), _dptr(b), eq,
+                           tol, max_iter, _dptr(x), _dptr(y), _dptr(s), _dptr(info))
+    if st < 0:
+        raise OracleError(lib.orc_last_error().decode())
+    return dict(x=x, y=y, s=s, status=st, iters=int(info[0]), prim_res=info[1], dual_res=info[2], gap=info[3])
+
+
 def load_robot_consts(path):
     import json
     with open(path) as f:
@@ -330,13 +357,13 @@ class SrbMpc:
     """The oracle's restatement of mpc::MPCSingleRigidBody (live path)."""
 
     def __init__(self, num_nodes, dt, consts, friction_coef=0.5, force_bound=150.0, swing_height=0.075, foot_offset=0.015,
-                 ee_box=(0.15, 0.15), force_cost=0.0, _handle=None):
+                 ee_box_size=(0.15, 0.15), force_cost=0.0, _handle=None):
         self.lib = load()
         self.N = num_nodes
         if _handle is not None:
             self.h = _handle
             return
-        info = _MpcInfo(num_nodes, friction_coef, dt, force_bound, swing_height, foot_offset, ee_box[0], ee_box[1], force_cost)
+        info = _MpcInfo(num_nodes, friction_coef, dt, force_bound, swing_height, foot_offset, ee_box_size[0], ee_box_size[1], force_cost)
         rc = _RobotConsts()
         rc.mass = consts["mass"]
         rc.Ir[:] = np.asarray(consts["Ir"], dtype=float).ravel().tolist()
@@ -359,6 +386,13 @@ class SrbMpc:
         if rc < 0:
             raise OracleError(self.lib.orc_last_error().decode())
         return rc
+
+    def select_solver(self, which):
+        """'ipm' (default; the reference's live Clarabel path) or 'admm' (its test-only OSQP path)."""
+        self.lib.orc_mpc_select_solver(self.h, 1 if which == "admm" else 0)
+
+    def set_ipm(self, tol_feas=0.0, tol_gap=0.0, max_iter=0, refine=-1):
+        self.lib.orc_mpc_set_ipm(self.h, tol_feas, tol_gap, max_iter, refine)
 
     def set_admm(self, initial=None, real_time=None):
         self.lib.orc_mpc_set_admm(self.h, C.byref(initial) if initial is not None else None,

@@ -81,7 +81,12 @@ for it in range(nsolves):
         # oracle: full solve of the same step for the line-search / trajectory comparison
         o.solve(states[b], 0.0, ees[b], real_time=True)
         ost = o.stats()
-        print(f"      oracle(ADMM) cost {ost['cost']:.6f} alpha {ost['alpha']} eqviol {ost['eq_violation']:.3e} | gpu cost {sz['cost']:.6f} "
+        oq = o.qp_solution()
+        zo = o.prev_qp_sol()
+        print(f"      qp_sol relerr {np.linalg.norm(oq['x'] - z) / np.linalg.norm(oq['x']):.2e} (oracle ipm iters {oq['iters']} status {oq['status']})"
+              f" z relerr {np.linalg.norm(zo - sol['z']) / np.linalg.norm(zo):.2e} states err {np.abs(o.states() - mpc.GetStates(b)).max():.2e}"
+              f" qp obj gpu {sz['qp_cost']:.8f} oracle {0.5 * oq['x'] @ (P @ oq['x']) + q @ oq['x']:.8f}")
+        print(f"      oracle(IPM) cost {ost['cost']:.6f} alpha {ost['alpha']} eqviol {ost['eq_violation']:.3e} | gpu cost {sz['cost']:.6f} "
               f"alpha {sz['alpha']} eqviol {sz['eq_violation']:.3e} merit {sz['merit']:.4f}/{ost['merit']:.4f}")
 np.savez_compressed(os.path.join(ROOT, "gpurun_out", "debug1.npz"), **dump)
 print("dumped")
