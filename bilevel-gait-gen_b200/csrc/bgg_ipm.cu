@@ -26,18 +26,29 @@ struct Smem {
     double *tkc, *ckc;                               // 2(N-3)
     double *nueq, *re, *dnu;                         // kMaxEq
     double* red;                                     // 40
+    double* pw;                                      // [(N-3)*4][2] foot-box position weights
+    int *pcnt, *poff;                                // [(N-3)*4]
+    Sample* smp;                                     // staged force samples
+    const double* phi;                               // position rows: shared memory when they fit, else HBM/L2
+    int phi_stride;
 };
 
 __device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 
 }  // namespace
 
+static size_t ipm_smem_core(const WsLayout& L) {
+    const size_t nu = L.max_nu, m = L.max_rows, kc = 2 * (L.N - 3), eb = 4 * (L.N - 3);
+    return 8 * (nu * (nu + 1) / 2 + 6 * nu + 7 * m + 2 * kc + 3 * kMaxEq + 40 + 2 * eb) + 8 * eb + sizeof(Sample) * kMaxSamples + 64;
+}
+static bool ipm_stage_phipos(const WsLayout& L) {   // keep the dense position rows on chip when they fit
+    return ipm_smem_core(L) + 8 * static_cast<size_t>(2 * (L.N - 3)) * L.max_nu <= 225 * 1024;
+}
 size_t ipm_smem_bytes(const WsLayout& L) {
-    const size_t nu = L.max_nu, m = L.max_rows, kc = 2 * (L.N - 3);
-    return 8 * (nu * (nu + 1) / 2 + 6 * nu + 7 * m + 2 * kc + 3 * kMaxEq + 40) + 64;
+    return ipm_smem_core(L) + (ipm_stage_phipos(L) ? 8 * static_cast<size_t>(2 * (L.N - 3)) * L.max_nu : 0);
 }
 
-__global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base) {
+__global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi) {
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
@@ -70,10 +81,35 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         S.rp = p; p += L.max_rows; S.wv = p; p += L.max_rows; S.d = p; p += L.max_rows;
         S.tkc = p; p += nkc; S.ckc = p; p += nkc;
         S.nueq = p; p += kMaxEq; S.re = p; p += kMaxEq; S.dnu = p; p += kMaxEq;
-        S.red = p;
+        S.red = p; p += 40;
+        S.pw = p; p += 2 * 4 * (N - 3);
+        S.pcnt = reinterpret_cast<int*>(p);
+        S.poff = S.pcnt + 4 * (N - 3);
+        p += 4 * (N - 3);
+        S.smp = reinterpret_cast<Sample*>(p);
+        p += sizeof(Sample) * kMaxSamples / 8;
+        if (stage_phi) {
+            S.phi = p;
+            S.phi_stride = nf;
+            for (int i = tid; i < nkc * nf; i += nth) p[i] = phipos[static_cast<size_t>(i / nf) * L.max_nu + (i % nf)];
+        } else {
+            S.phi = phipos;
+            S.phi_stride = L.max_nu;
+        }
+    }
+    for (int i = tid; i < ns * static_cast<int>(sizeof(Sample) / 8); i += nth)
+        reinterpret_cast<double*>(S.smp)[i] = reinterpret_cast<const double*>(samples)[i];
+    for (int i = tid; i < 4 * (N - 3); i += nth) {
+        const NodeLin& nl = nodes[i / 4 + kEENodeStart];
+        const int foot = i & 3;
+        S.pcnt[i] = nl.pcnt[foot];
+        S.poff[i] = nl.poff[foot];
+        S.pw[2 * i] = nl.pw[foot][0];
+        S.pw[2 * i + 1] = nl.pw[foot][1];
     }
     __shared__ int s_fbase[kNumEE], s_pbase[kNumEE], s_nfv[kNumEE], s_npv[kNumEE];
     __shared__ int s_flag;
+    __shared__ int s_sb[kNumEE + 1];   // per-foot sample ranges (samples are stored foot-major)
     if (tid < kNumEE) {
         s_fbase[tid] = Hd->fbase[tid];
         s_pbase[tid] = Hd->pbase[tid];
@@ -81,6 +117,13 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         s_npv[tid] = Hd->npv[tid];
     }
     for (int i = tid; i < nu; i += nth) S.g[i] = gg[i];
+    if (tid == 0) {
+        int e = 0;
+        s_sb[0] = 0;
+        for (int j = 0; j < ns; ++j)
+            while (samples[j].ee > e) s_sb[++e] = j;
+        while (e < kNumEE) s_sb[++e] = ns;
+    }
 
     // ---- right-hand sides d (and the active mask: wv < 0 marks an inactive row while setting up)
     const double box0 = Hd->ee_box[0] / 2, box1 = Hd->ee_box[1] / 2;
@@ -107,14 +150,14 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
     // out[0..m) = C v   (v: nu-vector in shared memory)
     auto apply_C = [&](const double* v, double* out) {
         for (int q = wid; q < nkc; q += nwarp) {     // dense position rows: one warp per (node, coord)
-            const double* row = phipos + static_cast<size_t>(q) * L.max_nu;
+            const double* row = S.phi + static_cast<size_t>(q) * S.phi_stride;
             double s = 0;
             for (int i = lane; i < nf; i += 32) s += row[i] * v[i];
             s = warp_sum(s);
             if (lane == 0) S.tkc[q] = s;
         }
         for (int j = tid; j < ns; j += nth) {
-            const Sample& sp = samples[j];
+            const Sample& sp = S.smp[j];
             double fv[3];
             for (int c = 0; c < 3; ++c) {
                 const double* vv = v + s_fbase[sp.ee] + c * s_nfv[sp.ee] + sp.off;
@@ -132,19 +175,17 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         }
         __syncthreads();
         for (int e = tid; e < ne; e += nth) {
-            const int c = e & 1, foot = (e >> 1) & 3, kk = e >> 3;
-            const NodeLin& nl = nodes[kk + kEENodeStart];
-            const double* vv = v + nf + s_pbase[foot] + c * s_npv[foot] + nl.poff[foot];
+            const int c = e & 1, foot = (e >> 1) & 3, kk = e >> 3, kf = kk * 4 + foot;
+            const double* vv = v + nf + s_pbase[foot] + c * s_npv[foot] + S.poff[kf];
             double s = -S.tkc[kk * 2 + c];
-            for (int i = 0; i < nl.pcnt[foot]; ++i) s += nl.pw[foot][i] * vv[i];
+            for (int i = 0; i < S.pcnt[kf]; ++i) s += S.pw[2 * kf + i] * vv[i];
             out[6 * ns + 2 * e] = s;
             out[6 * ns + 2 * e + 1] = -s;
         }
         __syncthreads();
     };
-    // out[0..nu) += C' y   (y: m-vector; rows with wv == 0 contribute nothing)
+    // out[0..nu) += C' y   (y: m-vector; inactive rows carry y == 0).  Every output entry is owned by one thread.
     auto add_Ct = [&](const double* y, double* out) {
-        // foot-box rows: per (node, coord) coefficient on the dense position row, gathered per column
         for (int q = tid; q < nkc; q += nth) {
             const int kk = q >> 1, c = q & 1;
             double s = 0;
@@ -155,36 +196,40 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
             S.ckc[q] = -s;
         }
         __syncthreads();
-        for (int i = tid; i < nf; i += nth) {
+        // force columns: dense position rows + this foot's samples
+        for (int col = tid; col < nf; col += nth) {
             double s = 0;
-            for (int q = 0; q < nkc; ++q) s += S.ckc[q] * phipos[static_cast<size_t>(q) * L.max_nu + i];
-            out[i] += s;
-        }
-        __syncthreads();
-        // sparse parts, one thread per destination column block to stay free of atomics:
-        // force columns of foot e / coord c are touched only by that foot's samples
-        if (tid < kNumEE * 3) {
-            const int e = tid / 3, c = tid % 3;
-            double* o = out + s_fbase[e] + c * s_nfv[e];
-            for (int j = 0; j < ns; ++j) {
-                const Sample& sp = samples[j];
-                if (sp.ee != e || !sp.active) continue;
+            for (int q = 0; q < nkc; ++q) s += S.ckc[q] * S.phi[static_cast<size_t>(q) * S.phi_stride + col];
+            int e = 0;
+            while (e < kNumEE - 1 && col >= s_fbase[e + 1]) ++e;
+            const int loc = col - s_fbase[e], c = loc / s_nfv[e], i = loc % s_nfv[e];
+            for (int j = s_sb[e]; j < s_sb[e + 1]; ++j) {
+                const Sample& sp = S.smp[j];
+                const int a = i - sp.off;
+                if (a < 0 || a >= sp.cnt || !sp.active) continue;
                 const double* yy = y + 6 * j;
                 double coef;
                 if (c == 2) coef = (yy[0] - yy[1]) - mu_f * (yy[2] + yy[3] + yy[4] + yy[5]);
                 else if (c == 0) coef = yy[2] - yy[3];
                 else coef = yy[4] - yy[5];
-                for (int i = 0; i < sp.cnt; ++i) o[sp.off + i] += coef * sp.w[i];
+                s += coef * sp.w[a];
             }
-        } else if (tid >= 32 && tid < 32 + kNumEE * 2) {
-            const int q = tid - 32, foot = q >> 1, c = q & 1;
-            double* o = out + nf + s_pbase[foot] + c * s_npv[foot];
+            out[col] += s;
+        }
+        // position columns: the foot-box rows whose active segment contains the variable
+        for (int col = nf + tid; col < nu; col += nth) {
+            const int pc = col - nf;
+            int foot = 0;
+            while (foot < kNumEE - 1 && pc >= s_pbase[foot + 1]) ++foot;
+            const int loc = pc - s_pbase[foot], c = loc / s_npv[foot], v = loc % s_npv[foot];
+            double s = 0;
             for (int kk = 0; kk < N - 3; ++kk) {
-                const NodeLin& nl = nodes[kk + kEENodeStart];
-                const int e = (kk * 4 + foot) * 2 + c;
-                const double coef = y[6 * ns + 2 * e] - y[6 * ns + 2 * e + 1];
-                for (int i = 0; i < nl.pcnt[foot]; ++i) o[nl.poff[foot] + i] += coef * nl.pw[foot][i];
+                const int kf = kk * 4 + foot, a = v - S.poff[kf];
+                if (a < 0 || a >= S.pcnt[kf]) continue;
+                const int e = kf * 2 + c;
+                s += (y[6 * ns + 2 * e] - y[6 * ns + 2 * e + 1]) * S.pw[2 * kf + a];
             }
+            out[col] += s;
         }
         __syncthreads();
     };
@@ -233,62 +278,90 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
             S.ckc[q] = s;
         }
         __syncthreads();
-        // force-force block: sum_q ckc[q] phi_q phi_q'   (16 x 16 thread tiling)
+        // force-force block: sum_q ckc[q] phi_q phi_q'   (4 x 4 register tiles, 16 x 16 threads over the tile grid)
         {
             const int ty = tid >> 4, tx = tid & 15;
-            for (int i = ty; i < nf; i += 16)
-                for (int j = tx; j <= i; j += 16) {
-                    double s = 0;
+            const int side = (nf + 3) >> 2;
+            for (int ti = ty; ti < side; ti += 16)
+                for (int tl = tx; tl <= ti; tl += 16) {
+                    const int i0 = 4 * ti, l0 = 4 * tl;
+                    double acc[4][4];
+#pragma unroll
+                    for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; ++c2) acc[a2][c2] = 0.0;
                     for (int q = 0; q < nkc; ++q) {
-                        const double* row = phipos + static_cast<size_t>(q) * L.max_nu;
-                        s += S.ckc[q] * row[i] * row[j];
+                        const double* row = S.phi + static_cast<size_t>(q) * S.phi_stride;
+                        const double wq = S.ckc[q];
+                        double ra[4], rc[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            ra[k] = (i0 + k < nf) ? wq * row[i0 + k] : 0.0;
+                            rc[k] = (l0 + k < nf) ? row[l0 + k] : 0.0;
+                        }
+#pragma unroll
+                        for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                            for (int c2 = 0; c2 < 4; ++c2) acc[a2][c2] += ra[a2] * rc[c2];
                     }
-                    S.K[pk(i, j)] += s;
+#pragma unroll
+                    for (int a2 = 0; a2 < 4; ++a2) {
+                        const int ii = i0 + a2;
+                        if (ii >= nf) continue;
+                        double* Ki = S.K + ii * (ii + 1) / 2;
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; ++c2)
+                            if (l0 + c2 <= ii) Ki[l0 + c2] += acc[a2][c2];
+                    }
                 }
         }
-        __syncthreads();
-        // position-force and position-position blocks of the foot-box rows: one thread per (foot, coord)
+        // position-force block of the foot-box rows: one thread per (foot, coord, force column)
+        for (int it = tid; it < kNumEE * 2 * nf; it += nth) {
+            const int j = it % nf, fc = it / nf, foot = fc >> 1, c = fc & 1;
+            const int pb = nf + s_pbase[foot] + c * s_npv[foot];
+            for (int kk = 0; kk < N - 3; ++kk) {
+                const int kf = kk * 4 + foot, e = kf * 2 + c;
+                const double om = S.wv[6 * ns + 2 * e] + S.wv[6 * ns + 2 * e + 1];
+                const double pj = om * S.phi[static_cast<size_t>(kk * 2 + c) * S.phi_stride + j];
+                for (int a = 0; a < S.pcnt[kf]; ++a) S.K[pk(pb + S.poff[kf] + a, j)] -= pj * S.pw[2 * kf + a];
+            }
+        }
+        // position-position block: one thread per (foot, coord)
         if (tid < kNumEE * 2) {
             const int foot = tid >> 1, c = tid & 1;
             const int pb = nf + s_pbase[foot] + c * s_npv[foot];
             for (int kk = 0; kk < N - 3; ++kk) {
-                const NodeLin& nl = nodes[kk + kEENodeStart];
-                const int e = (kk * 4 + foot) * 2 + c;
+                const int kf = kk * 4 + foot, e = kf * 2 + c;
                 const double om = S.wv[6 * ns + 2 * e] + S.wv[6 * ns + 2 * e + 1];
-                const double* row = phipos + static_cast<size_t>(kk * 2 + c) * L.max_nu;
-                for (int a = 0; a < nl.pcnt[foot]; ++a) {
-                    const int ca = pb + nl.poff[foot] + a;
-                    const double wa = om * nl.pw[foot][a];
-                    for (int j = 0; j < nf; ++j) S.K[pk(ca, j)] -= wa * row[j];
-                    for (int a2 = 0; a2 <= a; ++a2) S.K[pk(ca, pb + nl.poff[foot] + a2)] += wa * nl.pw[foot][a2];
-                }
+                for (int a = 0; a < S.pcnt[kf]; ++a)
+                    for (int a2 = 0; a2 <= a; ++a2)
+                        S.K[pk(pb + S.poff[kf] + a, pb + S.poff[kf] + a2)] += om * S.pw[2 * kf + a] * S.pw[2 * kf + a2];
             }
         }
-        // force samples: one thread per (foot, coord pair) owns a disjoint set of K entries
-        if (tid >= 32 && tid < 32 + kNumEE * 6) {
-            const int q = tid - 32, e = q / 6, cp = q % 6;
+        __syncthreads();
+        // force samples: one work item per K entry (foot, coord pair, variable pair); it sums over the foot's samples
+        for (int it = tid; it < kNumEE * 6 * 256; it += nth) {
+            const int i2 = it & 15, i = (it >> 4) & 15, cp = (it >> 8) % 6, e = it / (6 * 256);
+            if (i >= s_nfv[e] || i2 >= s_nfv[e]) continue;
             const int c1 = (cp < 3) ? cp : (cp == 3 ? 1 : 2);          // (0,0) (1,1) (2,2) (1,0) (2,0) (2,1)
             const int c2 = (cp < 3) ? cp : (cp == 5 ? 1 : 0);
-            for (int j = 0; j < ns; ++j) {
-                const Sample& sp = samples[j];
-                if (sp.ee != e || !sp.active) continue;
+            if (c1 == c2 && i2 > i) continue;
+            if (cp == 3) continue;                                     // x and y never share a row
+            double acc = 0;
+            for (int j = s_sb[e]; j < s_sb[e + 1]; ++j) {
+                const Sample& sp = S.smp[j];
+                const int a = i - sp.off, a2 = i2 - sp.off;
+                if (a < 0 || a >= sp.cnt || a2 < 0 || a2 >= sp.cnt || !sp.active) continue;
                 const double* w6 = S.wv + 6 * j;
-                // M = sum_r w_r c_r c_r' over the rows' coefficient 3-vectors
-                double Mcc;
-                if (c1 == 2 && c2 == 2) Mcc = (w6[0] + w6[1]) + mu_f * mu_f * (w6[2] + w6[3] + w6[4] + w6[5]);
-                else if (c1 == 0 && c2 == 0) Mcc = w6[2] + w6[3];
-                else if (c1 == 1 && c2 == 1) Mcc = w6[4] + w6[5];
-                else if (c1 == 1 && c2 == 0) Mcc = 0.0;
-                else if (c1 == 2 && c2 == 0) Mcc = -mu_f * (w6[2] - w6[3]);
+                double Mcc;   // sum_r w_r c_r c_r' over the six rows' coefficient 3-vectors
+                if (cp == 2) Mcc = (w6[0] + w6[1]) + mu_f * mu_f * (w6[2] + w6[3] + w6[4] + w6[5]);
+                else if (cp == 0) Mcc = w6[2] + w6[3];
+                else if (cp == 1) Mcc = w6[4] + w6[5];
+                else if (cp == 4) Mcc = -mu_f * (w6[2] - w6[3]);
                 else Mcc = -mu_f * (w6[4] - w6[5]);
-                if (Mcc == 0.0) continue;
-                const int r0 = s_fbase[e] + c1 * s_nfv[e] + sp.off, q0 = s_fbase[e] + c2 * s_nfv[e] + sp.off;
-                for (int a = 0; a < sp.cnt; ++a)
-                    for (int a2 = 0; a2 < sp.cnt; ++a2) {
-                        if (c1 == c2 && a2 > a) continue;
-                        S.K[pk(r0 + a, q0 + a2)] += Mcc * sp.w[a] * sp.w[a2];
-                    }
+                acc += Mcc * sp.w[a] * sp.w[a2];
             }
+            if (acc != 0.0) S.K[pk(s_fbase[e] + c1 * s_nfv[e] + i, s_fbase[e] + c2 * s_nfv[e] + i2)] += acc;
         }
         __syncthreads();
         if (tid == 0)
@@ -301,50 +374,183 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
                     }
             }
         __syncthreads();
-        // right-looking Cholesky, 16 x 16 thread tiling of the trailing update
+        // Blocked right-looking Cholesky on the packed lower triangle: 8-column panels, 4 x 4 register tiles in the
+        // trailing update (3 barriers per panel instead of 3 per column).
         if (tid == 0) s_flag = 0;
-        const int ty = tid >> 4, tx = tid & 15;
-        for (int j = 0; j < nu; ++j) {
-            __syncthreads();
-            const double djj = S.K[pk(j, j)];
-            if (!(djj > 0.0)) {
-                if (tid == 0) s_flag = 1;
-                break;
+        __syncthreads();
+        constexpr int NB = 8;
+        for (int b0 = 0; b0 < nu; b0 += NB) {
+            const int bs = (nu - b0 < NB) ? nu - b0 : NB;
+            // (1) factor the bs x bs diagonal block, one thread (short dependent chain, 36 entries)
+            if (tid == 0) {
+                for (int c = 0; c < bs; ++c) {
+                    double* Lc = S.K + pk(b0 + c, b0);
+                    double d = Lc[c];
+                    for (int k = 0; k < c; ++k) d -= Lc[k] * Lc[k];
+                    if (!(d > 0.0)) {
+                        s_flag = 1;
+                        d = 1.0;
+                    }
+                    const double dd = sqrt(d);
+                    Lc[c] = dd;
+                    const double inv = 1.0 / dd;
+                    for (int r = c + 1; r < bs; ++r) {
+                        double* Lr = S.K + pk(b0 + r, b0);
+                        double v = Lr[c];
+                        for (int k = 0; k < c; ++k) v -= Lr[k] * Lc[k];
+                        Lr[c] = v * inv;
+                    }
+                }
             }
-            const double inv = 1.0 / sqrt(djj);
             __syncthreads();
-            for (int i = j + tid; i < nu; i += nth) S.K[pk(i, j)] = (i == j) ? sqrt(djj) : S.K[pk(i, j)] * inv;
+            // (2) panel below the block: row i solves L[i, b] = A[i, b] L_bb^-T, one thread per row
+            for (int i = b0 + bs + tid; i < nu; i += nth) {
+                double* Li = S.K + pk(i, b0);
+                double row[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) row[c] = (c < bs) ? Li[c] : 0.0;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    if (c < bs) {
+                        const double* Lc = S.K + pk(b0 + c, b0);
+                        double v = row[c];
+#pragma unroll
+                        for (int k = 0; k < NB; ++k)
+                            if (k < c) v -= row[k] * Lc[k];
+                        row[c] = v / Lc[c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c < bs) Li[c] = row[c];
+            }
             __syncthreads();
-            for (int i = j + 1 + ty; i < nu; i += 16) {
-                const double lij = S.K[pk(i, j)];
-                const int rb = i * (i + 1) / 2;
-                for (int l = j + 1 + tx; l <= i; l += 16) S.K[rb + l] -= lij * S.K[pk(l, j)];
+            // (3) trailing update A[i][l] -= sum_c L[i][b0+c] L[l][b0+c], 4 x 4 tiles, 16 x 16 threads over the tile grid
+            const int t0 = b0 + bs;
+            if (t0 < nu) {
+                const int side = (nu - t0 + 3) >> 2;
+                const int ty = tid >> 4, tx = tid & 15;
+                for (int ti = ty; ti < side; ti += 16)
+                    for (int tl = tx; tl <= ti; tl += 16) {
+                        const int i0 = t0 + 4 * ti, l0 = t0 + 4 * tl;
+                        double acc[4][4];
+#pragma unroll
+                        for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                            for (int c2 = 0; c2 < 4; ++c2) acc[a2][c2] = 0.0;
+#pragma unroll
+                        for (int h = 0; h < NB; h += 4) {
+                            double ra[4][4], rc[4][4];
+#pragma unroll
+                            for (int a2 = 0; a2 < 4; ++a2) {
+                                const int ii = (i0 + a2 < nu) ? i0 + a2 : nu - 1, ll = (l0 + a2 < nu) ? l0 + a2 : nu - 1;
+                                const double* pa = S.K + pk(ii, b0 + h);
+                                const double* pc = S.K + pk(ll, b0 + h);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    ra[a2][k] = (h + k < bs) ? pa[k] : 0.0;
+                                    rc[a2][k] = (h + k < bs) ? pc[k] : 0.0;
+                                }
+                            }
+#pragma unroll
+                            for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                                for (int c2 = 0; c2 < 4; ++c2)
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) acc[a2][c2] += ra[a2][k] * rc[c2][k];
+                        }
+#pragma unroll
+                        for (int a2 = 0; a2 < 4; ++a2) {
+                            const int ii = i0 + a2;
+                            if (ii >= nu) continue;
+                            double* Ki = S.K + ii * (ii + 1) / 2;
+#pragma unroll
+                            for (int c2 = 0; c2 < 4; ++c2) {
+                                const int ll = l0 + c2;
+                                if (ll <= ii) Ki[ll] -= acc[a2][c2];
+                            }
+                        }
+                    }
+            }
+            __syncthreads();
+        }
+        // Invert the 16 x 16 diagonal blocks of the factor in place (they are only ever used through their inverse by
+        // the blocked substitutions below): half a warp per block, lane = column.
+        constexpr int SB = 16;
+        const int nblk = (nu + SB - 1) / SB;
+        for (int bb = wid; bb < nblk; bb += nwarp) {
+            const int r0 = bb * SB, bsz = (nu - r0 < SB) ? nu - r0 : SB;
+            double x[SB];
+            if (lane < bsz) {
+#pragma unroll
+                for (int rr = 0; rr < SB; ++rr) {
+                    x[rr] = 0.0;
+                    if (rr < bsz && rr >= lane) {
+                        const double* Lr = S.K + pk(r0 + rr, r0);
+                        double acc = (rr == lane) ? 1.0 : 0.0;
+#pragma unroll
+                        for (int k = 0; k < SB; ++k)
+                            if (k < rr && k >= lane) acc -= Lr[k] * x[k];
+                        x[rr] = acc / Lr[rr];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane < bsz) {
+#pragma unroll
+                for (int rr = 0; rr < SB; ++rr)
+                    if (rr < bsz && rr >= lane) S.K[pk(r0 + rr, r0 + lane)] = x[rr];
             }
         }
         __syncthreads();
         return s_flag == 0;
     };
-    // solve K x = rhs in place (x overwrites v) with the packed factor: one warp, shuffle reductions
+    // Solve K x = v in place with the packed factor whose 16 x 16 diagonal blocks hold their inverses: blocked forward
+    // and backward substitution, 16 rows x 16 threads per block step, half-warp shuffle reductions.
+    auto red16 = [](double v) {
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        return v;
+    };
     auto chol_solve = [&](double* v) {
+        constexpr int SB = 16;
+        const int nblk = (nu + SB - 1) / SB;
+        const int r = tid >> 4, sx = tid & 15;
+        double* tb = S.red;   // 16 doubles of scratch (block_reduce is not running concurrently)
         __syncthreads();
-        if (wid == 0) {
-            for (int i = 0; i < nu; ++i) {
+        for (int bb = 0; bb < nblk; ++bb) {   // L y = v
+            const int i = bb * SB + r;
+            double acc = 0;
+            if (i < nu) {
                 const double* Li = S.K + i * (i + 1) / 2;
-                double s = 0;
-                for (int j = lane; j < i; j += 32) s += Li[j] * v[j];
-                s = warp_sum(s);
-                if (lane == 0) v[i] = (v[i] - s) / Li[i];
-                __syncwarp();
+                for (int j = sx; j < bb * SB; j += 16) acc += Li[j] * v[j];
             }
-            for (int i = nu - 1; i >= 0; --i) {
-                double s = 0;
-                for (int j = i + 1 + lane; j < nu; j += 32) s += S.K[pk(j, i)] * v[j];
-                s = warp_sum(s);
-                if (lane == 0) v[i] = (v[i] - s) / S.K[pk(i, i)];
-                __syncwarp();
-            }
+            acc = red16(acc);
+            if (sx == 0 && i < nu) tb[r] = v[i] - acc;
+            __syncthreads();
+            double y = 0;
+            if (i < nu && sx <= r) y = S.K[pk(i, bb * SB + sx)] * tb[sx];
+            y = red16(y);
+            if (sx == 0 && i < nu) v[i] = y;
+            __syncthreads();
         }
-        __syncthreads();
+        for (int bb = nblk - 1; bb >= 0; --bb) {   // L' x = y
+            const int i = bb * SB + r;
+            double acc = 0;
+            if (i < nu)
+                for (int j = (bb + 1) * SB + sx; j < nu; j += 16) acc += S.K[pk(j, i)] * v[j];
+            acc = red16(acc);
+            if (sx == 0 && i < nu) tb[r] = v[i] - acc;
+            __syncthreads();
+            double y = 0;
+            const int jj = bb * SB + sx;
+            if (i < nu && jj < nu && sx >= r) y = S.K[pk(jj, i)] * tb[sx];   // X' : entry (r, sx) = X[sx][r]
+            y = red16(y);
+            if (sx == 0 && i < nu) v[i] = y;
+            __syncthreads();
+        }
     };
 
     // ------------------------------------------------------------------------------------------------ start point
@@ -586,7 +792,7 @@ void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, cudaStream_
         cudaFuncSetAttribute(k_ipm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         configured = smem;
     }
-    k_ipm<<<B, 256, smem, stream>>>(P, L, ws);
+    k_ipm<<<B, 256, smem, stream>>>(P, L, ws, ipm_stage_phipos(L) ? 1 : 0);
 }
 
 }  // namespace bgg
