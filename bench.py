@@ -126,6 +126,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
     ap.add_argument("--config", default="a1_configuration", choices=sorted(wl.CONFIGS))
     ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--ipm-refine", type=int, default=0, help="0 = library default, -1 = no refinement")
+    ap.add_argument("--max-spline-vars", type=int, default=0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -168,7 +170,8 @@ def main():
 
     B, N = args.batch, cfg["num_nodes"]
     states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=1000 + rank)
-    mpc = bg.BatchedMPC(N, cfg["integrator_dt"], wl.robot(), device=local_rank, **wl.mpc_kwargs(cfg))
+    mpc = bg.BatchedMPC(N, cfg["integrator_dt"], wl.robot(), device=local_rank, ipm_refine=args.ipm_refine,
+                        max_spline_vars=args.max_spline_vars, **wl.mpc_kwargs(cfg))
     mpc.AddQuadraticTrackingCost(wl.target_tangent(cfg), np.asarray(cfg["Q"], float))
     mpc.Reset(B)
     mpc.SetStateTrajectoryWarmStart(states)

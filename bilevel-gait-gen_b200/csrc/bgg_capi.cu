@@ -36,6 +36,8 @@ struct bgg_handle {
     double *h_state = nullptr, *h_t0 = nullptr, *h_ee = nullptr;
     WsHeader* h_hdr = nullptr;   // pinned [batch]
     WsHeader* d_hdr = nullptr;   // compact copy of the headers [batch]
+    int* d_max = nullptr;        // batch maxima (nu, n_samples) of the current solve
+    int* h_max = nullptr;        // pinned
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
@@ -158,6 +160,8 @@ int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) 
     }
     for (auto& e : h->ev) cudaEventCreate(&e);
     for (auto& e : h->user_ev) cudaEventCreate(&e);
+    cudaMalloc(&h->d_max, 2 * sizeof(int));
+    cudaMallocHost(&h->h_max, 2 * sizeof(int));
     *out = h;
     return BGG_OK;
 }
@@ -191,6 +195,8 @@ void bgg_destroy(bgg_handle* h) {
         if (e) cudaEventDestroy(e);
     for (auto& e : h->user_ev)
         if (e) cudaEventDestroy(e);
+    cudaFree(h->d_max);
+    cudaFreeHost(h->h_max);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -289,14 +295,19 @@ int bgg_solve_resident(bgg_handle* h) {
     const int B = h->batch;
     if (h->profiling) cudaEventRecord(h->ev[0], h->stream);
     launch_prepare(h->P, h->d_inst, h->d_state, h->d_t0, h->d_ee, h->L, h->d_ws, B, h->stream);
+    // shared memory (and with it the number of CTAs per SM) is sized from this batch's actual problem sizes
+    launch_batch_max(h->L, h->d_ws, B, h->d_max, h->stream);
+    CU(cudaMemcpyAsync(h->h_max, h->d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     if (h->profiling) cudaEventRecord(h->ev[1], h->stream);
-    launch_condense(h->P, h->L, h->d_ws, B, h->stream);
+    CU(cudaStreamSynchronize(h->stream));
+    const int nu_max = h->h_max[0] > 0 ? h->h_max[0] : 8, ns_max = h->h_max[1];
+    launch_condense(h->P, h->L, h->d_ws, B, nu_max, h->stream);
     if (h->profiling) cudaEventRecord(h->ev[2], h->stream);
-    launch_ipm(h->P, h->L, h->d_ws, B, h->stream);
+    launch_ipm(h->P, h->L, h->d_ws, B, nu_max, ns_max, h->stream);
     if (h->profiling) cudaEventRecord(h->ev[3], h->stream);
     launch_finish(h->P, h->d_inst, h->L, h->d_ws, B, h->stream);
     if (h->profiling) cudaEventRecord(h->ev[4], h->stream);
-    h->launches += 4;
+    h->launches += 5;
     CU(cudaGetLastError());
     return BGG_OK;
 }

@@ -20,12 +20,16 @@ __device__ __forceinline__ void cross3d(const double a[3], const double b[3], do
     o[2] = a[0] * b[1] - a[1] * b[0];
 }
 
+static size_t condense_smem_for(int nu_cap) {
+    const size_t nu = nu_cap;
+    return 8 * (nu * (nu + 1) / 2 + 2 * kNx * nu + nu + 4 * kNx) + sizeof(NodeLin) + 256;
+}
 size_t condense_smem_bytes(const WsLayout& L) {
     const size_t nu = L.max_nu;
     return 8 * (nu * (nu + 1) / 2 + 2 * kNx * nu + nu + 4 * kNx) + sizeof(NodeLin) + 256;
 }
 
-__global__ void __launch_bounds__(256) k_condense(Params P, WsLayout L, char* __restrict__ ws_base) {
+__global__ void __launch_bounds__(256) k_condense(Params P, WsLayout L, char* __restrict__ ws_base, int cap_nu) {
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
     WsHeader* Hd = reinterpret_cast<WsHeader*>(ws + L.hdr);
@@ -41,9 +45,9 @@ __global__ void __launch_bounds__(256) k_condense(Params P, WsLayout L, char* __
     const int npk = nu * (nu + 1) / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Hp = reinterpret_cast<double*>(smem_raw);          // packed lower triangle
-    double* Phi = Hp + L.max_nu * (L.max_nu + 1) / 2;          // [2][12][nu]
-    double* gs = Phi + 2 * kNx * L.max_nu;                     // [nu]
-    double* phi = gs + L.max_nu;                               // [2][12]
+    double* Phi = Hp + cap_nu * (cap_nu + 1) / 2;              // [2][12][nu]
+    double* gs = Phi + 2 * kNx * cap_nu;                       // [nu]
+    double* phi = gs + cap_nu;                                 // [2][12]
     double* pq = phi + 2 * kNx;                                // [2][12]: P_k (diag) and P_k phi_k + q_k
     NodeLin* nl = reinterpret_cast<NodeLin*>(pq + 2 * kNx);
     __shared__ int s_fbase[kNumEE], s_pbase[kNumEE], s_nfv[kNumEE], s_npv[kNumEE];
@@ -171,14 +175,30 @@ __global__ void __launch_bounds__(256) k_condense(Params P, WsLayout L, char* __
     }
 }
 
-void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, cudaStream_t stream) {
-    const size_t smem = condense_smem_bytes(L);
+void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, cudaStream_t stream) {
+    int cap = (nu_max + 7) / 8 * 8;
+    if (cap > L.max_nu) cap = L.max_nu;
+    const size_t smem = condense_smem_for(cap);
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(k_condense, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         configured = smem;
     }
-    k_condense<<<B, 256, smem, stream>>>(P, L, ws);
+    k_condense<<<B, 256, smem, stream>>>(P, L, ws, cap);
+}
+
+__global__ void k_batch_max(WsLayout L, const char* __restrict__ ws, int B, int* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const WsHeader* h = reinterpret_cast<const WsHeader*>(ws + static_cast<size_t>(b) * L.stride + L.hdr);
+    if (h->error) return;
+    atomicMax(&out[0], h->nu);
+    atomicMax(&out[1], h->n_samples);
+}
+
+void launch_batch_max(const WsLayout& L, const char* ws, int B, int* out, cudaStream_t stream) {
+    cudaMemsetAsync(out, 0, 2 * sizeof(int), stream);
+    k_batch_max<<<(B + 255) / 256, 256, 0, stream>>>(L, ws, B, out);
 }
 
 // ---- parity tap: dense Ad [N][12][12], Bd [N][12][nu_stride], cd [N][12] per instance (what the reference holds in

@@ -37,18 +37,37 @@ __device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; } 
 
 }  // namespace
 
-static size_t ipm_smem_core(const WsLayout& L) {
-    const size_t nu = L.max_nu, m = L.max_rows, kc = 2 * (L.N - 3), eb = 4 * (L.N - 3);
-    return 8 * (nu * (nu + 1) / 2 + 6 * nu + 7 * m + 2 * kc + 3 * kMaxEq + 40 + 2 * eb) + 8 * eb + sizeof(Sample) * kMaxSamples + 64;
+struct IpmCaps {          // per-launch shared-memory sizing, from the actual maxima over the batch
+    int nu, rows, ns, stage_phi;
+};
+static size_t ipm_smem_core(int N, int nu, int rows, int ns) {
+    const size_t kc = 2 * (N - 3), eb = 4 * (N - 3);
+    return 8 * (static_cast<size_t>(nu) * (nu + 1) / 2 + 6 * nu + 6 * static_cast<size_t>(rows) + 2 * eb * 2 + 2 * kc + 3 * kMaxEq + 40 + 2 * eb) +
+           8 * eb + sizeof(Sample) * static_cast<size_t>(ns) + 64;
 }
-static bool ipm_stage_phipos(const WsLayout& L) {   // keep the dense position rows on chip when they fit
-    return ipm_smem_core(L) + 8 * static_cast<size_t>(2 * (L.N - 3)) * L.max_nu <= 225 * 1024;
+static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max) {
+    IpmCaps c;
+    c.nu = (nu_max + 7) / 8 * 8;
+    if (c.nu > L.max_nu) c.nu = L.max_nu;
+    c.ns = ns_max < 1 ? 1 : ns_max;
+    c.rows = 6 * c.ns + 2 * (L.N - 3) * 8;
+    const size_t core = ipm_smem_core(L.N, c.nu, c.rows, c.ns);
+    const size_t phi = 8 * static_cast<size_t>(2 * (L.N - 3)) * c.nu;
+    // two CTAs per SM when the core fits twice into the 227 KB; the dense position rows are staged on chip only
+    // if that does not cost the second CTA
+    const size_t half = 113 * 1024;
+    if (core <= half) c.stage_phi = (core + phi <= half) ? 1 : 0;
+    else c.stage_phi = (core + phi <= 225 * 1024) ? 1 : 0;
+    return c;
 }
-size_t ipm_smem_bytes(const WsLayout& L) {
-    return ipm_smem_core(L) + (ipm_stage_phipos(L) ? 8 * static_cast<size_t>(2 * (L.N - 3)) * L.max_nu : 0);
+static size_t ipm_smem_for(const WsLayout& L, const IpmCaps& c) {
+    return ipm_smem_core(L.N, c.nu, c.rows, c.ns) + (c.stage_phi ? 8 * static_cast<size_t>(2 * (L.N - 3)) * c.nu : 0);
+}
+size_t ipm_smem_bytes(const WsLayout& L) {   // worst case for the configured caps (bgg_create's feasibility check)
+    return ipm_smem_core(L.N, L.max_nu, L.max_rows, kMaxSamples);
 }
 
-__global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi) {
+__global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi, int cap_nu, int cap_rows) {
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
@@ -74,11 +93,12 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
     Smem S;
     {
         double* p = reinterpret_cast<double*>(smem_raw);
-        S.K = p; p += L.max_nu * (L.max_nu + 1) / 2;
-        S.u = p; p += L.max_nu; S.du = p; p += L.max_nu; S.rd = p; p += L.max_nu;
-        S.rhs = p; p += L.max_nu; S.g = p; p += L.max_nu; S.tmpn = p; p += L.max_nu;
-        S.s = p; p += L.max_rows; S.lam = p; p += L.max_rows; S.ds = p; p += L.max_rows; S.dl = p; p += L.max_rows;
-        S.rp = p; p += L.max_rows; S.wv = p; p += L.max_rows; S.d = p; p += L.max_rows;
+        S.K = p; p += cap_nu * (cap_nu + 1) / 2;
+        S.u = p; p += cap_nu; S.du = p; p += cap_nu; S.rd = p; p += cap_nu;
+        S.rhs = p; p += cap_nu; S.g = p; p += cap_nu; S.tmpn = p; p += cap_nu;
+        S.s = p; p += cap_rows; S.lam = p; p += cap_rows; S.ds = p; p += cap_rows; S.dl = p; p += cap_rows;
+        S.rp = p; p += cap_rows; S.wv = p; p += cap_rows;
+        S.d = p; p += 2 * 8 * (N - 3);   // right-hand sides of the foot-box rows only (force rows: see rhs_of)
         S.tkc = p; p += nkc; S.ckc = p; p += nkc;
         S.nueq = p; p += kMaxEq; S.re = p; p += kMaxEq; S.dnu = p; p += kMaxEq;
         S.red = p; p += 40;
@@ -87,7 +107,7 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         S.poff = S.pcnt + 4 * (N - 3);
         p += 4 * (N - 3);
         S.smp = reinterpret_cast<Sample*>(p);
-        p += sizeof(Sample) * kMaxSamples / 8;
+        p += (sizeof(Sample) * static_cast<size_t>(ns) + 7) / 8;
         if (stage_phi) {
             S.phi = p;
             S.phi_stride = nf;
@@ -110,6 +130,8 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
     __shared__ int s_fbase[kNumEE], s_pbase[kNumEE], s_nfv[kNumEE], s_npv[kNumEE];
     __shared__ int s_flag;
     __shared__ int s_sb[kNumEE + 1];   // per-foot sample ranges (samples are stored foot-major)
+    __shared__ EqRow s_eq[kMaxEq];
+    if (tid < neq) s_eq[tid] = eqs[tid];
     if (tid < kNumEE) {
         s_fbase[tid] = Hd->fbase[tid];
         s_pbase[tid] = Hd->pbase[tid];
@@ -125,25 +147,25 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         while (e < kNumEE) s_sb[++e] = ns;
     }
 
-    // ---- right-hand sides d (and the active mask: wv < 0 marks an inactive row while setting up)
+    // ---- right-hand sides d and the active mask (wv = 1 / 0 while setting up).  Force rows have the fixed pattern
+    // (force_bound, 0, 0, 0, 0, 0) per sample; only the foot-box right-hand sides are stored.
     const double box0 = Hd->ee_box[0] / 2, box1 = Hd->ee_box[1] / 2;
+    const double fbound = P.force_bound;
+    const int m_force = 6 * ns;
     for (int j = tid; j < ns; j += nth) {
         const bool act = samples[j].active != 0;
-        double* dj = S.d + 6 * j;
-        dj[0] = P.force_bound;
-        dj[1] = 0.0;
-        dj[2] = dj[3] = dj[4] = dj[5] = 0.0;
         for (int r = 0; r < 6; ++r) S.wv[6 * j + r] = act ? 1.0 : 0.0;
     }
     for (int e = tid; e < ne; e += nth) {
         const int c = e & 1, foot = (e >> 1) & 3, kk = e >> 3;   // node k = kk + 4
         const double bx = c ? box1 : box0;
         const double off = xoff[(kk + kEENodeStart) * kNx + c];
-        S.d[6 * ns + 2 * e + 0] = (bx + P.hip_xy[foot][c]) + off;
-        S.d[6 * ns + 2 * e + 1] = -(-bx + P.hip_xy[foot][c]) - off;
-        S.wv[6 * ns + 2 * e + 0] = 1.0;
-        S.wv[6 * ns + 2 * e + 1] = 1.0;
+        S.d[2 * e + 0] = (bx + P.hip_xy[foot][c]) + off;
+        S.d[2 * e + 1] = -(-bx + P.hip_xy[foot][c]) - off;
+        S.wv[m_force + 2 * e + 0] = 1.0;
+        S.wv[m_force + 2 * e + 1] = 1.0;
     }
+    auto rhs_of = [&](int i) -> double { return (i < m_force) ? ((i % 6 == 0) ? fbound : 0.0) : S.d[i - m_force]; };
     __syncthreads();
 
     // ------------------------------------------------------------------------------------------------ operators
@@ -245,7 +267,7 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
     // re = E v - e (or E v when rhs == false) ; out += E' y
     auto apply_E = [&](const double* v, double* out, bool with_rhs) {
         if (tid < neq) {
-            const EqRow& q = eqs[tid];
+            const EqRow& q = s_eq[tid];
             double s = with_rhs ? -q.rhs : 0.0;
             for (int i = 0; i < q.cnt; ++i) s += q.w[i] * v[q.col[i]];
             out[tid] = s;
@@ -253,9 +275,10 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         __syncthreads();
     };
     auto add_Et = [&](const double* y, double* out, double scale) {
-        if (tid == 0)
+        if (tid < kNumEE * 2)   // one thread per (foot, coord): rows of different groups touch different columns
             for (int r = 0; r < neq; ++r) {
-                const EqRow& q = eqs[r];
+                const EqRow& q = s_eq[r];
+                if (q.pad != tid) continue;
                 for (int i = 0; i < q.cnt; ++i) out[q.col[i]] += scale * y[r] * q.w[i];
             }
         __syncthreads();
@@ -364,9 +387,10 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
             if (acc != 0.0) S.K[pk(s_fbase[e] + c1 * s_nfv[e] + i, s_fbase[e] + c2 * s_nfv[e] + i2)] += acc;
         }
         __syncthreads();
-        if (tid == 0)
+        if (tid < kNumEE * 2)
             for (int r = 0; r < neq; ++r) {
-                const EqRow& q = eqs[r];
+                const EqRow& q = s_eq[r];
+                if (q.pad != tid) continue;
                 for (int a = 0; a < q.cnt; ++a)
                     for (int a2 = 0; a2 <= a; ++a2) {
                         const int ia = q.col[a], ib = q.col[a2];
@@ -381,26 +405,29 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         constexpr int NB = 8;
         for (int b0 = 0; b0 < nu; b0 += NB) {
             const int bs = (nu - b0 < NB) ? nu - b0 : NB;
-            // (1) factor the bs x bs diagonal block, one thread (short dependent chain, 36 entries)
-            if (tid == 0) {
-                for (int c = 0; c < bs; ++c) {
-                    double* Lc = S.K + pk(b0 + c, b0);
-                    double d = Lc[c];
-                    for (int k = 0; k < c; ++k) d -= Lc[k] * Lc[k];
-                    if (!(d > 0.0)) {
-                        s_flag = 1;
-                        d = 1.0;
-                    }
-                    const double dd = sqrt(d);
-                    Lc[c] = dd;
-                    const double inv = 1.0 / dd;
-                    for (int r = c + 1; r < bs; ++r) {
-                        double* Lr = S.K + pk(b0 + r, b0);
-                        double v = Lr[c];
-                        for (int k = 0; k < c; ++k) v -= Lr[k] * Lc[k];
-                        Lr[c] = v * inv;
+            // (1) factor the bs x bs diagonal block inside warp 0: lane r owns row r, right-looking with shuffles
+            if (wid == 0) {
+                double a8[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) a8[c] = (lane < bs && c <= lane && c < bs) ? S.K[pk(b0 + lane, b0 + c)] : 0.0;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    if (c < bs) {
+                        const double d = __shfl_sync(0xffffffffu, a8[c], c);
+                        const bool bad = !(d > 0.0);
+                        if (bad && lane == 0) s_flag = 1;
+                        const double inv = bad ? 1.0 : rsqrt(d);
+                        a8[c] = (lane == c) ? d * inv : a8[c] * inv;
+#pragma unroll
+                        for (int c2 = c + 1; c2 < NB; ++c2) {
+                            const double t = __shfl_sync(0xffffffffu, a8[c], c2);   // L[c2][c]
+                            if (lane >= c2) a8[c2] -= a8[c] * t;
+                        }
                     }
                 }
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (lane < bs && c <= lane && c < bs) S.K[pk(b0 + lane, b0 + c)] = a8[c];
             }
             __syncthreads();
             // (2) panel below the block: row i solves L[i, b] = A[i, b] L_bb^-T, one thread per row
@@ -557,8 +584,8 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
     // u0 = argmin of the equality/inequality-penalised quadratic: (H + C'C + E'E/delta) u = -g + C'd + E'e/delta
     bool ok = build_and_factor();
     for (int i = tid; i < nu; i += nth) S.rhs[i] = -S.g[i];
-    for (int i = tid; i < m; i += nth) S.rp[i] = (S.wv[i] != 0.0) ? S.d[i] : 0.0;
-    if (tid < neq) S.re[tid] = eqs[tid].rhs;
+    for (int i = tid; i < m; i += nth) S.rp[i] = (S.wv[i] != 0.0) ? rhs_of(i) : 0.0;
+    if (tid < neq) S.re[tid] = s_eq[tid].rhs;
     __syncthreads();
     add_Ct(S.rp, S.rhs);
     add_Et(S.re, S.rhs, inv_delta);
@@ -568,7 +595,7 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
     double mn = 1e300;
     for (int i = tid; i < m; i += nth)
         if (S.wv[i] != 0.0) {
-            S.s[i] = S.d[i] - S.ds[i];
+            S.s[i] = rhs_of(i) - S.ds[i];
             mn = fmin(mn, S.s[i]);
         }
     mn = block_reduce<kMin>(mn, S.red);
@@ -609,13 +636,13 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
     {
         double v = 0;
         for (int i = tid; i < m; i += nth)
-            if (S.wv[i] != 0.0) v = fmax(v, fabs(S.d[i]));
+            if (S.wv[i] != 0.0) v = fmax(v, fabs(rhs_of(i)));
         nrm_d = fmax(1.0, block_reduce<kMax>(v, S.red));
     }
 
     // ------------------------------------------------------------------------------------------------ main loop
     int it = 0, status = kMaxIter;
-    double n_rd = 0, n_rp = 0, n_re = 0, mu = 0, gap_scale = 1, qp_obj = 0, last_rp = 0, last_re = 0;
+    double n_rd = 0, n_rp = 0, n_re = 0, mu = 0, gap_scale = 1, qp_obj = 0, last_rp = 0, last_re = 0, last_rd = 0, last_mu = 0;
     for (it = 0; it <= P.ipm_max_iter; ++it) {
         // residuals: rd = H u + g + C'lam + E'nu ; rp = C u + s - d ; re = E u - e
         apply_H(S.u, S.rd);
@@ -634,16 +661,33 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         for (int i = tid; i < nu; i += nth) a = fmax(a, fabs(S.rd[i]));
         for (int i = tid; i < m; i += nth) {
             if (S.lam[i] > 0.0) {   // active row (inactive rows keep lam == 0 exactly)
-                S.rp[i] = S.rp[i] + S.s[i] - S.d[i];
+                S.rp[i] = S.rp[i] + S.s[i] - rhs_of(i);
                 c = fmax(c, fabs(S.rp[i]));
                 dsum += S.s[i] * S.lam[i];
             } else {
                 S.rp[i] = 0.0;
             }
         }
-        n_rd = block_reduce<kMax>(a, S.red);
-        n_rp = block_reduce<kMax>(c, S.red);
-        dsum = block_reduce<kSum>(dsum, S.red);
+        {   // one pass for the three reductions: two maxima and a sum
+            a = warp_max(a);
+            c = warp_max(c);
+            dsum = warp_sum(dsum);
+            __syncthreads();
+            if (lane == 0) {
+                S.red[wid] = a;
+                S.red[8 + wid] = c;
+                S.red[16 + wid] = dsum;
+            }
+            __syncthreads();
+            a = c = dsum = 0;
+            for (int w = 0; w < nwarp; ++w) {
+                a = fmax(a, S.red[w]);
+                c = fmax(c, S.red[8 + w]);
+                dsum += S.red[16 + w];
+            }
+            n_rd = a;
+            n_rp = c;
+        }
         mu = dsum / m_act;
         n_re = 0;
         for (int r = 0; r < neq; ++r) n_re = fmax(n_re, fabs(S.re[r]));
@@ -653,10 +697,14 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
             status = kOther;
             n_rp = last_rp;
             n_re = last_re;
+            n_rd = last_rd;
+            mu = last_mu;
             break;
         }
         last_rp = n_rp;
         last_re = n_re;
+        last_rd = n_rd;
+        last_mu = mu;
         if (n_rd <= P.ipm_tol_feas * nrm_q && n_rp <= P.ipm_tol_feas * nrm_d && n_re <= P.ipm_tol_feas * nrm_d &&
             dsum <= P.ipm_tol_gap * gap_scale) {
             status = kSolved;
@@ -668,7 +716,7 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         for (int i = tid; i < m; i += nth) S.wv[i] = (S.lam[i] > 0.0) ? S.lam[i] / S.s[i] : 0.0;
         __syncthreads();
         ok = build_and_factor();
-        if (!ok) {
+        if (!ok) {   // residuals of this iteration are valid; classify at exit
             status = kOther;
             break;
         }
@@ -751,14 +799,17 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
         if (tid < neq) S.nueq[tid] += alpha * S.dnu[tid];
         __syncthreads();
     }
-    // a diverging iteration on a problem whose primal residual never came down: infeasible (no homogeneous embedding)
-    if (status == kOther && (n_rp > 1e-4 * nrm_d || n_re > 1e-4 * nrm_d)) status = kPrimalInfeasible;
-    if (status == kMaxIter) {
+    // Exit classification when the iteration stopped without meeting the tolerances (iteration limit, or a
+    // factorisation / NaN breakdown once the scaling W = lam/s has blown up):
+    //  * residuals within 1e3 x the tolerances         -> SolvedInacc (Clarabel's "AlmostSolved")
+    //  * primal residual still far from feasible        -> PrimalInfeasible (multipliers diverge on an infeasible QP;
+    //                                                      Clarabel certifies this through its homogeneous embedding)
+    if (status == kMaxIter || status == kOther) {
         const double loose = 1e3;
         if (n_rd <= loose * P.ipm_tol_feas * nrm_q && n_rp <= loose * P.ipm_tol_feas * nrm_d &&
             n_re <= loose * P.ipm_tol_feas * nrm_d && mu * m_act <= loose * P.ipm_tol_gap * gap_scale)
             status = kSolvedInacc;
-        else if (n_rp > 1e-4 * nrm_d || n_re > 1e-4 * nrm_d)
+        else if (n_rp > loose * P.ipm_tol_feas * nrm_d || n_re > loose * P.ipm_tol_feas * nrm_d)
             status = kPrimalInfeasible;
     }
 
@@ -770,7 +821,7 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
     for (int i = tid; i < nu; i += nth) uo[i] = S.u[i];
     for (int i = tid; i < m; i += nth) {
         lo[i] = S.lam[i];
-        so[i] = (S.lam[i] > 0.0 || S.s[i] != 1.0) ? S.s[i] : S.d[i];   // inactive rows: slack = d (row is 0 <= d)
+        so[i] = (S.lam[i] > 0.0 || S.s[i] != 1.0) ? S.s[i] : rhs_of(i);   // inactive rows: slack = d (row is 0 <= d)
     }
     if (tid < neq) no[tid] = S.nueq[tid];
     if (tid == 0) {
@@ -785,14 +836,15 @@ __global__ void __launch_bounds__(256) k_ipm(Params P, WsLayout L, char* __restr
     (void)npk;
 }
 
-void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, cudaStream_t stream) {
-    const size_t smem = ipm_smem_bytes(L);
+void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, cudaStream_t stream) {
+    const IpmCaps c = ipm_caps(L, nu_max, ns_max);
+    const size_t smem = ipm_smem_for(L, c);
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(k_ipm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         configured = smem;
     }
-    k_ipm<<<B, 256, smem, stream>>>(P, L, ws, ipm_stage_phipos(L) ? 1 : 0);
+    k_ipm<<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows);
 }
 
 }  // namespace bgg

@@ -45,8 +45,10 @@ __device__ __forceinline__ double block_reduce(double v, double* scratch) {
 // kernel launchers (each is asynchronous on `stream`)
 void launch_prepare(const Params& P, Instance* inst, const double* state, const double* t0, const double* ee_start,
                     const WsLayout& L, char* ws, int B, cudaStream_t stream);
-void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, cudaStream_t stream);
-void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, cudaStream_t stream);
+void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, cudaStream_t stream);
+void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, cudaStream_t stream);
+// max over the batch of (nu, n_samples) after launch_prepare, written to out[0..1] (device)
+void launch_batch_max(const WsLayout& L, const char* ws, int B, int* out, cudaStream_t stream);
 void launch_finish(const Params& P, Instance* inst, const WsLayout& L, char* ws, int B, cudaStream_t stream);
 size_t ipm_smem_bytes(const WsLayout& L);
 size_t condense_smem_bytes(const WsLayout& L);

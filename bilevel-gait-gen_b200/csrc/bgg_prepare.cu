@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(128) k_prepare(Params P, Instance* __restrict_
             for (int c = 0; c < 2; ++c) {
                 EqRow& q = eqs[r++];
                 q.cnt = cnt;
+                q.pad = e * 2 + c;   // rows of one (foot, coord) only touch that pair's position variables
                 q.rhs = value_at(sf[e], false, c, td);
                 for (int j = 0; j < 2; ++j) {
                     q.w[j] = (j < cnt) ? w[j] : 0.0;
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(128) k_prepare(Params P, Instance* __restrict_
             for (int c = 0; c < 2; ++c) {
                 EqRow& q = eqs[r++];
                 q.cnt = cnt;
+                q.pad = e * 2 + c;
                 q.rhs = ee_start[(b * kNumEE + e) * 3 + c];
                 for (int j = 0; j < 2; ++j) {
                     q.w[j] = (j < cnt) ? w[j] : 0.0;

@@ -52,7 +52,7 @@ struct EqRow {                // touch-down / foot-start rows: w . u_pos[col] = 
     double w[2];
     double rhs;
     int32_t col[2];           // column inside the spline variables (>= nf)
-    int32_t cnt, pad;
+    int32_t cnt, pad;         // pad: (foot * 2 + coord) group of the row
 };
 
 constexpr int kMaxEq = 16;

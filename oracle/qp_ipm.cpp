@@ -185,7 +185,7 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
 
     res.status = MaxIter;
     int it = 0;
-    double n_rd = 0, n_rp = 0, n_re = 0, mu = 0, gscale = 1, last_rp = 0, last_re = 0;
+    double n_rd = 0, n_rp = 0, n_re = 0, mu = 0, gscale = 1, last_rp = 0, last_re = 0, last_rd = 0, last_mu = 0;
     for (it = 0; it <= st.max_iter; it++) {
         P.mul(z.data(), Pz.data());
         double pobj = 0;
@@ -210,10 +210,14 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
             res.status = Other;
             n_rp = last_rp;
             n_re = last_re;
+            n_rd = last_rd;
+            mu = last_mu;
             break;
         }
         last_rp = n_rp;
         last_re = n_re;
+        last_rd = n_rd;
+        last_mu = mu;
         if (n_rd <= st.tol_feas * nrm_q && n_rp <= st.tol_feas * nrm_b && n_re <= st.tol_feas * nrm_b && sdl <= st.tol_gap * gscale) {
             res.status = Solved;
             break;
@@ -275,15 +279,14 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
         }
         for (int e = 0; e < me; e++) nu[e] += alpha * dnu[e];
     }
-    // a diverging iteration (multipliers blowing up until the factorisation breaks) on a problem whose primal residual
-    // never came down is how infeasibility shows without Clarabel's homogeneous embedding
-    if (res.status == Other && (n_rp > 1e-4 * nrm_b || n_re > 1e-4 * nrm_b)) res.status = PrimalInfeasible;
-    if (res.status == MaxIter) {
+    // Exit classification without Clarabel's homogeneous embedding: residuals within 1e3 x tolerance -> SolvedInacc
+    // ("AlmostSolved"); primal residual still far from feasible after the multipliers diverged -> PrimalInfeasible.
+    if (res.status == MaxIter || res.status == Other) {
         const double loose = 1e3;
         if (n_rd <= loose * st.tol_feas * nrm_q && n_rp <= loose * st.tol_feas * nrm_b && n_re <= loose * st.tol_feas * nrm_b &&
             mu * mi <= loose * st.tol_gap * gscale)
             res.status = SolvedInacc;
-        else if (n_rp > 1e-4 * nrm_b || n_re > 1e-4 * nrm_b)
+        else if (n_rp > loose * st.tol_feas * nrm_b || n_re > loose * st.tol_feas * nrm_b)
             res.status = PrimalInfeasible;
     }
     res.iters = it;
