@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     __shared__ int s_flag;
     __shared__ int s_sb[kNumEE + 1];   // per-foot sample ranges (samples are stored foot-major)
     __shared__ EqRow s_eq[kMaxEq];
+    __shared__ int s_ib[kNumEE + 1];   // prefix of K-entry work items of the force-sample rows: 5 nfv^2 per foot
     if (tid < neq) s_eq[tid] = eqs[tid];
     if (tid < kNumEE) {
         s_fbase[tid] = Hd->fbase[tid];
@@ -145,6 +146,8 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         for (int j = 0; j < ns; ++j)
             while (samples[j].ee > e) s_sb[++e] = j;
         while (e < kNumEE) s_sb[++e] = ns;
+        s_ib[0] = 0;
+        for (int f = 0; f < kNumEE; ++f) s_ib[f + 1] = s_ib[f] + 5 * Hd->nfv[f] * Hd->nfv[f];
     }
 
     // ---- right-hand sides d and the active mask (wv = 1 / 0 while setting up).  Force rows have the fixed pattern
@@ -363,13 +366,16 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         }
         __syncthreads();
         // force samples: one work item per K entry (foot, coord pair, variable pair); it sums over the foot's samples
-        for (int it = tid; it < kNumEE * 6 * 256; it += nth) {
-            const int i2 = it & 15, i = (it >> 4) & 15, cp = (it >> 8) % 6, e = it / (6 * 256);
-            if (i >= s_nfv[e] || i2 >= s_nfv[e]) continue;
+        const int it_total = s_ib[kNumEE];
+        for (int it = tid; it < it_total; it += nth) {
+            int e = 0;
+            while (it >= s_ib[e + 1]) ++e;
+            const int nv = s_nfv[e], loc = it - s_ib[e];
+            const int cpi = loc / (nv * nv), rem = loc % (nv * nv), i = rem / nv, i2 = rem % nv;
+            const int cp = (cpi < 3) ? cpi : cpi + 1;                  // coordinate pairs 0,1,2,4,5 (x-y never share a row)
             const int c1 = (cp < 3) ? cp : (cp == 3 ? 1 : 2);          // (0,0) (1,1) (2,2) (1,0) (2,0) (2,1)
             const int c2 = (cp < 3) ? cp : (cp == 5 ? 1 : 0);
             if (c1 == c2 && i2 > i) continue;
-            if (cp == 3) continue;                                     // x and y never share a row
             double acc = 0;
             for (int j = s_sb[e]; j < s_sb[e + 1]; ++j) {
                 const Sample& sp = S.smp[j];
@@ -405,53 +411,56 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         constexpr int NB = 8;
         for (int b0 = 0; b0 < nu; b0 += NB) {
             const int bs = (nu - b0 < NB) ? nu - b0 : NB;
-            // (1) factor the bs x bs diagonal block inside warp 0: lane r owns row r, right-looking with shuffles
-            if (wid == 0) {
-                double a8[NB];
+            // (1) every warp factors the bs x bs diagonal block redundantly in registers (lane r owns row r,
+            // right-looking with shuffles): no barrier and no idle warps between the block and its panel.
+            double a8[NB];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) a8[c] = (lane < bs && c <= lane && c < bs) ? S.K[pk(b0 + lane, b0 + c)] : 0.0;
+            for (int c = 0; c < NB; ++c) a8[c] = (lane < bs && c <= lane && c < bs) ? S.K[pk(b0 + lane, b0 + c)] : 0.0;
 #pragma unroll
-                for (int c = 0; c < NB; ++c) {
-                    if (c < bs) {
-                        const double d = __shfl_sync(0xffffffffu, a8[c], c);
-                        const bool bad = !(d > 0.0);
-                        if (bad && lane == 0) s_flag = 1;
-                        const double inv = bad ? 1.0 : rsqrt(d);
-                        a8[c] = (lane == c) ? d * inv : a8[c] * inv;
+            for (int c = 0; c < NB; ++c) {
+                if (c < bs) {
+                    const double d = __shfl_sync(0xffffffffu, a8[c], c);
+                    const bool bad = !(d > 0.0);
+                    if (bad && tid == 0) s_flag = 1;
+                    const double inv = bad ? 1.0 : rsqrt(d);
+                    a8[c] = (lane == c) ? d * inv : a8[c] * inv;
 #pragma unroll
-                        for (int c2 = c + 1; c2 < NB; ++c2) {
-                            const double t = __shfl_sync(0xffffffffu, a8[c], c2);   // L[c2][c]
-                            if (lane >= c2) a8[c2] -= a8[c] * t;
-                        }
+                    for (int c2 = c + 1; c2 < NB; ++c2) {
+                        const double t = __shfl_sync(0xffffffffu, a8[c], c2);   // L[c2][c]
+                        if (lane >= c2) a8[c2] -= a8[c] * t;
                     }
                 }
+            }
+            // (2) panel below the block: row i solves L[i, b] = A[i, b] L_bb^-T, one thread per row; L_bb comes from the
+            // warp's own registers through shuffles
+            for (int base = b0 + bs; base < nu; base += nth) {
+                const int i = base + tid;
+                const bool act = i < nu;
+                double* Li = S.K + pk(act ? i : nu - 1, b0);
+                double row[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) row[c] = (act && c < bs) ? Li[c] : 0.0;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    double v = row[c];
+#pragma unroll
+                    for (int k = 0; k < NB; ++k)
+                        if (k < c) v -= row[k] * __shfl_sync(0xffffffffu, a8[k], c);
+                    const double dcc = __shfl_sync(0xffffffffu, a8[c], c);
+                    row[c] = (c < bs) ? v / dcc : 0.0;
+                }
+                if (act) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c)
+                        if (c < bs) Li[c] = row[c];
+                }
+            }
+            __syncthreads();
+            if (wid == 0) {   // the factored block itself (nobody reads it again before the final barrier)
 #pragma unroll
                 for (int c = 0; c < NB; ++c)
                     if (lane < bs && c <= lane && c < bs) S.K[pk(b0 + lane, b0 + c)] = a8[c];
             }
-            __syncthreads();
-            // (2) panel below the block: row i solves L[i, b] = A[i, b] L_bb^-T, one thread per row
-            for (int i = b0 + bs + tid; i < nu; i += nth) {
-                double* Li = S.K + pk(i, b0);
-                double row[NB];
-#pragma unroll
-                for (int c = 0; c < NB; ++c) row[c] = (c < bs) ? Li[c] : 0.0;
-#pragma unroll
-                for (int c = 0; c < NB; ++c) {
-                    if (c < bs) {
-                        const double* Lc = S.K + pk(b0 + c, b0);
-                        double v = row[c];
-#pragma unroll
-                        for (int k = 0; k < NB; ++k)
-                            if (k < c) v -= row[k] * Lc[k];
-                        row[c] = v / Lc[c];
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < NB; ++c)
-                    if (c < bs) Li[c] = row[c];
-            }
-            __syncthreads();
             // (3) trailing update A[i][l] -= sum_c L[i][b0+c] L[l][b0+c], 4 x 4 tiles, 16 x 16 threads over the tile grid
             const int t0 = b0 + bs;
             if (t0 < nu) {
