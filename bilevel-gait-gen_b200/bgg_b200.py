@@ -82,6 +82,7 @@ def lib():
         L.bgg_get_sizes.argtypes = [C.c_void_p, C.c_int, C.POINTER(Sizes)]
         L.bgg_get_dynamics.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int]
         L.bgg_get_condensed.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
+        L.bgg_export_qp_csc.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _ip, _dp, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int]
         L.bgg_get_solution.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
         L.bgg_instance_bytes.restype = C.c_size_t
         L.bgg_get_instance.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -97,7 +98,7 @@ def exported_symbols():
     return ["bgg_last_error", "bgg_device_count", "bgg_create", "bgg_destroy", "bgg_set_costs", "bgg_batch_reset",
             "bgg_set_warm_states", "bgg_set_contact_times", "bgg_solve_batch", "bgg_upload_inputs", "bgg_solve_resident",
             "bgg_download_results", "bgg_synchronize", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count", "bgg_event_record", "bgg_event_elapsed_ms",
-            "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_get_solution", "bgg_instance_bytes",
+            "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_export_qp_csc", "bgg_get_solution", "bgg_instance_bytes",
             "bgg_get_instance", "bgg_set_instance", "bgg_get_states", "bgg_eval_splines"]
 
 
@@ -124,6 +125,7 @@ class BatchedMPC:
         cfg = Config()
         cfg.num_nodes = num_nodes
         cfg.max_spline_vars = max_spline_vars
+        self.max_nu = max_spline_vars if max_spline_vars > 0 else 160
         cfg.device = device
         cfg.ipm_max_iter = ipm_max_iter
         cfg.ipm_refine = ipm_refine
@@ -279,6 +281,29 @@ class BatchedMPC:
         pp, xo = np.zeros((2 * (self.N - 3), nu)), np.zeros((self.N + 1, 12))
         self._chk(self.L.bgg_get_condensed(self.h, b, _d(H), _d(g), _d(pp), _d(xo)))
         return dict(H=H, g=g, phipos=pp, xoff=xo)
+
+    def GetQPData(self, first=0, count=1, nnz_cap=25000):
+        """The reference's QP (MPC::GetQPData) of the last solve for instances [first, first+count): a list of dicts with
+        scipy csc A (reference sparsity), the diagonal of P, q, ub and the equality / inequality row counts.
+        nnz_cap defaults to the reference's own reserve (mpc.cpp:47)."""
+        import scipy.sparse as sp
+        n_stride = 12 * (self.N + 1) + self.max_nu
+        m_stride = 12 * (self.N + 1) + 6 * 160 + 2 * (self.N - 3) * 8 + 16
+        dims = np.zeros((count, 6), np.int32)
+        cp = np.zeros((count, n_stride + 1), np.int32)
+        ri = np.zeros((count, nnz_cap), np.int32)
+        va = np.zeros((count, nnz_cap))
+        pd, q, ub = np.zeros((count, n_stride)), np.zeros((count, n_stride)), np.zeros((count, m_stride))
+        self._chk(self.L.bgg_export_qp_csc(self.h, first, count, _i(dims), _i(cp), _i(ri), _d(va), nnz_cap, _d(pd), _d(q),
+                                           _d(ub), n_stride, m_stride))
+        out = []
+        for k in range(count):
+            n, m, nnz, neq, nin, err = (int(v) for v in dims[k])
+            if err:
+                raise BggError(f"instance {first + k}: export error bits {err}")
+            A = sp.csc_matrix((va[k, :nnz].copy(), ri[k, :nnz].copy(), cp[k, :n + 1].copy()), shape=(m, n))
+            out.append(dict(A=A, P_diag=pd[k, :n].copy(), q=q[k, :n].copy(), ub=ub[k, :m].copy(), num_eq=neq, num_ineq=nin))
+        return out
 
     def solution(self, b=0):
         sz = self.sizes(b)

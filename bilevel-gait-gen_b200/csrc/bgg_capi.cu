@@ -450,6 +450,47 @@ int bgg_get_condensed(bgg_handle* h, int b, double* H, double* g, double* phipos
     return BGG_OK;
 }
 
+int bgg_export_qp_csc(bgg_handle* h, int first, int count, int32_t* dims, int32_t* colptr, int32_t* rowidx, double* val,
+                      int nnz_cap, double* p_diag, double* q, double* ub, int n_stride, int m_stride) {
+    if (!h || !dims || !colptr || !rowidx || !val || !p_diag || !q || !ub || first < 0 || count <= 0 || first + count > h->batch)
+        return fail(BGG_EINVAL, "bad argument");
+    const int n_max = kNx * (h->P.N + 1) + h->P.max_nu;
+    const int m_max = kNx * (h->P.N + 1) + h->L.max_rows + kMaxEq;
+    if (n_stride < n_max || m_stride < m_max || nnz_cap <= 0)
+        return fail(BGG_EINVAL, "strides must cover 12(N+1)+max_spline_vars columns and every constraint row");
+    CU(cudaSetDevice(h->device));
+    const size_t c = count;
+    int32_t *d_dims, *d_cp, *d_ri;
+    double *d_val, *d_pd, *d_q, *d_ub;
+    CU(cudaMalloc(&d_dims, 4 * 6 * c));
+    CU(cudaMalloc(&d_cp, 4 * c * (n_stride + 1)));
+    CU(cudaMalloc(&d_ri, 4 * c * nnz_cap));
+    CU(cudaMalloc(&d_val, 8 * c * nnz_cap));
+    CU(cudaMalloc(&d_pd, 8 * c * n_stride));
+    CU(cudaMalloc(&d_q, 8 * c * n_stride));
+    CU(cudaMalloc(&d_ub, 8 * c * m_stride));
+    CU(cudaMemsetAsync(d_cp, 0, 4 * c * (n_stride + 1), h->stream));
+    CU(cudaMemsetAsync(d_ri, 0, 4 * c * nnz_cap, h->stream));
+    CU(cudaMemsetAsync(d_val, 0, 8 * c * nnz_cap, h->stream));
+    CU(cudaMemsetAsync(d_pd, 0, 8 * c * n_stride, h->stream));
+    CU(cudaMemsetAsync(d_q, 0, 8 * c * n_stride, h->stream));
+    CU(cudaMemsetAsync(d_ub, 0, 8 * c * m_stride, h->stream));
+    launch_export_csc(h->P, h->L, h->d_ws + static_cast<size_t>(first) * h->L.stride, count, d_cp, d_ri, d_val, d_pd, d_q, d_ub,
+                      d_dims, n_stride, m_stride, nnz_cap, h->stream);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(dims, d_dims, 4 * 6 * c, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(colptr, d_cp, 4 * c * (n_stride + 1), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(rowidx, d_ri, 4 * c * nnz_cap, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(val, d_val, 8 * c * nnz_cap, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(p_diag, d_pd, 8 * c * n_stride, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(q, d_q, 8 * c * n_stride, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ub, d_ub, 8 * c * m_stride, cudaMemcpyDeviceToHost));
+    cudaFree(d_dims); cudaFree(d_cp); cudaFree(d_ri); cudaFree(d_val); cudaFree(d_pd); cudaFree(d_q); cudaFree(d_ub);
+    return BGG_OK;
+}
+
 int bgg_get_solution(bgg_handle* h, int b, double* qp_sol, double* z, double* lam, double* slack, double* nu_eq) {
     if (!h || b < 0 || b >= h->batch) return fail(BGG_EINVAL, "bad instance");
     bgg_sizes sz;

@@ -264,8 +264,6 @@ __global__ void __launch_bounds__(128) k_finish(Params P, Instance* __restrict__
         Hd->cost = cost_new;
         Hd->merit = P.merit_mu * dfin + cost_rt;
         Hd->merit_dd = merit_dd;
-        Hd->ee_box[0] = I.ee_box[0];
-        Hd->ee_box[1] = I.ee_box[1];
     }
 }
 

@@ -57,4 +57,9 @@ size_t condense_smem_bytes(const WsLayout& L);
 void launch_export_dynamics(const Params& P, const WsLayout& L, char* ws, int B, double* Ad, double* Bd, double* cd,
                             int nu_stride, cudaStream_t stream);
 
+// the reference's sparse QP (CSC, bit-identical sparsity) from the structured form; see csrc/bgg_assemble.cu
+void launch_export_csc(const Params& P, const WsLayout& L, const char* ws, int B, int32_t* colptr, int32_t* rowidx, double* val,
+                       double* p_diag, double* q, double* ub, int32_t* dims, int n_stride, int m_stride, int nnz_cap,
+                       cudaStream_t stream);
+
 }  // namespace bgg

@@ -118,7 +118,8 @@ int bgg_event_elapsed_ms(bgg_handle* h, int slot_start, int slot_end, float* ms)
 typedef struct bgg_sizes {
     int32_t n, nu, nf, np, n_samples, n_eebox, n_eq, n_td, m_ineq, status, iters, ls_iters, error;
     int32_t nfv[BGG_NUM_EE], npv[BGG_NUM_EE], fbase[BGG_NUM_EE], pbase[BGG_NUM_EE];
-    double t0, alpha, cost, prim_res, dual_res, gap, eq_violation, step_norm, merit, merit_dd, ee_box[2];
+    double t0, alpha, cost, prim_res, dual_res, gap, eq_violation, step_norm, merit, merit_dd;
+    double ee_box[2]; /* foot-box size the last QP was built with (the adapted size lives in the instance) */
     double qp_cost; /* objective of the QP optimum, 1/2 z'Pz + q'z */
 } bgg_sizes;
 int bgg_get_sizes(bgg_handle* h, int instance, bgg_sizes* out);
@@ -130,6 +131,17 @@ int bgg_get_dynamics(bgg_handle* h, int first, int count, double* Ad, double* Bd
 /* Condensed QP of the last solve: H [nu][nu], g [nu], phipos [2(N-3)][nu] (position rows of the state map for the
  * foot-box rows, node-major from node 4), xoff [N+1][12] (state offsets).  Any pointer may be NULL. */
 int bgg_get_condensed(bgg_handle* h, int instance, double* H, double* g, double* phipos, double* xoff);
+
+/* The QP of the last solve exactly as the reference hands it to its solver (MPC::GetQPData, mpc.h; QPData::
+ * ConstructSparseMats / ConstructVectors, mpc/qp/qp_data.cpp:169-289; utils/sparse_matrix_builder.cpp:11-42), for
+ * instances [first, first+count): constraint matrix in compressed-sparse-column form with the reference's sparsity
+ * (exact zeros dropped, rows ascending inside a column, constraint blocks stacked Dynamics | ForceBox | FrictionCone |
+ * EndEffectorLocation | TDPosition | EndEffectorStart), the diagonal of P, q, and the Clarabel-form right-hand side ub.
+ * dims [count][6] = {n, m, nnz, equality rows, inequality rows, error}; colptr [count][n_stride+1];
+ * rowidx / val [count][nnz_cap]; p_diag / q [count][n_stride]; ub [count][m_stride].  error bit 3 = nnz > nnz_cap
+ * (colptr is still valid, rowidx / val are not written). */
+int bgg_export_qp_csc(bgg_handle* h, int first, int count, int32_t* dims, int32_t* colptr, int32_t* rowidx, double* val,
+                      int nnz_cap, double* p_diag, double* q, double* ub, int n_stride, int m_stride);
 
 /* Solution of the last solve.  qp_sol [n]: the QP optimum z* = [x_0..x_N | u] (MPC::Solve's `sol`);
  * z [n]: prev_qp_sol after the line-search update (MPC::GetQPSolution, mpc.cpp:1071-1073);

@@ -75,6 +75,36 @@ def test_first_solve_matches_oracle(cfg_name):
         assert abs(gsz["eq_violation"] - ost["eq_violation"]) <= 5e-3 * max(1.0, ost["eq_violation"])
 
 
+def _assert_same_qp(gq, oq):
+    """Sparse QP of the CUDA path vs the oracle's restatement of QPData: sparsity bit-exact, values within 1e-10."""
+    A, oA = gq["A"], oq["A"]
+    assert A.shape == oA.shape
+    assert np.array_equal(A.indptr, oA.indptr), "column pointers differ"
+    assert np.array_equal(A.indices, oA.indices), "row indices differ"
+    assert np.abs(A.data - oA.data).max() <= 1e-10 * max(1.0, np.abs(oA.data).max())
+    assert np.abs(gq["P_diag"] - oq["P"].diagonal()).max() <= 1e-12
+    assert oq["P"].nnz == oq["P"].shape[0], "the oracle's P is diagonal"
+    assert np.array_equal(gq["q"], oq["q"])
+    assert np.abs(gq["ub"] - oq["ub"]).max() <= 1e-10 * max(1.0, np.abs(oq["ub"]).max())
+    assert gq["num_eq"] == int(oq["is_eq"].sum()) and gq["num_ineq"] == int((~oq["is_eq"]).sum())
+
+
+@pytest.mark.parametrize("cfg_name", ["a1_configuration", "a1_gait_opt_config"])
+def test_sparse_qp_export_matches_reference_assembly(cfg_name):
+    """Kernel 3: MPC::GetQPData -- the CSC constraint matrix the reference builds through SparseMatrixBuilder /
+    setFromTriplets, from the structured rows."""
+    cfg = wl.CONFIGS[cfg_name]
+    B = 4
+    states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=5)
+    gpu = common.make_gpu(cfg_name, B, states)
+    gpu.GetRealTimeUpdate(states, t0, ee)
+    qps = gpu.GetQPData(0, B)
+    for b in range(B):
+        o = common.make_oracle(cfg_name, states[b])
+        o.assemble(states[b], 0.0, ee[b])
+        _assert_same_qp(qps[b], o.qp())
+
+
 def test_receding_horizon_with_mirrored_trajectory():
     """Slide t0 over 0.7 s (knots are appended and dropped, touch-down rows appear and vanish); before each solve the
     GPU instance is overwritten with the oracle's trajectory so both solve from identical inputs."""
@@ -94,6 +124,7 @@ def test_receding_horizon_with_mirrored_trajectory():
         out = gpu.GetRealTimeUpdate(state[None], np.array([t0]), ee_now[None])
         o.assemble(state, t0, ee_now)
         qp = o.qp()
+        _assert_same_qp(gpu.GetQPData(0, 1)[0], qp)
         osz, gsz = o.sizes(), gpu.sizes(0)
         seen_sizes.add((osz["n"], osz["m"]))
         assert gsz["error"] == 0
