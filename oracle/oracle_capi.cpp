@@ -428,6 +428,39 @@ double orc_mpc_cost(void* h) { return M(h).GetCost(); }
 void orc_mpc_force_at(void* h, int ee, double t, double* out) { M(h).Trajectory().GetForce(ee, t, out); }
 void orc_mpc_ee_at(void* h, int ee, double t, double* out) { M(h).Trajectory().GetEndEffectorLocation(ee, t, out); }
 
+// Contact-time parameter partials of the last solve's QP (gait_partials.cpp).  Triplets are written up to `cap`
+// entries each; returns 0, 1 when the last solve was not `Solved` (the reference returns false), -1 on error.
+// counts = [nnz dA, nnz dG, num_eq, num_ineq]
+int orc_mpc_param_partials(void* h, int ee, int contact_idx, int cap, int* counts, int* Ar, int* Ac, double* Av, int* Gr,
+                           int* Gc, double* Gv, double* db) {
+    ORC_TRY
+    ParamPartials pp;
+    if (!M(h).ComputeParamPartialsClarabel(M(h).Trajectory(), pp, ee, contact_idx)) return 1;
+    counts[0] = static_cast<int>(pp.dA.v.size());
+    counts[1] = static_cast<int>(pp.dG.v.size());
+    counts[2] = pp.num_eq;
+    counts[3] = pp.num_ineq;
+    if (counts[0] > cap || counts[1] > cap) throw std::runtime_error("triplet capacity too small");
+    std::copy(pp.dA.ri.begin(), pp.dA.ri.end(), Ar);
+    std::copy(pp.dA.ci.begin(), pp.dA.ci.end(), Ac);
+    std::copy(pp.dA.v.begin(), pp.dA.v.end(), Av);
+    std::copy(pp.dG.ri.begin(), pp.dG.ri.end(), Gr);
+    std::copy(pp.dG.ci.begin(), pp.dG.ci.end(), Gc);
+    std::copy(pp.dG.v.begin(), pp.dG.v.end(), Gv);
+    std::copy(pp.db.begin(), pp.db.end(), db);
+    return 0;
+    ORC_CATCH(-1)
+}
+// number of contact times per foot (Trajectory::GetNumContactNodes) and their values / types
+int orc_mpc_num_contacts(void* h, int ee) { return M(h).Trajectory().Foot(ee).GetNumContacts(); }
+void orc_mpc_get_contact_times(void* h, int ee, double* t, int* type) {
+    const auto ct = M(h).Trajectory().GetContactTimes();
+    for (size_t i = 0; i < ct.at(ee).size(); i++) {
+        t[i] = ct[ee][i].t;
+        type[i] = static_cast<int>(ct[ee][i].type);
+    }
+}
+
 // merit evaluation taps (mpc.cpp:749-788) for the line-search kernel's parity test
 double orc_mpc_merit(void* h, const double* z) {
     ORC_TRY

@@ -194,8 +194,24 @@ struct SolveStats {       // MPC::RecordStats, mpc.cpp:804-816
     int qp_iters = 0;
 };
 
+// mpc/include/qp/qp_partials.h:15-36 (the fields the Clarabel path fills): partials of the QP data with respect to
+// one contact time, as triplets in the equality-row / inequality-row numbering of ClarabelInterface::
+// SetupDerivativeCalcs (equalities: Dynamics | TDPosition | EndEffectorStart; inequalities: ForceBox | FrictionCone |
+// EndEffectorLocation).
+struct ParamPartials {
+    TripletBuilder dA, dG;
+    Vec db, dh;
+    int num_eq = 0, num_ineq = 0, num_vars = 0;
+};
+
 class SrbMpc {
 public:
+    // gait_partials.cpp
+    bool ComputeParamPartialsClarabel(const Traj& traj, ParamPartials& out, int ee, int contact_idx) const;   // mpc_single_rigid_body.cpp:642-792
+    void AddForceBoxConstraintPartials(TripletBuilder& b, int contact_idx, int start_idx, int ee) const;       // mpc.cpp:416-531
+    void AddFrictionConeConstraintPartials(TripletBuilder& b, int contact_idx, int start_idx, int ee) const;   // mpc.cpp:240-350
+    void AddTDPositionConstraintPartial(TripletBuilder& b, Vec& db, int contact_idx, int eq_idx, int ee) const;   // mpc_single_rigid_body.cpp:889-927
+
     SrbMpc(const MpcInfo& info, const RobotConsts& rc, std::shared_ptr<QpSolver> solver);
 
     void AddQuadraticTrackingCost(const Vec& state_des, const Mat& Q);   // mpc.cpp:533-540
