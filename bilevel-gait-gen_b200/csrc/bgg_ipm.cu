@@ -14,6 +14,7 @@
 //   6 ns + 2 e + 0 : -p_c(k) + w.u_pos <=  hip_c + box_c/2     e = ((k-4)*4 + foot)*2 + c   (mpc_single_rigid_body.cpp:381-443)
 //   6 ns + 2 e + 1 :  p_c(k) - w.u_pos <= -(hip_c - box_c/2)
 #include "bgg_kernels.cuh"
+#include "bgg_kkt.cuh"
 
 namespace bgg {
 
@@ -29,6 +30,7 @@ struct Smem {
     double* pw;                                      // [(N-3)*4][2] foot-box position weights
     int *pcnt, *poff;                                // [(N-3)*4]
     Sample* smp;                                     // staged force samples
+    ColInfo* col;                                    // [nu] per-variable tables of the K assembly
     const double* phi;                               // position rows: shared memory when they fit, else HBM/L2
     int phi_stride;
 };
@@ -43,7 +45,7 @@ struct IpmCaps {          // per-launch shared-memory sizing, from the actual ma
 static size_t ipm_smem_core(int N, int nu, int rows, int ns) {
     const size_t kc = 2 * (N - 3), eb = 4 * (N - 3);
     return 8 * (static_cast<size_t>(nu) * (nu + 1) / 2 + 6 * nu + 6 * static_cast<size_t>(rows) + 2 * eb * 2 + 2 * kc + 3 * kMaxEq + 40 + 2 * eb) +
-           8 * eb + sizeof(Sample) * static_cast<size_t>(ns) + 64;
+           8 * eb + sizeof(Sample) * static_cast<size_t>(ns) + sizeof(ColInfo) * static_cast<size_t>(nu) + 64;
 }
 static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max) {
     IpmCaps c;
@@ -108,6 +110,8 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         p += 4 * (N - 3);
         S.smp = reinterpret_cast<Sample*>(p);
         p += (sizeof(Sample) * static_cast<size_t>(ns) + 7) / 8;
+        S.col = reinterpret_cast<ColInfo*>(p);
+        p += (sizeof(ColInfo) * static_cast<size_t>(nu) + 7) / 8;
         if (stage_phi) {
             S.phi = p;
             S.phi_stride = nf;
@@ -131,7 +135,6 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     __shared__ int s_flag;
     __shared__ int s_sb[kNumEE + 1];   // per-foot sample ranges (samples are stored foot-major)
     __shared__ EqRow s_eq[kMaxEq];
-    __shared__ int s_ib[kNumEE + 1];   // prefix of K-entry work items of the force-sample rows: 5 nfv^2 per foot
     if (tid < neq) s_eq[tid] = eqs[tid];
     if (tid < kNumEE) {
         s_fbase[tid] = Hd->fbase[tid];
@@ -146,8 +149,6 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         for (int j = 0; j < ns; ++j)
             while (samples[j].ee > e) s_sb[++e] = j;
         while (e < kNumEE) s_sb[++e] = ns;
-        s_ib[0] = 0;
-        for (int f = 0; f < kNumEE; ++f) s_ib[f + 1] = s_ib[f] + 5 * Hd->nfv[f] * Hd->nfv[f];
     }
 
     // ---- right-hand sides d and the active mask (wv = 1 / 0 while setting up).  Force rows have the fixed pattern
@@ -169,6 +170,8 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         S.wv[m_force + 2 * e + 1] = 1.0;
     }
     auto rhs_of = [&](int i) -> double { return (i < m_force) ? ((i % 6 == 0) ? fbound : 0.0) : S.d[i - m_force]; };
+    __syncthreads();
+    kkt_build_colinfo(S.col, nu, nf, N, s_fbase, s_pbase, s_nfv, s_npv, s_sb, S.smp, S.pcnt, S.poff);
     __syncthreads();
 
     // ------------------------------------------------------------------------------------------------ operators
@@ -287,123 +290,13 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         __syncthreads();
     };
 
-    // K = H + C' diag(wv) C + E'E/delta (packed lower triangle in shared memory), then in-place Cholesky.
+    // K = H + C' diag(wv) C + E'E/delta (packed lower triangle in shared memory, csrc/bgg_kkt.cuh), then in-place Cholesky.
+    KktView kv;
+    kv.K = S.K; kv.ld = 0; kv.Hg = Hg; kv.nu = nu; kv.nf = nf; kv.N = N; kv.ns = ns; kv.ne = ne; kv.neq = neq; kv.nkc = nkc;
+    kv.wv = S.wv; kv.phi = S.phi; kv.phi_stride = S.phi_stride; kv.pw = S.pw; kv.pcnt = S.pcnt; kv.poff = S.poff;
+    kv.smp = S.smp; kv.eq = s_eq; kv.col = S.col; kv.ckc = S.ckc; kv.mu_f = mu_f; kv.inv_delta = inv_delta; kv.sign = 1.0;
     auto build_and_factor = [&]() -> bool {
-        for (int p = tid; p < nu * nu; p += nth) {
-            const int i = p / nu, j = p % nu;
-            if (j <= i) S.K[pk(i, j)] = Hg[p];
-        }
-        // (node, coord) weights of the dense foot-box rows
-        for (int q = tid; q < nkc; q += nth) {
-            const int kk = q >> 1, c = q & 1;
-            double s = 0;
-            for (int foot = 0; foot < kNumEE; ++foot) {
-                const int e = (kk * 4 + foot) * 2 + c;
-                s += S.wv[6 * ns + 2 * e] + S.wv[6 * ns + 2 * e + 1];
-            }
-            S.ckc[q] = s;
-        }
-        __syncthreads();
-        // force-force block: sum_q ckc[q] phi_q phi_q'   (4 x 4 register tiles, 16 x 16 threads over the tile grid)
-        {
-            const int ty = tid >> 4, tx = tid & 15;
-            const int side = (nf + 3) >> 2;
-            for (int ti = ty; ti < side; ti += 16)
-                for (int tl = tx; tl <= ti; tl += 16) {
-                    const int i0 = 4 * ti, l0 = 4 * tl;
-                    double acc[4][4];
-#pragma unroll
-                    for (int a2 = 0; a2 < 4; ++a2)
-#pragma unroll
-                        for (int c2 = 0; c2 < 4; ++c2) acc[a2][c2] = 0.0;
-                    for (int q = 0; q < nkc; ++q) {
-                        const double* row = S.phi + static_cast<size_t>(q) * S.phi_stride;
-                        const double wq = S.ckc[q];
-                        double ra[4], rc[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            ra[k] = (i0 + k < nf) ? wq * row[i0 + k] : 0.0;
-                            rc[k] = (l0 + k < nf) ? row[l0 + k] : 0.0;
-                        }
-#pragma unroll
-                        for (int a2 = 0; a2 < 4; ++a2)
-#pragma unroll
-                            for (int c2 = 0; c2 < 4; ++c2) acc[a2][c2] += ra[a2] * rc[c2];
-                    }
-#pragma unroll
-                    for (int a2 = 0; a2 < 4; ++a2) {
-                        const int ii = i0 + a2;
-                        if (ii >= nf) continue;
-                        double* Ki = S.K + ii * (ii + 1) / 2;
-#pragma unroll
-                        for (int c2 = 0; c2 < 4; ++c2)
-                            if (l0 + c2 <= ii) Ki[l0 + c2] += acc[a2][c2];
-                    }
-                }
-        }
-        // position-force block of the foot-box rows: one thread per (foot, coord, force column)
-        for (int it = tid; it < kNumEE * 2 * nf; it += nth) {
-            const int j = it % nf, fc = it / nf, foot = fc >> 1, c = fc & 1;
-            const int pb = nf + s_pbase[foot] + c * s_npv[foot];
-            for (int kk = 0; kk < N - 3; ++kk) {
-                const int kf = kk * 4 + foot, e = kf * 2 + c;
-                const double om = S.wv[6 * ns + 2 * e] + S.wv[6 * ns + 2 * e + 1];
-                const double pj = om * S.phi[static_cast<size_t>(kk * 2 + c) * S.phi_stride + j];
-                for (int a = 0; a < S.pcnt[kf]; ++a) S.K[pk(pb + S.poff[kf] + a, j)] -= pj * S.pw[2 * kf + a];
-            }
-        }
-        // position-position block: one thread per (foot, coord)
-        if (tid < kNumEE * 2) {
-            const int foot = tid >> 1, c = tid & 1;
-            const int pb = nf + s_pbase[foot] + c * s_npv[foot];
-            for (int kk = 0; kk < N - 3; ++kk) {
-                const int kf = kk * 4 + foot, e = kf * 2 + c;
-                const double om = S.wv[6 * ns + 2 * e] + S.wv[6 * ns + 2 * e + 1];
-                for (int a = 0; a < S.pcnt[kf]; ++a)
-                    for (int a2 = 0; a2 <= a; ++a2)
-                        S.K[pk(pb + S.poff[kf] + a, pb + S.poff[kf] + a2)] += om * S.pw[2 * kf + a] * S.pw[2 * kf + a2];
-            }
-        }
-        __syncthreads();
-        // force samples: one work item per K entry (foot, coord pair, variable pair); it sums over the foot's samples
-        const int it_total = s_ib[kNumEE];
-        for (int it = tid; it < it_total; it += nth) {
-            int e = 0;
-            while (it >= s_ib[e + 1]) ++e;
-            const int nv = s_nfv[e], loc = it - s_ib[e];
-            const int cpi = loc / (nv * nv), rem = loc % (nv * nv), i = rem / nv, i2 = rem % nv;
-            const int cp = (cpi < 3) ? cpi : cpi + 1;                  // coordinate pairs 0,1,2,4,5 (x-y never share a row)
-            const int c1 = (cp < 3) ? cp : (cp == 3 ? 1 : 2);          // (0,0) (1,1) (2,2) (1,0) (2,0) (2,1)
-            const int c2 = (cp < 3) ? cp : (cp == 5 ? 1 : 0);
-            if (c1 == c2 && i2 > i) continue;
-            double acc = 0;
-            for (int j = s_sb[e]; j < s_sb[e + 1]; ++j) {
-                const Sample& sp = S.smp[j];
-                const int a = i - sp.off, a2 = i2 - sp.off;
-                if (a < 0 || a >= sp.cnt || a2 < 0 || a2 >= sp.cnt || !sp.active) continue;
-                const double* w6 = S.wv + 6 * j;
-                double Mcc;   // sum_r w_r c_r c_r' over the six rows' coefficient 3-vectors
-                if (cp == 2) Mcc = (w6[0] + w6[1]) + mu_f * mu_f * (w6[2] + w6[3] + w6[4] + w6[5]);
-                else if (cp == 0) Mcc = w6[2] + w6[3];
-                else if (cp == 1) Mcc = w6[4] + w6[5];
-                else if (cp == 4) Mcc = -mu_f * (w6[2] - w6[3]);
-                else Mcc = -mu_f * (w6[4] - w6[5]);
-                acc += Mcc * sp.w[a] * sp.w[a2];
-            }
-            if (acc != 0.0) S.K[pk(s_fbase[e] + c1 * s_nfv[e] + i, s_fbase[e] + c2 * s_nfv[e] + i2)] += acc;
-        }
-        __syncthreads();
-        if (tid < kNumEE * 2)
-            for (int r = 0; r < neq; ++r) {
-                const EqRow& q = s_eq[r];
-                if (q.pad != tid) continue;
-                for (int a = 0; a < q.cnt; ++a)
-                    for (int a2 = 0; a2 <= a; ++a2) {
-                        const int ia = q.col[a], ib = q.col[a2];
-                        S.K[ia >= ib ? pk(ia, ib) : pk(ib, ia)] += inv_delta * q.w[a] * q.w[a2];
-                    }
-            }
-        __syncthreads();
+        kkt_assemble<true>(kv, s_fbase, s_nfv);
         // Blocked right-looking Cholesky on the packed lower triangle: 8-column panels, 4 x 4 register tiles in the
         // trailing update (3 barriers per panel instead of 3 per column).
         if (tid == 0) s_flag = 0;

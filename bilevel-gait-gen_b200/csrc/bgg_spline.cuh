@@ -353,4 +353,165 @@ BGG_HD void init_foot(FootSpline& s, const double* times, int num_contacts, bool
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Partials with respect to the contact times (the gait optimiser's parameters).  A foot's contact times are its
+// LiftOff / TouchDown knots in order; interior force knots move proportionally with the two contact times of their
+// stance, the mid-swing knot with the two of its swing (SetContactTimes, :860-892).
+BGG_HD int num_contacts(const FootSpline& s) {   // GetNumContacts, :999-1008
+    int c = 0;
+    for (int i = 0; i < s.n; ++i) c += (s.ttype[i] != kInter);
+    return c;
+}
+BGG_HD int contact_to_knot(const FootSpline& s, int contact_idx) {   // ConvertContactNodeToSplineNode, :1114-1128
+    int c = 0;
+    for (int i = 0; i < s.n; ++i) {
+        if (c == contact_idx && s.ttype[i] != kInter) return i;
+        if (s.ttype[i] != kInter) c++;
+    }
+    return -1;
+}
+BGG_HD int force_chain_back(const FootSpline& s, int lo) {   // FullDeriv knots walked back from `lo` (:602-609, 686-693)
+    int j = 0;
+    while (lo - j >= 0 && s.ftype[lo - j] == kFullDeriv) j++;
+    return j;
+}
+struct HermiteD {   // d(basis weight)/d(theta) given d(tau)/d(theta) and d(DeltaT)/d(theta), :1199-1244
+    double x0, x1, d0, d1;
+};
+BGG_HD HermiteD hermite_d(double tau, double dT, double dtau, double ddT) {
+    const double i1 = 1.0 / dT, i2 = i1 * i1, i3 = i2 * i1, i4 = i2 * i2, t2 = tau * tau, t3 = t2 * tau;
+    HermiteD h;
+    h.x0 = (6 * i3 * t2 - 6 * i4 * t3) * ddT + (-6 * i2 * tau + 6 * i3 * t2) * dtau;
+    h.x1 = (-6 * i3 * t2 + 6 * i4 * t3) * ddT + (6 * i2 * tau - 6 * i3 * t2) * dtau;
+    h.d0 = (2 * i2 * t2 - 2 * i3 * t3) * ddT + (1 - i1 * 4 * tau + i2 * 3 * t2) * dtau;
+    h.d1 = (i2 * t2 - 2 * i3 * t3) * ddT + (-i1 * 2 * tau + i2 * 3 * t2) * dtau;
+    return h;
+}
+
+// ComputePartialWrtTime, :513-648: d(value at `time`)/d(contact time `time_idx`).  Position: coord 0 / 1 only.
+BGG_HD double partial_wrt_time(const FootSpline& s, bool force, int coord, double time, int time_idx) {
+    const int kind = force ? kForce : kPosXY;
+    const int up = upper_idx(s, kind, time), lo = lower_idx(s, kind, time);
+    const double dT = s.t[up] - s.t[lo], tau = time - s.t[lo];
+    const int node = contact_to_knot(s, time_idx);
+    const uint8_t* ty = knot_types(s, kind);
+    const double(*v)[2] = force ? s.f[coord] : s.p[coord];
+    const bool direct = (node == lo || node == up), wrt_lower = (node == lo);
+    const double Pn = static_cast<double>(kNumForcePolys);
+    const double x0 = v[lo][0], x1 = v[up][0];
+    double x0d = 0, x1d = 0;
+    if (ty[lo] == kFullDeriv) x0d = force ? v[lo][1] * kForceMult : v[lo][1];
+    if (ty[up] == kFullDeriv) x1d = force ? v[up][1] * kForceMult : v[up][1];
+    const double i1 = 1.0 / dT, i2 = i1 * i1, i3 = i2 * i1, i4 = i2 * i2;
+    const double a2 = -i2 * (3 * (x0 - x1) + dT * (2 * x0d + x1d));
+    const double a3 = i3 * (2 * (x0 - x1) + dT * (x0d + x1d));
+    const double t2 = tau * tau, t3 = t2 * tau;
+    const double vel = x0d + a2 * 2 * tau + a3 * 3 * t2;
+    double ddT, dtau;
+    if (direct && wrt_lower) {
+        ddT = force ? -1.0 / Pn : -1.0;
+        dtau = -1.0;
+    } else if (direct) {
+        ddT = force ? 1.0 / Pn : 1.0;
+        dtau = force ? -static_cast<double>(kNumForcePolys - 1) / Pn : 0.0;
+    } else if (node > up && node <= upper_idx(s, kPosXY, time)) {
+        ddT = 1.0 / Pn;
+        dtau = -static_cast<double>(force_chain_back(s, lo)) / Pn;
+    } else if (node < lo && node >= lower_idx(s, kPosXY, time)) {
+        ddT = -1.0 / Pn;
+        dtau = -(static_cast<double>(-force_chain_back(s, lo)) / Pn + 1.0);
+    } else {
+        return 0.0;
+    }
+    const double da2 = 6 * i3 * (x0 - x1) * ddT + (2 * x0d + x1d) * i2 * ddT;
+    const double da3 = -6 * i4 * (x0 - x1) * ddT - 2 * i3 * (x0d + x1d) * ddT;
+    return da2 * t2 + da3 * t3 + vel * dtau;
+}
+
+// ComputeCoefPartialWrtTime(Force, ...), :655-763: partials of the force_lin weights; same for x, y, z.  dtwdth is the
+// sensitivity of the query time itself (the constraint samples move with their stance).  Returns the weight count.
+BGG_HD int force_coef_partial(const FootSpline& s, double time, int time_idx, double dtwdth, double out[4]) {
+    const int up = upper_idx(s, kForce, time), lo = lower_idx(s, kForce, time);
+    double dT = s.t[up] - s.t[lo];
+    if (dT == 0) dT = s.t[up] - s.t[lower_idx(s, kForce, time - 1e-4)];
+    const double tau = time - s.t[lo];
+    const uint8_t tl = s.ftype[lo], tu = s.ftype[up];
+    int cnt;
+    if ((tl == kNoDeriv && tu == kFullDeriv) || (tl == kFullDeriv && tu == kNoDeriv)) cnt = 2;
+    else if (lo == up) cnt = 1;
+    else cnt = 4;
+    for (int i = 0; i < 4; ++i) out[i] = 0.0;
+    if (tl == kNoDeriv && tu == kNoDeriv) return 0;
+    const int node = contact_to_knot(s, time_idx);
+    const bool direct = (node == lo || node == up);
+    bool wrt_lower = (node == lo);
+    const double Pn = static_cast<double>(kNumForcePolys);
+    const int j = force_chain_back(s, lo);
+    double ddT = 1.0 / Pn, dtau = dtwdth;
+    if (wrt_lower) {
+        ddT = -1.0 / Pn;
+        dtau += static_cast<double>(j) / Pn - 1.0;
+    } else {
+        dtau += -static_cast<double>(j) / Pn;
+    }
+    bool fill = false;
+    if (direct) {
+        const HermiteD h = hermite_d(tau, dT, dtau, ddT);
+        if (wrt_lower) {
+            out[0] = h.x1;
+            out[1] = h.d1 * kForceMult;
+        } else {
+            out[0] = h.x0;
+            out[1] = h.d0 * kForceMult;
+        }
+    } else if (node > up && node <= upper_idx(s, kPosXY, time)) {
+        ddT = 1.0 / Pn;
+        dtau = dtwdth - static_cast<double>(j) / Pn;
+        fill = true;
+    } else if (node < lo && node >= lower_idx(s, kPosXY, time)) {
+        ddT = -1.0 / Pn;
+        dtau = dtwdth + static_cast<double>(j) / Pn - 1.0;
+        fill = true;
+    }
+    if (fill) {
+        const HermiteD h = hermite_d(tau, dT, dtau, ddT);
+        if (tl == kFullDeriv) {
+            out[0] = h.x0;
+            out[1] = kForceMult * h.d0;
+            if (tu == kFullDeriv) {
+                out[2] = h.x1;
+                out[3] = kForceMult * h.d1;
+            }
+        } else if (tu == kFullDeriv) {
+            out[0] = h.x1;
+            out[1] = kForceMult * h.d1;
+        }
+    }
+    return cnt;
+}
+
+// ComputeCoefPartialWrtTime(Position, x / y, ...), :764-803: partials of the pos_lin weights.  Returns the count.
+BGG_HD int pos_coef_partial(const FootSpline& s, double time, int time_idx, double out[2]) {
+    const int up = upper_idx(s, kPosXY, time), lo = lower_idx(s, kPosXY, time);
+    double dT = s.t[up] - s.t[lo];
+    if (dT == 0) dT = s.t[up] - s.t[lower_idx(s, kPosXY, time - 1e-4)];
+    const double tau = time - s.t[lo];
+    int cnt = 1;
+    if (lo != up && s.ftype[lo] == kNoDeriv && lo + 2 < s.n && s.ftype[lo + 2] == kNoDeriv) cnt = 2;
+    out[0] = out[1] = 0.0;
+    const int node = contact_to_knot(s, time_idx);
+    const bool direct = (node == lo || node == up), wrt_lower = (node == lo);
+    double ddT = 1.0, dtau = 0.0;
+    if (wrt_lower) {
+        dtau = -1.0;
+        ddT = -1.0;
+    }
+    if (direct && lo != up && lo + 1 < s.n && s.ztype[lo + 1] == kFullDeriv) {
+        const HermiteD h = hermite_d(tau, dT, dtau, ddT);
+        out[0] = h.x0;
+        if (cnt > 1) out[1] = h.x1;
+    }
+    return cnt;
+}
+
 }  // namespace bgg
