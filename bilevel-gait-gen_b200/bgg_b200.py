@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbgg_b200.so")
 
 NX, NX_MAN, NUM_EE = 12, 13, 4
+MAX_CONTACTS = 12   # BGG_MAX_CONTACTS
 MAX_KNOTS, MAX_NODES = 28, 64
 STATUS_NAMES = ["Solved", "SolvedInacc", "MaxIter", "PrimalInfeasible", "DualInfeasible", "PrimalInfeasibleInacc",
                 "DualInfeasibleInacc", "Unsolved", "Other"]
@@ -83,6 +84,10 @@ def lib():
         L.bgg_get_dynamics.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int]
         L.bgg_get_condensed.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
         L.bgg_export_qp_csc.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _ip, _dp, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int]
+        L.bgg_gait_gradient_batch.argtypes = [C.c_void_p, _ip, _ip, _dp]
+        L.bgg_get_adjoint.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.bgg_get_contact_times.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _ip, _ip]
+        L.bgg_set_solution.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
         L.bgg_get_solution.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
         L.bgg_instance_bytes.restype = C.c_size_t
         L.bgg_get_instance.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -98,7 +103,8 @@ def exported_symbols():
     return ["bgg_last_error", "bgg_device_count", "bgg_create", "bgg_destroy", "bgg_set_costs", "bgg_batch_reset",
             "bgg_set_warm_states", "bgg_set_contact_times", "bgg_solve_batch", "bgg_upload_inputs", "bgg_solve_resident",
             "bgg_download_results", "bgg_synchronize", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count", "bgg_event_record", "bgg_event_elapsed_ms",
-            "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_export_qp_csc", "bgg_get_solution", "bgg_instance_bytes",
+            "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_export_qp_csc", "bgg_gait_gradient_batch", "bgg_get_adjoint",
+            "bgg_get_contact_times", "bgg_set_solution", "bgg_get_solution", "bgg_instance_bytes",
             "bgg_get_instance", "bgg_set_instance", "bgg_get_states", "bgg_eval_splines"]
 
 
@@ -119,7 +125,7 @@ class BatchedMPC:
 
     def __init__(self, num_nodes, integrator_dt, robot, friction_coef=0.5, force_bound=150.0, swing_height=0.075,
                  foot_offset=0.015, ee_box_size=(0.15, 0.15), force_cost=0.0, device=0, max_spline_vars=0,
-                 ipm_tol=0.0, ipm_max_iter=0, ipm_refine=0):
+                 ipm_tol=0.0, ipm_max_iter=0, ipm_refine=0, ipm_tol_gap=0.0):
         self.L = lib()
         self.N = num_nodes
         cfg = Config()
@@ -137,7 +143,7 @@ class BatchedMPC:
         cfg.ee_box_size[0], cfg.ee_box_size[1] = ee_box_size
         cfg.force_cost = force_cost
         cfg.ipm_tol_feas = ipm_tol
-        cfg.ipm_tol_gap = ipm_tol
+        cfg.ipm_tol_gap = ipm_tol_gap if ipm_tol_gap > 0 else ipm_tol
         cfg.ipm_eq_delta = 0.0
         rb = Robot()
         rb.mass = robot["mass"]
@@ -305,12 +311,41 @@ class BatchedMPC:
             out.append(dict(A=A, P_diag=pd[k, :n].copy(), q=q[k, :n].copy(), ub=ub[k, :m].copy(), num_eq=neq, num_ineq=nin))
         return out
 
+    # --- gait optimiser -------------------------------------------------------------------------------------------
+    def ComputeCostFcnDerivWrtContactTimes(self):
+        """MPCController::GaitOpt's derivative chain for the whole batch: returns dict(status [B], n_contacts [B][4],
+        dHdtheta: list of per-instance arrays over all contact times, foot-major)."""
+        B = self.B
+        status, nct = np.zeros(B, np.int32), np.zeros((B, NUM_EE), np.int32)
+        dh = np.zeros((B, NUM_EE, MAX_CONTACTS))
+        self._chk(self.L.bgg_gait_gradient_batch(self.h, _i(status), _i(nct), _d(dh)))
+        grads = [np.concatenate([dh[b, e, :nct[b, e]] for e in range(NUM_EE)]) for b in range(B)]
+        return dict(status=status, n_contacts=nct, dHdtheta=grads, raw=dh)
+
+    def adjoint(self, b=0):
+        sz = self.sizes(b)
+        dz, dlam = np.zeros(sz["n"]), np.zeros(sz["m_ineq"])
+        dnu, nu, dnue = np.zeros(12 * (self.N + 1)), np.zeros(12 * (self.N + 1)), np.zeros(sz["n_eq"])
+        self._chk(self.L.bgg_get_adjoint(self.h, b, _d(dz), _d(dlam), _d(dnu), _d(dnue), _d(nu)))
+        return dict(dz=dz, dlam=dlam, dnu_dyn=dnu, dnu_eq=dnue, nu_dyn=nu, sizes=sz)
+
+    def GetContactTimes(self, first=0, count=None):
+        count = self.B - first if count is None else count
+        t = np.zeros((count, NUM_EE, MAX_CONTACTS))
+        ty, n = np.zeros((count, NUM_EE, MAX_CONTACTS), np.int32), np.zeros((count, NUM_EE), np.int32)
+        self._chk(self.L.bgg_get_contact_times(self.h, first, count, _d(t), _i(ty), _i(n)))
+        return t, ty, n
+
     def solution(self, b=0):
         sz = self.sizes(b)
         qp, z = np.zeros(sz["n"]), np.zeros(sz["n"])
         lam, sl, nu = np.zeros(sz["m_ineq"]), np.zeros(sz["m_ineq"]), np.zeros(sz["n_eq"])
         self._chk(self.L.bgg_get_solution(self.h, b, _d(qp), _d(z), _d(lam), _d(sl), _d(nu)))
         return dict(qp_sol=qp, z=z, lam=lam, slack=sl, nu_eq=nu, sizes=sz)
+
+    def set_solution(self, b, qp_sol=None, z=None, lam=None, slack=None, nu_eq=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (qp_sol, z, lam, slack, nu_eq)]
+        self._chk(self.L.bgg_set_solution(self.h, b, *[None if a is None else _d(a) for a in arrs]))
 
     def get_instance(self, b=0):
         assert self.L.bgg_instance_bytes() == INSTANCE_DTYPE.itemsize, (self.L.bgg_instance_bytes(), INSTANCE_DTYPE.itemsize)

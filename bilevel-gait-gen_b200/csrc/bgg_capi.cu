@@ -10,6 +10,7 @@
 
 using namespace bgg;
 
+static_assert(BGG_MAX_CONTACTS == kMaxContacts, "include/bgg.h and csrc/bgg_ws.cuh disagree");
 static_assert(sizeof(WsHeader) == 248, "bench.py reports the per-instance result record as 248 bytes");
 
 static thread_local std::string g_err;
@@ -38,6 +39,8 @@ struct bgg_handle {
     WsHeader* d_hdr = nullptr;   // compact copy of the headers [batch]
     int* d_max = nullptr;        // batch maxima (nu, n_samples) of the current solve
     int* h_max = nullptr;        // pinned
+    int last_nu_max = 0, last_ns_max = 0;   // batch maxima of the last solve (shared-memory sizing of later kernels)
+    int max_smem = 0;
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
@@ -150,6 +153,7 @@ int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) 
     h->L = make_layout(P.N, P.max_nu);
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+    h->max_smem = max_smem;
     if (ipm_smem_bytes(h->L) > static_cast<size_t>(max_smem) || condense_smem_bytes(h->L) > static_cast<size_t>(max_smem)) {
         delete h;
         return fail(BGG_EINVAL, "num_nodes / max_spline_vars need more shared memory than the device offers");
@@ -301,6 +305,8 @@ int bgg_solve_resident(bgg_handle* h) {
     if (h->profiling) cudaEventRecord(h->ev[1], h->stream);
     CU(cudaStreamSynchronize(h->stream));
     const int nu_max = h->h_max[0] > 0 ? h->h_max[0] : 8, ns_max = h->h_max[1];
+    h->last_nu_max = nu_max;
+    h->last_ns_max = ns_max;
     launch_condense(h->P, h->L, h->d_ws, B, nu_max, h->stream);
     if (h->profiling) cudaEventRecord(h->ev[2], h->stream);
     launch_ipm(h->P, h->L, h->d_ws, B, nu_max, ns_max, h->stream);
@@ -502,6 +508,92 @@ int bgg_get_solution(bgg_handle* h, int b, double* qp_sol, double* z, double* la
     if (lam && (rc = fetch(h, lam, ws + h->L.lam, 8 * static_cast<size_t>(sz.m_ineq)))) return rc;
     if (slack && (rc = fetch(h, slack, ws + h->L.slack, 8 * static_cast<size_t>(sz.m_ineq)))) return rc;
     if (nu_eq && (rc = fetch(h, nu_eq, ws + h->L.nueq, 8 * static_cast<size_t>(sz.n_eq)))) return rc;
+    return BGG_OK;
+}
+
+int bgg_gait_gradient_batch(bgg_handle* h, int32_t* status, int32_t* n_contacts, double* dHdtheta) {
+    if (!h || !h->batch) return fail(BGG_EINVAL, "no batch");
+    if (!h->last_nu_max) return fail(BGG_ESTATE, "bgg_gait_gradient_batch needs a solve first");
+    CU(cudaSetDevice(h->device));
+    const int B = h->batch;
+    // 14 KB of the opt-in shared memory are taken by the kernel's static arrays (the four staged foot splines)
+    if (launch_gradient(h->P, h->d_inst, h->L, h->d_ws, B, h->last_nu_max, h->last_ns_max, h->max_smem - 14 * 1024, h->stream))
+        return fail(BGG_EINVAL, "the gait-gradient kernel needs more shared memory than the device offers for this many spline variables");
+    h->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<GradInfo> gi(B);
+    std::vector<double> dh(static_cast<size_t>(B) * kNumEE * kMaxContacts);
+    CU(cudaMemcpy2D(gi.data(), sizeof(GradInfo), h->d_ws + h->L.ginfo, h->L.stride, sizeof(GradInfo), B, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy2D(dh.data(), 8 * kNumEE * kMaxContacts, h->d_ws + h->L.gdH, h->L.stride, 8 * kNumEE * kMaxContacts, B,
+                    cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; ++b) {
+        if (status) status[b] = gi[b].status;
+        if (n_contacts)
+            for (int e = 0; e < kNumEE; ++e) n_contacts[b * kNumEE + e] = gi[b].nct[e];
+    }
+    if (dHdtheta) std::memcpy(dHdtheta, dh.data(), 8 * dh.size());
+    return BGG_OK;
+}
+
+int bgg_get_adjoint(bgg_handle* h, int b, double* dz, double* dlam, double* dnu_dyn, double* dnu_eq, double* nu_dyn) {
+    if (!h || b < 0 || b >= h->batch) return fail(BGG_EINVAL, "bad instance");
+    bgg_sizes sz;
+    int rc = bgg_get_sizes(h, b, &sz);
+    if (rc) return rc;
+    const char* ws = h->d_ws + static_cast<size_t>(b) * h->L.stride;
+    const size_t nd = 8 * static_cast<size_t>(kNx) * (h->P.N + 1);
+    if (dz && (rc = fetch(h, dz, ws + h->L.gdz, 8 * static_cast<size_t>(sz.n)))) return rc;
+    if (dlam && (rc = fetch(h, dlam, ws + h->L.gdlam, 8 * static_cast<size_t>(sz.m_ineq)))) return rc;
+    if (dnu_dyn && (rc = fetch(h, dnu_dyn, ws + h->L.gdnu, nd))) return rc;
+    if (dnu_eq && (rc = fetch(h, dnu_eq, ws + h->L.gdnue, 8 * static_cast<size_t>(sz.n_eq)))) return rc;
+    if (nu_dyn && (rc = fetch(h, nu_dyn, ws + h->L.dualx, nd))) return rc;
+    return BGG_OK;
+}
+
+int bgg_get_contact_times(bgg_handle* h, int first, int count, double* times, int32_t* types, int32_t* counts) {
+    if (!h || !times || !types || !counts || first < 0 || count <= 0 || first + count > h->batch) return fail(BGG_EINVAL, "bad range");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<Instance> tmp(count);
+    CU(cudaMemcpy(tmp.data(), h->d_inst + first, sizeof(Instance) * static_cast<size_t>(count), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < count; ++b)
+        for (int e = 0; e < kNumEE; ++e) {
+            const FootSpline& s = tmp[b].foot[e];
+            int c = 0;
+            for (int i = 0; i < BGG_MAX_CONTACTS; ++i) {
+                times[(b * kNumEE + e) * BGG_MAX_CONTACTS + i] = 0.0;
+                types[(b * kNumEE + e) * BGG_MAX_CONTACTS + i] = 0;
+            }
+            for (int i = 0; i < s.n && c < BGG_MAX_CONTACTS; ++i)
+                if (s.ttype[i] != kInter) {
+                    times[(b * kNumEE + e) * BGG_MAX_CONTACTS + c] = s.t[i];
+                    types[(b * kNumEE + e) * BGG_MAX_CONTACTS + c] = s.ttype[i];
+                    c++;
+                }
+            counts[b * kNumEE + e] = c;
+        }
+    return BGG_OK;
+}
+
+int bgg_set_solution(bgg_handle* h, int b, const double* qp_sol, const double* z, const double* lam, const double* slack,
+                     const double* nu_eq) {
+    if (!h || b < 0 || b >= h->batch) return fail(BGG_EINVAL, "bad instance");
+    bgg_sizes sz;
+    int rc = bgg_get_sizes(h, b, &sz);
+    if (rc) return rc;
+    char* ws = h->d_ws + static_cast<size_t>(b) * h->L.stride;
+    const size_t ustart = static_cast<size_t>(kNx) * (h->P.N + 1);
+    if (qp_sol) {
+        CU(cudaMemcpy(ws + h->L.zqp, qp_sol, 8 * static_cast<size_t>(sz.n), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ws + h->L.u, qp_sol + ustart, 8 * static_cast<size_t>(sz.nu), cudaMemcpyHostToDevice));
+    }
+    if (z) CU(cudaMemcpy(ws + h->L.zprev, z, 8 * static_cast<size_t>(sz.n), cudaMemcpyHostToDevice));
+    if (lam) CU(cudaMemcpy(ws + h->L.lam, lam, 8 * static_cast<size_t>(sz.m_ineq), cudaMemcpyHostToDevice));
+    if (slack) CU(cudaMemcpy(ws + h->L.slack, slack, 8 * static_cast<size_t>(sz.m_ineq), cudaMemcpyHostToDevice));
+    if (nu_eq) CU(cudaMemcpy(ws + h->L.nueq, nu_eq, 8 * static_cast<size_t>(sz.n_eq), cudaMemcpyHostToDevice));
+    const int32_t st = kSolved;
+    CU(cudaMemcpy(ws + h->L.hdr + offsetof(WsHeader, status), &st, sizeof st, cudaMemcpyHostToDevice));
     return BGG_OK;
 }
 

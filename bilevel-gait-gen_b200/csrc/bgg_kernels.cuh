@@ -62,4 +62,9 @@ void launch_export_csc(const Params& P, const WsLayout& L, const char* ws, int B
                        double* p_diag, double* q, double* ub, int32_t* dims, int n_stride, int m_stride, int nnz_cap,
                        cudaStream_t stream);
 
+// gait gradient (csrc/bgg_gradient.cu); returns -1 when the shared memory it needs exceeds max_smem
+int launch_gradient(const Params& P, const Instance* inst, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int max_smem,
+                    cudaStream_t stream);
+size_t gradient_smem_bytes(const WsLayout& L, int nu_max, int ns_max);
+
 }  // namespace bgg

@@ -56,11 +56,22 @@ struct EqRow {                // touch-down / foot-start rows: w . u_pos[col] = 
 };
 
 constexpr int kMaxEq = 16;
+constexpr int kMaxContacts = 12;   // contact times (LiftOff / TouchDown knots) per foot inside kMaxKnots
+
+struct GradInfo {             // result record of the gait-gradient kernel
+    int32_t status;           // 0 ok, 1 last solve was not `Solved` (the reference returns false), 2 singular system
+    int32_t n_theta;
+    int32_t nct[kNumEE];      // contact times per foot
+    int32_t pad[2];
+    double pivot_min;         // smallest |pivot| of the LU factorisation (diagnostic)
+    double resid;             // relative residual of the reduced adjoint system after refinement
+};
 constexpr int kMaxSamples = kNumEE * kMaxStances * kSamplesPerStance;
 
 struct WsLayout {             // byte offsets inside one instance's workspace
     size_t stride;
     size_t hdr, nodes, samples, eq, zprev, H, g, phipos, xoff, u, lam, slack, nueq, zqp, dualx;
+    size_t gdx, gdz, gdlam, gdnu, gdnue, gdH, ginfo;   // gait-gradient outputs (csrc/bgg_gradient.cu)
     int32_t N, max_nu, max_rows, pad;
 };
 
@@ -87,6 +98,13 @@ inline WsLayout make_layout(int N, int max_nu) {
     L.nueq = take(8 * kMaxEq);
     L.zqp = take(8 * n_max);
     L.dualx = take(8 * static_cast<size_t>(kNx) * (N + 1));           // dynamics multipliers (adjoint recursion)
+    L.gdx = take(8 * n_max);                                          // P z + q at prev_qp_sol
+    L.gdz = take(8 * n_max);                                          // adjoint: dz
+    L.gdlam = take(8 * static_cast<size_t>(L.max_rows));              // dlam (kernel row order)
+    L.gdnu = take(8 * static_cast<size_t>(kNx) * (N + 1));            // dnu of the dynamics rows
+    L.gdnue = take(8 * kMaxEq);                                       // dnu of the touch-down / foot-start rows
+    L.gdH = take(8 * kNumEE * kMaxContacts);                          // dH/dtheta, foot-major
+    L.ginfo = take(sizeof(GradInfo));
     L.stride = o;
     return L;
 }

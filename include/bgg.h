@@ -148,6 +148,31 @@ int bgg_export_qp_csc(bgg_handle* h, int first, int count, int32_t* dims, int32_
  * lam / slack [m_ineq] in the kernel's row order (see csrc/bgg_ipm.cu), nu_eq [n_eq]. */
 int bgg_get_solution(bgg_handle* h, int instance, double* qp_sol, double* z, double* lam, double* slack, double* nu_eq);
 
+/* --- gait optimiser: derivative of the cost with respect to the contact times ------------------------------------- */
+#define BGG_MAX_CONTACTS 12   /* contact times (LiftOff / TouchDown knots) per foot */
+
+/* MPCController::GaitOpt's derivative chain for every instance, after a solve (controllers/mpc_controller.cpp:518-552):
+ * MPC::ComputeDerivativeTerms + GetQPPartials (mpc.cpp:1047-1069; clarabel_interface.cpp:182-260, 262-612),
+ * MPCSingleRigidBody::ComputeParamPartialsClarabel for every contact time (mpc_single_rigid_body.cpp:642-792),
+ * GaitOptimizer::ModifyQPPartials + ComputeCostFcnDerivWrtContactTimes (gait_optimizer.cpp:92-179, 536-539).
+ * dHdtheta [batch][4][BGG_MAX_CONTACTS] (foot-major, unused entries 0); n_contacts [batch][4];
+ * status [batch]: 0 ok, 1 the last solve was not `Solved` (the reference's calls return false), 2 singular system. */
+int bgg_gait_gradient_batch(bgg_handle* h, int32_t* status, int32_t* n_contacts, double* dHdtheta);
+
+/* Adjoint of the last bgg_gait_gradient_batch for one instance (parity tap): dz [n], dlam [m_ineq] (kernel row order),
+ * dnu_dyn / nu_dyn [12 (N+1)] (differential and value of the dynamics-row multipliers), dnu_eq [n_eq]. */
+int bgg_get_adjoint(bgg_handle* h, int instance, double* dz, double* dlam, double* dnu_dyn, double* dnu_eq, double* nu_dyn);
+
+/* Trajectory::GetContactTimes (mpc/trajectory.cpp:339-346) of instances [first, first+count):
+ * times / types [count][4][BGG_MAX_CONTACTS] (type 0 LiftOff, 1 TouchDown), counts [count][4]. */
+int bgg_get_contact_times(bgg_handle* h, int first, int count, double* times, int32_t* types, int32_t* counts);
+
+/* Parity tap: overwrite the stored solution of the last solve of one instance (any pointer may be NULL) so that the
+ * derivative kernels can be checked on exactly the primal / dual point another solver produced.  Layouts as in
+ * bgg_get_solution; the status of the instance is set to BGG_SOLVED. */
+int bgg_set_solution(bgg_handle* h, int instance, const double* qp_sol, const double* z, const double* lam, const double* slack,
+                     const double* nu_eq);
+
 /* Raw trajectory of one instance (the POD bgg::Instance of csrc/bgg_types.cuh). */
 size_t bgg_instance_bytes(void);
 int bgg_get_instance(bgg_handle* h, int instance, void* out);

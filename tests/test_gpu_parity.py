@@ -191,3 +191,132 @@ def test_full_size_batch_properties():
     for b in (0, 1234, 4095):
         sz = gpu.sizes(b)
         assert sz["prim_res"] < 1e-6 and sz["error"] == 0
+
+
+def _gradient_case(cfg_name, states, ee, rt_steps=1, tol_gap=0.0):
+    """Oracle and CUDA path solve the same RTI step from a mirrored trajectory; returns both sides' derivative data."""
+    import gait_oracle as go
+    B = len(states)
+    kw = dict(ipm_tol=1e-8, ipm_tol_gap=tol_gap) if tol_gap > 0 else {}
+    gpu = common.make_gpu(cfg_name, B, states, **kw)
+    oracles = []
+    for b in range(B):
+        o = common.make_oracle(cfg_name, states[b])
+        if tol_gap > 0:
+            o.set_ipm(tol_gap=tol_gap)
+        o.initial_run(states[b], ee[b])
+        common.mirror_oracle_to_gpu(o, gpu, b)
+        oracles.append(o)
+    t0 = np.zeros(B)
+    for _ in range(rt_steps):
+        out = gpu.GetRealTimeUpdate(states, t0, ee)
+    for b in range(B):
+        for _ in range(rt_steps):
+            oracles[b].solve(states[b], 0.0, ee[b], real_time=True)
+    return gpu, oracles, out, go
+
+
+@pytest.mark.parametrize("cfg_name", ["a1_configuration", "a1_gait_opt_config"])
+def test_gait_gradient_matches_oracle(cfg_name):
+    """Kernel 6: adjoint of the QP and dH/dtheta for every contact time, against the oracle's restatement
+    of ClarabelInterface::SetupDerivativeCalcs (sparse LU of the full differential system) and ComputeParamPartialsClarabel.
+    Tolerance 1e-4 relative (north_star)."""
+    cfg = wl.CONFIGS[cfg_name]
+    N = cfg["num_nodes"]
+    B = 3
+    states, _, ee = wl.batched_trot_inputs(cfg, B, seed=21)
+    states[0] = cfg["srb_init"]
+    ee[0] = wl.EE_NOMINAL
+    gpu, oracles, out, go = _gradient_case(cfg_name, states, ee)
+    res = gpu.ComputeCostFcnDerivWrtContactTimes()
+    checked = 0
+    for b in range(B):
+        o = oracles[b]
+        terms = go.derivative_terms(o)
+        if terms is None or out["status"][b] != 0:
+            assert res["status"][b] == 1 or terms is None
+            continue
+        assert res["status"][b] == 0
+        ct = go.contact_times(o)
+        assert [len(t) for t, _ in ct] == res["n_contacts"][b].tolist()
+        gt, gty, gn = gpu.GetContactTimes(b, 1)
+        for e in range(4):
+            assert np.array_equal(gt[0, e, :gn[0, e]], ct[e][0]) and np.array_equal(gty[0, e, :gn[0, e]], ct[e][1])
+        adj = gpu.adjoint(b)
+        sol = gpu.solution(b)
+        order = common.gpu_rows_to_reference_order(sol, N)
+        nd = 12 * (N + 1)
+        # dz itself is tiny (|dz| ~ 1e-3 against multipliers of 1e3) and moves by percents with the last digits of the
+        # solver's final (lam, s); it is checked on identical inputs in test_gait_gradient_kernel_on_injected_solution
+        assert _rel(adj["nu_dyn"], terms["nu"][:nd]) < 1e-6
+        assert _rel(adj["dnu_dyn"], terms["dnu"][:nd]) < 1e-4
+        assert _rel(adj["dnu_eq"], terms["dnu"][nd:]) < 1e-4
+        assert np.abs(adj["dlam"][order] * sol["lam"][order] - terms["dlam"] * terms["lam"]).max() <= 1e-4 * max(
+            1.0, np.abs(terms["dlam"] * terms["lam"]).max())
+        g_o = go.cost_gradient(o, terms)
+        g = res["dHdtheta"][b]
+        assert g.shape == g_o.shape
+        assert np.abs(g - g_o).max() <= 1e-4 * max(1.0, np.abs(g_o).max()), (g, g_o)
+        checked += 1
+    assert checked >= 2
+
+
+@pytest.mark.parametrize("cfg_name", ["a1_configuration", "a1_gait_opt_config"])
+def test_gait_gradient_kernel_on_injected_solution(cfg_name):
+    """Kernel 6 in isolation: the oracle's primal / dual point and trajectory are written into the CUDA path's workspace,
+    so both sides differentiate the same point.  The condensed LU + Schur complement + refinement then has to reproduce
+    the sparse LU of the full (n+m)^2 differential system: dz within 1e-5, dH/dtheta within 1e-8 relative."""
+    cfg = wl.CONFIGS[cfg_name]
+    N = cfg["num_nodes"]
+    B = 3
+    states, _, ee = wl.batched_trot_inputs(cfg, B, seed=21)
+    states[0] = cfg["srb_init"]
+    ee[0] = wl.EE_NOMINAL
+    gpu, oracles, out, go = _gradient_case(cfg_name, states, ee)
+    nd = 12 * (N + 1)
+    all_terms = []
+    for b in range(B):
+        o = oracles[b]
+        terms = go.derivative_terms(o)
+        all_terms.append(terms)
+        if terms is None:
+            continue
+        sol = gpu.solution(b)
+        order = common.gpu_rows_to_reference_order(sol, N)
+        lam_k, s_k = np.zeros_like(sol["lam"]), np.zeros_like(sol["slack"])
+        lam_k[order], s_k[order] = terms["lam"], terms["slack"]
+        common.mirror_oracle_to_gpu(o, gpu, b)
+        gpu.set_solution(b, qp_sol=terms["primal"], z=terms["z"], lam=lam_k, slack=s_k, nu_eq=terms["nu"][nd:])
+    res = gpu.ComputeCostFcnDerivWrtContactTimes()
+    checked = 0
+    for b in range(B):
+        terms = all_terms[b]
+        if terms is None:
+            continue
+        assert res["status"][b] == 0
+        adj = gpu.adjoint(b)
+        assert _rel(adj["dz"], terms["dz"]) < 1e-5
+        assert _rel(adj["nu_dyn"], terms["nu"][:nd]) < 1e-10
+        assert _rel(adj["dnu_dyn"], terms["dnu"][:nd]) < 1e-8
+        assert _rel(adj["dnu_eq"], terms["dnu"][nd:]) < 1e-8
+        g_o = go.cost_gradient(oracles[b], terms)
+        assert np.abs(res["dHdtheta"][b] - g_o).max() <= 1e-8 * max(1.0, np.abs(g_o).max())
+        checked += 1
+    assert checked >= 2
+
+
+def test_gait_gradient_refuses_unsolved_instances():
+    """MPC::ComputeDerivativeTerms returns false unless the last solve was `Solved` (mpc.cpp:1047-1057)."""
+    cfg_name = "a1_configuration"
+    cfg = wl.CONFIGS[cfg_name]
+    B = 64
+    states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=0)
+    gpu = common.make_gpu(cfg_name, B, states)
+    out = gpu.GetRealTimeUpdate(states, t0, ee)
+    res = gpu.ComputeCostFcnDerivWrtContactTimes()
+    assert np.array_equal(res["status"] == 0, out["status"] == 0)
+    assert np.any(out["status"] != 0), "the first solve from pinned random feet leaves some instances infeasible"
+    for b in np.flatnonzero(out["status"] != 0):
+        assert res["status"][b] == 1 and np.all(res["raw"][b] == 0)
+    for b in np.flatnonzero(out["status"] == 0)[:8]:
+        assert np.all(np.isfinite(res["dHdtheta"][b])) and len(res["dHdtheta"][b]) == 20
