@@ -85,6 +85,8 @@ def lib():
         L.bgg_get_condensed.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
         L.bgg_export_qp_csc.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _ip, _dp, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int]
         L.bgg_gait_gradient_batch.argtypes = [C.c_void_p, _ip, _ip, _dp]
+        L.bgg_optimize_contact_times_batch.argtypes = [C.c_void_p, _dp, C.c_double, C.c_double, _dp, _dp, _dp, _dp, _ip]
+        L.bgg_line_search_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _ip]
         L.bgg_get_adjoint.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
         L.bgg_get_contact_times.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _ip, _ip]
         L.bgg_set_solution.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
@@ -103,7 +105,8 @@ def exported_symbols():
     return ["bgg_last_error", "bgg_device_count", "bgg_create", "bgg_destroy", "bgg_set_costs", "bgg_batch_reset",
             "bgg_set_warm_states", "bgg_set_contact_times", "bgg_solve_batch", "bgg_upload_inputs", "bgg_solve_resident",
             "bgg_download_results", "bgg_synchronize", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count", "bgg_event_record", "bgg_event_elapsed_ms",
-            "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_export_qp_csc", "bgg_gait_gradient_batch", "bgg_get_adjoint",
+            "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_export_qp_csc", "bgg_gait_gradient_batch", "bgg_optimize_contact_times_batch",
+            "bgg_line_search_batch", "bgg_get_adjoint",
             "bgg_get_contact_times", "bgg_set_solution", "bgg_get_solution", "bgg_instance_bytes",
             "bgg_get_instance", "bgg_set_instance", "bgg_get_states", "bgg_eval_splines"]
 
@@ -321,6 +324,28 @@ class BatchedMPC:
         self._chk(self.L.bgg_gait_gradient_batch(self.h, _i(status), _i(nct), _d(dh)))
         grads = [np.concatenate([dh[b, e, :nct[b, e]] for e in range(NUM_EE)]) for b in range(B)]
         return dict(status=status, n_contacts=nct, dHdtheta=grads, raw=dh)
+
+    def OptimizeContactTimes(self, time, dHdtheta=None, trust=1.0, alpha=1.0):
+        """GaitOptimizer::OptimizeContactTimes for the whole batch.  dHdtheta: [B][4][MAX_CONTACTS] or None (use the last
+        gradient).  Returns dict(step, xk, new_times: [B][4][MAX_CONTACTS]; status [B][4])."""
+        B = self.B
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(time, np.float64), (B,)))
+        step, xk, nt = (np.zeros((B, NUM_EE, MAX_CONTACTS)) for _ in range(3))
+        st = np.zeros((B, NUM_EE), np.int32)
+        g = None if dHdtheta is None else np.ascontiguousarray(dHdtheta, np.float64)
+        self._chk(self.L.bgg_optimize_contact_times_batch(self.h, _d(t), trust, alpha, None if g is None else _d(g), _d(step), _d(xk),
+                                                          _d(nt), _i(st)))
+        return dict(step=step, xk=xk, new_times=nt, status=st)
+
+    def LineSearch(self, state, time, ee_start_locations, xk, step, K=10):
+        """GaitOptimizer::LineSearch for the whole batch (K = LS_SIZE copies per instance, all solved as one batch)."""
+        s, t, e = self._inputs(state, time, ee_start_locations)
+        B = self.B
+        best, costs, q = np.zeros(B, np.int32), np.zeros((B, K)), np.zeros((B, K), np.int32)
+        xk = np.ascontiguousarray(xk, np.float64)
+        step = np.ascontiguousarray(step, np.float64)
+        self._chk(self.L.bgg_line_search_batch(self.h, K, _d(xk), _d(step), _d(s), _d(t), _d(e), _i(best), _d(costs), _i(q)))
+        return dict(best=best, costs=costs, quality=q)
 
     def adjoint(self, b=0):
         sz = self.sizes(b)

@@ -13,6 +13,7 @@ $NVCC $ARCH $COMMON -dc -o build/bgg_ipm.o csrc/bgg_ipm.cu 2> build/ptxas_ipm.lo
 $NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_finish.o csrc/bgg_finish.cu 2> build/ptxas_finish.log
 $NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_assemble.o csrc/bgg_assemble.cu 2> build/ptxas_assemble.log
 $NVCC $ARCH $COMMON -dc -o build/bgg_gradient.o csrc/bgg_gradient.cu 2> build/ptxas_gradient.log
+$NVCC $ARCH $COMMON -dc -o build/bgg_gait.o csrc/bgg_gait.cu 2> build/ptxas_gait.log
 $NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_capi.o csrc/bgg_capi.cu 2> build/ptxas_capi.log
-$NVCC $ARCH -shared -o libbgg_b200.so build/bgg_prepare.o build/bgg_condense.o build/bgg_ipm.o build/bgg_finish.o build/bgg_assemble.o build/bgg_gradient.o build/bgg_capi.o -lcudart
+$NVCC $ARCH -shared -o libbgg_b200.so build/bgg_prepare.o build/bgg_condense.o build/bgg_ipm.o build/bgg_finish.o build/bgg_assemble.o build/bgg_gradient.o build/bgg_gait.o build/bgg_capi.o -lcudart
 echo "built $(pwd)/libbgg_b200.so"

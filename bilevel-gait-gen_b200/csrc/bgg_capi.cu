@@ -47,6 +47,11 @@ struct bgg_handle {
     int64_t launches = 0;
     cudaEvent_t user_ev[8] = {};
     bool costs_set = false;
+    // line-search children (batch x K copies), allocated on first use
+    int ls_cap = 0;
+    Instance* d_ls_inst = nullptr;
+    char* d_ls_ws = nullptr;
+    double *d_ls_state = nullptr, *d_ls_t0 = nullptr, *d_ls_ee = nullptr;
 };
 
 __global__ void k_gather_headers(WsLayout L, const char* __restrict__ ws, WsHeader* __restrict__ out, int B) {
@@ -181,6 +186,15 @@ static void free_batch(bgg_handle* h) {
     cudaFreeHost(h->h_t0);
     cudaFreeHost(h->h_ee);
     cudaFreeHost(h->h_hdr);
+    cudaFree(h->d_ls_inst);
+    cudaFree(h->d_ls_ws);
+    cudaFree(h->d_ls_state);
+    cudaFree(h->d_ls_t0);
+    cudaFree(h->d_ls_ee);
+    h->d_ls_inst = nullptr;
+    h->d_ls_ws = nullptr;
+    h->d_ls_state = h->d_ls_t0 = h->d_ls_ee = nullptr;
+    h->ls_cap = 0;
     h->d_inst = nullptr;
     h->d_ws = nullptr;
     h->d_state = h->d_t0 = h->d_ee = nullptr;
@@ -292,30 +306,35 @@ int bgg_upload_inputs(bgg_handle* h, const double* state, const double* t0, cons
     return BGG_OK;
 }
 
-int bgg_solve_resident(bgg_handle* h) {
-    if (!h || !h->batch) return fail(BGG_EINVAL, "no batch");
-    if (!h->costs_set) return fail(BGG_ESTATE, "bgg_set_costs has not been called");
-    CU(cudaSetDevice(h->device));
-    const int B = h->batch;
-    if (h->profiling) cudaEventRecord(h->ev[0], h->stream);
-    launch_prepare(h->P, h->d_inst, h->d_state, h->d_t0, h->d_ee, h->L, h->d_ws, B, h->stream);
+// steps 1-11 of MPCSingleRigidBody::Solve for `B` instances living in (inst, ws) with inputs (state, t0, ee) on the device
+static int solve_pipeline(bgg_handle* h, Instance* inst, char* ws, const double* state, const double* t0, const double* ee, int B,
+                          bool profile) {
+    if (profile) cudaEventRecord(h->ev[0], h->stream);
+    launch_prepare(h->P, inst, state, t0, ee, h->L, ws, B, h->stream);
     // shared memory (and with it the number of CTAs per SM) is sized from this batch's actual problem sizes
-    launch_batch_max(h->L, h->d_ws, B, h->d_max, h->stream);
+    launch_batch_max(h->L, ws, B, h->d_max, h->stream);
     CU(cudaMemcpyAsync(h->h_max, h->d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    if (h->profiling) cudaEventRecord(h->ev[1], h->stream);
+    if (profile) cudaEventRecord(h->ev[1], h->stream);
     CU(cudaStreamSynchronize(h->stream));
     const int nu_max = h->h_max[0] > 0 ? h->h_max[0] : 8, ns_max = h->h_max[1];
     h->last_nu_max = nu_max;
     h->last_ns_max = ns_max;
-    launch_condense(h->P, h->L, h->d_ws, B, nu_max, h->stream);
-    if (h->profiling) cudaEventRecord(h->ev[2], h->stream);
-    launch_ipm(h->P, h->L, h->d_ws, B, nu_max, ns_max, h->stream);
-    if (h->profiling) cudaEventRecord(h->ev[3], h->stream);
-    launch_finish(h->P, h->d_inst, h->L, h->d_ws, B, h->stream);
-    if (h->profiling) cudaEventRecord(h->ev[4], h->stream);
+    launch_condense(h->P, h->L, ws, B, nu_max, h->stream);
+    if (profile) cudaEventRecord(h->ev[2], h->stream);
+    launch_ipm(h->P, h->L, ws, B, nu_max, ns_max, h->stream);
+    if (profile) cudaEventRecord(h->ev[3], h->stream);
+    launch_finish(h->P, inst, h->L, ws, B, h->stream);
+    if (profile) cudaEventRecord(h->ev[4], h->stream);
     h->launches += 5;
     CU(cudaGetLastError());
     return BGG_OK;
+}
+
+int bgg_solve_resident(bgg_handle* h) {
+    if (!h || !h->batch) return fail(BGG_EINVAL, "no batch");
+    if (!h->costs_set) return fail(BGG_ESTATE, "bgg_set_costs has not been called");
+    CU(cudaSetDevice(h->device));
+    return solve_pipeline(h, h->d_inst, h->d_ws, h->d_state, h->d_t0, h->d_ee, h->batch, h->profiling);
 }
 
 int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double* alpha, double* cost) {
@@ -533,6 +552,83 @@ int bgg_gait_gradient_batch(bgg_handle* h, int32_t* status, int32_t* n_contacts,
             for (int e = 0; e < kNumEE; ++e) n_contacts[b * kNumEE + e] = gi[b].nct[e];
     }
     if (dHdtheta) std::memcpy(dHdtheta, dh.data(), 8 * dh.size());
+    return BGG_OK;
+}
+
+int bgg_optimize_contact_times_batch(bgg_handle* h, const double* time, double trust, double alpha, const double* dHdtheta,
+                                     double* step, double* xk, double* new_times, int32_t* status) {
+    if (!h || !h->batch || !time || !step || !xk || !new_times) return fail(BGG_EINVAL, "null argument / no batch");
+    CU(cudaSetDevice(h->device));
+    const size_t B = h->batch, nv = B * kNumEE * kMaxContacts;
+    double *d_time, *d_grad = nullptr, *d_out;
+    int32_t* d_st;
+    CU(cudaMalloc(&d_time, 8 * B));
+    CU(cudaMalloc(&d_out, 8 * 3 * nv));
+    CU(cudaMalloc(&d_st, 4 * B * kNumEE));
+    CU(cudaMemcpyAsync(d_time, time, 8 * B, cudaMemcpyHostToDevice, h->stream));
+    if (dHdtheta) {
+        CU(cudaMalloc(&d_grad, 8 * nv));
+        CU(cudaMemcpyAsync(d_grad, dHdtheta, 8 * nv, cudaMemcpyHostToDevice, h->stream));
+    }
+    launch_gait_lp(h->d_inst, h->L, h->d_ws, h->batch, d_grad, d_time, trust, alpha, d_out, d_out + nv, d_out + 2 * nv, d_st, h->stream);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(step, d_out, 8 * nv, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(xk, d_out + nv, 8 * nv, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(new_times, d_out + 2 * nv, 8 * nv, cudaMemcpyDeviceToHost));
+    if (status) CU(cudaMemcpy(status, d_st, 4 * B * kNumEE, cudaMemcpyDeviceToHost));
+    cudaFree(d_time);
+    cudaFree(d_out);
+    cudaFree(d_st);
+    if (d_grad) cudaFree(d_grad);
+    return BGG_OK;
+}
+
+int bgg_line_search_batch(bgg_handle* h, int K, const double* xk, const double* step, const double* state, const double* t0,
+                          const double* ee_start, int32_t* best, double* costs, int32_t* quality) {
+    if (!h || !h->batch || K <= 0 || !xk || !step || !state || !t0 || !ee_start) return fail(BGG_EINVAL, "null argument / no batch");
+    if (!h->costs_set) return fail(BGG_ESTATE, "bgg_set_costs has not been called");
+    CU(cudaSetDevice(h->device));
+    const size_t B = h->batch, C = B * K, nv = B * kNumEE * kMaxContacts;
+    if (static_cast<int>(C) > h->ls_cap) {
+        CU(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_ls_inst); cudaFree(h->d_ls_ws); cudaFree(h->d_ls_state); cudaFree(h->d_ls_t0); cudaFree(h->d_ls_ee);
+        h->ls_cap = 0;
+        CU(cudaMalloc(&h->d_ls_inst, sizeof(Instance) * C));
+        CU(cudaMalloc(&h->d_ls_ws, h->L.stride * C));
+        CU(cudaMalloc(&h->d_ls_state, 8 * kNxMan * C));
+        CU(cudaMalloc(&h->d_ls_t0, 8 * C));
+        CU(cudaMalloc(&h->d_ls_ee, 8 * 12 * C));
+        CU(cudaMemsetAsync(h->d_ls_ws, 0, h->L.stride * C, h->stream));
+        h->ls_cap = static_cast<int>(C);
+    }
+    int rc = bgg_upload_inputs(h, state, t0, ee_start);
+    if (rc) return rc;
+    double* d_vec;
+    int32_t *d_best, *d_q;
+    double* d_costs;
+    CU(cudaMalloc(&d_vec, 8 * 2 * nv));
+    CU(cudaMalloc(&d_best, 4 * B));
+    CU(cudaMalloc(&d_q, 4 * C));
+    CU(cudaMalloc(&d_costs, 8 * C));
+    CU(cudaMemcpyAsync(d_vec, xk, 8 * nv, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_vec + nv, step, 8 * nv, cudaMemcpyHostToDevice, h->stream));
+    launch_ls_expand(h->d_inst, h->d_ls_inst, h->batch, K, d_vec, d_vec + nv, h->d_state, h->d_t0, h->d_ee, h->d_ls_state, h->d_ls_t0,
+                     h->d_ls_ee, h->stream);
+    rc = solve_pipeline(h, h->d_ls_inst, h->d_ls_ws, h->d_ls_state, h->d_ls_t0, h->d_ls_ee, static_cast<int>(C), false);
+    if (rc) return rc;
+    launch_ls_select(h->d_inst, h->d_ls_inst, h->L, h->d_ls_ws, h->batch, K, d_best, d_costs, d_q, h->stream);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    if (best) CU(cudaMemcpy(best, d_best, 4 * B, cudaMemcpyDeviceToHost));
+    if (costs) CU(cudaMemcpy(costs, d_costs, 8 * C, cudaMemcpyDeviceToHost));
+    if (quality) CU(cudaMemcpy(quality, d_q, 4 * C, cudaMemcpyDeviceToHost));
+    cudaFree(d_vec);
+    cudaFree(d_best);
+    cudaFree(d_q);
+    cudaFree(d_costs);
     return BGG_OK;
 }
 

@@ -67,4 +67,12 @@ int launch_gradient(const Params& P, const Instance* inst, const WsLayout& L, ch
                     cudaStream_t stream);
 size_t gradient_smem_bytes(const WsLayout& L, int nu_max, int ns_max);
 
+// gait optimiser outer step (csrc/bgg_gait.cu)
+void launch_gait_lp(const Instance* inst, const WsLayout& L, const char* ws, int B, const double* grad, const double* time, double trust,
+                    double alpha, double* step, double* xk, double* times, int32_t* status, cudaStream_t stream);
+void launch_ls_expand(const Instance* parent, Instance* child, int B, int K, const double* xk, const double* step, const double* state,
+                      const double* t0, const double* ee, double* c_state, double* c_t0, double* c_ee, cudaStream_t stream);
+void launch_ls_select(Instance* parent, const Instance* child, const WsLayout& L, const char* child_ws, int B, int K, int32_t* best,
+                      double* costs, int32_t* quality, cudaStream_t stream);
+
 }  // namespace bgg

@@ -159,6 +159,24 @@ int bgg_get_solution(bgg_handle* h, int instance, double* qp_sol, double* z, dou
  * status [batch]: 0 ok, 1 the last solve was not `Solved` (the reference's calls return false), 2 singular system. */
 int bgg_gait_gradient_batch(bgg_handle* h, int32_t* status, int32_t* n_contacts, double* dHdtheta);
 
+/* GaitOptimizer::OptimizeContactTimes (mpc/gait_optimizer.cpp:185-364; constraint builders :410-534) for every
+ * instance: the LP  min dH/dtheta . s  over the step of all contact times (polytope / start / trust-region / next-node
+ * rows; BFGS is disabled in the reference).  time [batch] is the current time, trust the infinity-norm trust region
+ * (the reference's Delta_ = 1), alpha scales the step (`step_ = alpha * step_`).  dHdtheta [batch][4][BGG_MAX_CONTACTS]
+ * or NULL to use each instance's last bgg_gait_gradient_batch result.  Outputs, each [batch][4][BGG_MAX_CONTACTS]:
+ * step, xk (the contact times the step applies to) and new_times = ConvertQPVecToContactTimes(xk + step);
+ * status [batch][4]: 0 converged, 2 iteration limit.  The instances are not modified. */
+int bgg_optimize_contact_times_batch(bgg_handle* h, const double* time, double trust, double alpha, const double* dHdtheta,
+                                     double* step, double* xk, double* new_times, int32_t* status);
+
+/* GaitOptimizer::LineSearch (mpc/gait_optimizer.cpp:671-753) for every instance: K copies, copy i with the contact times
+ * ConvertQPVecToContactTimes(xk + (i / K) step) (GetContactTimes(alpha), :645-669), one RTI solve each from
+ * (state, t0, ee_start) -- all batch x K solves run as one batch on the device -- then the arg-min of
+ * cost / num_decision_vars over the copies that are not primal infeasible and SetWarmStartTrajectory(best).
+ * The reference's LS_SIZE is 10.  best [batch] (-1: every copy infeasible, copy 0 is kept), costs / quality [batch][K]. */
+int bgg_line_search_batch(bgg_handle* h, int K, const double* xk, const double* step, const double* state, const double* t0,
+                          const double* ee_start, int32_t* best, double* costs, int32_t* quality);
+
 /* Adjoint of the last bgg_gait_gradient_batch for one instance (parity tap): dz [n], dlam [m_ineq] (kernel row order),
  * dnu_dyn / nu_dyn [12 (N+1)] (differential and value of the dynamics-row multipliers), dnu_eq [n_eq]. */
 int bgg_get_adjoint(bgg_handle* h, int instance, double* dz, double* dlam, double* dnu_dyn, double* dnu_eq, double* nu_dyn);

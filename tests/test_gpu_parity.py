@@ -320,3 +320,68 @@ def test_gait_gradient_refuses_unsolved_instances():
         assert res["status"][b] == 1 and np.all(res["raw"][b] == 0)
     for b in np.flatnonzero(out["status"] == 0)[:8]:
         assert np.all(np.isfinite(res["dHdtheta"][b])) and len(res["dHdtheta"][b]) == 20
+
+
+@pytest.mark.parametrize("cfg_name", ["a1_configuration", "a1_gait_opt_config"])
+def test_contact_time_lp_and_line_search_match_oracle(cfg_name):
+    """SURVEY 8a20-a21: GaitOptimizer::OptimizeContactTimes (the LP over the contact-time step) and
+    GaitOptimizer::LineSearch (LS_SIZE = 10 re-solves, arg-min of cost / n), CUDA path against the oracle."""
+    cfg = wl.CONFIGS[cfg_name]
+    B = 3
+    states, _, ee = wl.batched_trot_inputs(cfg, B, seed=21)
+    states[0] = cfg["srb_init"]
+    ee[0] = wl.EE_NOMINAL
+    gpu, oracles, out, go = _gradient_case(cfg_name, states, ee)
+    res = gpu.ComputeCostFcnDerivWrtContactTimes()
+    lp = gpu.OptimizeContactTimes(0.0)            # on the CUDA path's own gradient
+    assert np.all(lp["status"] == 0)
+    # LP: against the oracle's LP optimum for the oracle's gradient (the two gradients agree to 1e-7, the optimum is a vertex)
+    steps_o, xk_o = [], []
+    for b in range(B):
+        o = oracles[b]
+        if res["status"][b] != 0 or o.qp_solution()["status"] != 0:
+            steps_o.append(None)
+            xk_o.append(None)
+            continue
+        ct = go.contact_times(o)
+        g_o = go.cost_gradient(o)
+        s_o = go.solve_gait_lp(ct, g_o, 0.0)
+        counts = [len(t) for t, _ in ct]
+        s_g = np.concatenate([lp["step"][b, e, :counts[e]] for e in range(4)])
+        x_g = np.concatenate([lp["xk"][b, e, :counts[e]] for e in range(4)])
+        assert np.abs(s_g - s_o).max() < 1e-6, (s_g, s_o)
+        assert np.array_equal(x_g, np.concatenate([t for t, _ in ct]))
+        nt_o = np.concatenate(go.contact_times_for(ct, x_g, s_o, 1.0))
+        nt_g = np.concatenate([lp["new_times"][b, e, :counts[e]] for e in range(4)])
+        assert np.abs(nt_g - nt_o).max() < 1e-6
+        steps_o.append(s_o)
+        xk_o.append(x_g)
+    # line search with LS_SIZE = 10 from the same step on both sides
+    K = 10
+    ls = gpu.LineSearch(states, np.zeros(B), ee, lp["xk"], lp["step"], K=K)
+    checked = 0
+    for b in range(B):
+        if steps_o[b] is None:
+            continue
+        o = oracles[b]
+        ct = go.contact_times(o)
+        best_o, costs_o, q_o = go.line_search(o, states[b], 0.0, ee[b], ct, xk_o[b], steps_o[b], ls_size=K)
+        assert np.array_equal(ls["quality"][b], q_o), (ls["quality"][b], q_o)
+        ok = q_o != 3
+        assert np.abs(ls["costs"][b][ok] - costs_o[ok]).max() <= 1e-4 * max(1.0, np.abs(costs_o[ok]).max())
+        # arg-min: identical unless two candidates tie within the parity tolerance
+        if ls["best"][b] != best_o:
+            assert abs(costs_o[ls["best"][b]] - costs_o[best_o]) <= 1e-4 * max(1.0, abs(costs_o[best_o]))
+        checked += 1
+    assert checked >= 2
+    # SetWarmStartTrajectory(best): the parent now carries the winning copy's contact times
+    t_after, _, n_after = gpu.GetContactTimes()
+    for b in range(B):
+        if steps_o[b] is None or ls["best"][b] < 0:
+            continue
+        alpha = ls["best"][b] / K
+        counts = n_after[b]
+        want = np.concatenate(go.contact_times_for(go.contact_times(oracles[b]), xk_o[b],
+                                                   np.concatenate([lp["step"][b, e, :counts[e]] for e in range(4)]), alpha))
+        got = np.concatenate([t_after[b, e, :counts[e]] for e in range(4)])
+        assert np.abs(got - want).max() < 1e-9
