@@ -85,6 +85,32 @@ def ipm_algorithmic_bytes(N, nu, n_samples, n_eebox, n_eq):
     return reads + writes
 
 
+def ipm_algorithmic_flops(N, nu, nf, iters, refine=1):
+    """FP64 flops of one k_ipm instance (2 per multiply-add), DESIGN.md "kernel 4": per interior-point iteration one K
+    assembly (rank-2(N-3) update of the nf x nf triangle), one nu^3/3 Cholesky, 2 (1 + refine) blocked substitution
+    pairs, 1 + 2 refine products with H and ~10 products with the structured C / C'; plus the start point."""
+    nkc = 2 * (N - 3)
+    per_it = 2 * (nkc * nf * (nf + 1) / 2 + nu ** 3 / 6 + 2 * (1 + refine) * nu * nu + (1 + 2 * refine) * nu * nu + 10 * nkc * nf)
+    return (iters + 1) * per_it
+
+
+def oracle_latency(cfg_name, solves):
+    """Single-thread latency of the oracle's RTI solve on the nominal instance (ms): p50, p95."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common
+    cfg = wl.CONFIGS[cfg_name]
+    init = np.asarray(cfg["srb_init"], float)
+    o = common.make_oracle(cfg_name)
+    o.initial_run(init, wl.EE_NOMINAL)
+    ts = []
+    for _ in range(solves):
+        t = time.perf_counter()
+        o.solve(init, 0.0, wl.EE_NOMINAL, real_time=True)
+        ts.append(1e3 * (time.perf_counter() - t))
+    return float(np.percentile(ts, 50)), float(np.percentile(ts, 95))
+
+
 def oracle_throughput(cfg_name, sample, steps, warmup, threads):
     """CPU leg: the oracle's restatement of the live reference path (interior-point QP), `sample` instances of the same
     synthetic workload spread over `threads` host threads; every instance does `warmup` + `steps` RTI solves."""
@@ -128,6 +154,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--ipm-refine", type=int, default=0, help="0 = library default, -1 = no refinement")
     ap.add_argument("--max-spline-vars", type=int, default=0)
+    ap.add_argument("--latency-solves", type=int, default=200)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -140,8 +167,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = args.cpu_sample or 4 * cores
+        sample = args.cpu_sample or 8 * cores
         v, el = oracle_throughput(args.config, sample, args.steps, args.warmup, cores)
+        p50, p95 = oracle_latency(args.config, 30)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -149,7 +177,8 @@ def main():
                            "the reference binary needs Eigen/pinocchio/Clarabel which are absent from this image"},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": f"{sample} instances x {args.steps} RTI solves on {cores} threads"},
-                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "latency": {"p50_ms": p50, "p95_ms": p95, "what": "one RTI solve of the nominal instance, one host thread"}}
         print(json.dumps(line))
         return
 
@@ -214,6 +243,26 @@ def main():
     barrier()
     clocks = sampler.stop()
 
+    # ---- single-instance latency (BASELINE metric's second half): one MPC, host buffers in, results out, per call
+    lat = None
+    if rank == 0:
+        one = bg.BatchedMPC(N, cfg["integrator_dt"], wl.robot(), device=local_rank, ipm_refine=args.ipm_refine, **wl.mpc_kwargs(cfg))
+        one.AddQuadraticTrackingCost(wl.target_tangent(cfg), np.asarray(cfg["Q"], float))
+        one.Reset(1)
+        init = np.asarray(cfg["srb_init"], float)[None]
+        one.SetStateTrajectoryWarmStart(init)
+        ee1 = wl.EE_NOMINAL[None].copy()
+        one.CreateInitialRun(init, ee1)
+        ts = []
+        for _ in range(args.latency_solves):
+            t = time.perf_counter()
+            r1 = one.GetRealTimeUpdate(init, np.zeros(1), ee1)
+            ts.append(1e3 * (time.perf_counter() - t))
+        lat = {"p50_ms": float(np.percentile(ts, 50)), "p95_ms": float(np.percentile(ts, 95)), "solves": len(ts),
+               "status": int(r1["status"][0]), "ipm_iters": int(r1["iters"][0]),
+               "what": "bgg_solve_batch with batch = 1 (host buffers in, results out), wall clock per call"}
+        one.close()
+
     if world > 1:
         t = torch.tensor([ms_dev, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -257,16 +306,28 @@ def main():
                 "d2h_bytes_per_step": B * 248, "timing": "wall clock around bgg_solve_batch, synchronised both sides"},
         "gpu_launches": int(launches),
         "kernel_ms": kms,
+        "latency": lat,
         "roofline": {"kernel": "k_ipm", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "note": "FP64-pipe / latency bound by design: the QP is shared-memory resident, HBM holds only its "
                              "compulsory inputs and outputs"},
     }
+    # FP64 pipe: the ceiling that does bound k_ipm (north_star: "FP64 pipe utilisation reported against B200 peak")
+    try:
+        fp64_peak = bg.measure_fp64_peak(local_rank)
+        flops = B * ipm_algorithmic_flops(N, sz["nu"], sz["nf"], float(np.mean(res["iters"])))
+        line["fp64"] = {"kernel": "k_ipm", "achieved_tflops": flops / (kms["ipm"] * 1e-3) / 1e12, "peak_tflops": fp64_peak,
+                        "frac": flops / (kms["ipm"] * 1e-3) / 1e12 / fp64_peak,
+                        "peak_source": "measured here: register-resident FMA chains (bgg_measure_fp64_peak)"}
+    except Exception as e:  # noqa: BLE001
+        line["fp64"] = {"error": str(e)}
     if world == 1:
-        sample = args.cpu_sample or 4 * cores
-        v, el = oracle_throughput(args.config, sample, 2, 1, cores)
+        sample = args.cpu_sample or 8 * cores
+        v, el = oracle_throughput(args.config, sample, 20, 2, cores)
+        p50, p95 = oracle_latency(args.config, 30)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{sample} instances x 2 RTI solves (1 warm-up) on {cores} threads, {el:.1f} s"}
+                                "sample": f"{sample} instances x 20 RTI solves (2 warm-up) on {cores} threads, {el:.1f} s",
+                                "latency_p50_ms": p50, "latency_p95_ms": p95}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -64,6 +64,7 @@ def lib():
             raise BggError(f"{LIB_PATH} is missing: build it with bilevel-gait-gen_b200/build.sh (no CPU fallback exists)")
         L = C.CDLL(LIB_PATH)
         L.bgg_last_error.restype = C.c_char_p
+        L.bgg_measure_fp64_peak.argtypes = [C.c_int, _dp]
         L.bgg_create.argtypes = [C.POINTER(Config), C.POINTER(Robot), C.POINTER(C.c_void_p)]
         L.bgg_destroy.argtypes = [C.c_void_p]
         L.bgg_set_costs.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
@@ -102,13 +103,20 @@ def lib():
 
 def exported_symbols():
     """Names include/bgg.h declares; used by the CPU-side ABI test."""
-    return ["bgg_last_error", "bgg_device_count", "bgg_create", "bgg_destroy", "bgg_set_costs", "bgg_batch_reset",
+    return ["bgg_last_error", "bgg_device_count", "bgg_measure_fp64_peak", "bgg_create", "bgg_destroy", "bgg_set_costs", "bgg_batch_reset",
             "bgg_set_warm_states", "bgg_set_contact_times", "bgg_solve_batch", "bgg_upload_inputs", "bgg_solve_resident",
             "bgg_download_results", "bgg_synchronize", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count", "bgg_event_record", "bgg_event_elapsed_ms",
             "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_export_qp_csc", "bgg_gait_gradient_batch", "bgg_optimize_contact_times_batch",
             "bgg_line_search_batch", "bgg_get_adjoint",
             "bgg_get_contact_times", "bgg_set_solution", "bgg_get_solution", "bgg_instance_bytes",
             "bgg_get_instance", "bgg_set_instance", "bgg_get_states", "bgg_eval_splines"]
+
+
+def measure_fp64_peak(device=0):
+    v = C.c_double(0.0)
+    if lib().bgg_measure_fp64_peak(device, C.byref(v)):
+        raise BggError(lib().bgg_last_error().decode())
+    return v.value
 
 
 def _d(a):

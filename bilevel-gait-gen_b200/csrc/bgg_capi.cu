@@ -107,7 +107,48 @@ __global__ void k_eval_splines(const Instance* inst, int b, const double* __rest
     }
 }
 
+// register-resident FP64 FMA chains: the ceiling the solver kernels are measured against (bench.py, "fp64" entry)
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 extern "C" {
+
+int bgg_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return fail(BGG_EINVAL, "null argument");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, 8 * static_cast<size_t>(blocks) * 256));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_fp64_peak<<<blocks, 256>>>(d, iters);   // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        k_fp64_peak<<<blocks, 256>>>(d, iters);
+        cudaEventRecord(e1);
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * iters * static_cast<double>(blocks) * 256 / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return BGG_OK;
+}
 
 const char* bgg_last_error(void) { return g_err.c_str(); }
 

@@ -72,6 +72,10 @@ typedef struct bgg_handle bgg_handle;
 const char* bgg_last_error(void);
 int bgg_device_count(void);
 
+/* Measured FP64 FMA throughput of `device` (register-resident FMA chains, best of 5): the ceiling bench.py reports
+ * the solver kernels against.  No reference counterpart. */
+int bgg_measure_fp64_peak(int device, double* tflops);
+
 /* MPCSingleRigidBody::MPCSingleRigidBody (mpc/mpc_single_rigid_body.cpp:8-23) + MPC::MPC (mpc/mpc.cpp:38-76). */
 int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out);
 void bgg_destroy(bgg_handle* h);
