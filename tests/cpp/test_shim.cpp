@@ -1,0 +1,129 @@
+// Host-shim test in the shape of the reference's test/mpc_test.cpp:17-135: build an MPCSingleRigidBody from an MPCInfo,
+// set the costs the way CreateMPC does (:21-40), run CreateInitialRun and a real-time update, read sizes / QP data /
+// solve quality, then the gait optimiser's derivative -> LP -> line search sequence of MPCController::GaitOpt
+// (controllers/mpc_controller.cpp:518-573, 322-343).  Prints "key value" lines that tests/test_host_shim.py checks
+// against the oracle.  Needs a GPU (the library has no CPU fallback).
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+
+#include "mpc_b200.h"
+
+using namespace mpc;
+
+static bgg_robot ReadRobot(const char* path) {
+    // "mass Ir[9] Ir_inv[9] hip_xy[8]" as plain numbers (written by the python side from tests/golden/a1_robot_consts.json)
+    bgg_robot rb{};
+    FILE* f = std::fopen(path, "r");
+    if (!f) throw std::runtime_error("cannot open robot constants file");
+    double* dst[4] = {&rb.mass, rb.Ir, rb.Ir_inv, rb.hip_xy};
+    const int cnt[4] = {1, 9, 9, 8};
+    for (int k = 0; k < 4; ++k)
+        for (int i = 0; i < cnt[k]; ++i)
+            if (std::fscanf(f, "%lf", dst[k] + i) != 1) throw std::runtime_error("short robot constants file");
+    std::fclose(f);
+    rb.gravity[2] = -9.81;
+    return rb;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) return 2;
+    try {
+        MPCInfo info;   // apps/a1_configuration.yaml
+        info.num_nodes = 20;
+        info.integrator_dt = 0.05;
+        info.friction_coef = 0.5;
+        info.force_bound = 150;
+        info.swing_height = 0.075;
+        info.foot_offset = 0.015;
+        info.ee_box_size = vector_2t(0.15, 0.15);
+        info.force_cost = 0;
+        MPCSingleRigidBody mpc(info, ReadRobot(argv[1]));
+
+        const double q[12] = {340, 340, 4000, .1, .1, 10, 3000, 3000, 3000, 1, 1, 1};
+        matrix_t Q = matrix_t::Zero(12, 12);
+        for (int i = 0; i < 12; ++i) Q(i, i) = q[i];
+        vector_t init_state(13), des_alg(12);
+        const double s0[13] = {0, 0, .3, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0};
+        for (int i = 0; i < 13; ++i) init_state(i) = s0[i];
+        for (int i = 0; i < 12; ++i) des_alg(i) = (i == 2) ? 0.3 : 0.0;   // ConvertManifoldStateToTangentState(srb_target)
+        mpc.SetStateTrajectoryWarmStart(std::vector<vector_t>(info.num_nodes + 1, init_state));
+        mpc.AddQuadraticTrackingCost(des_alg, Q);
+        mpc.AddForceCost(info.force_cost);
+        mpc.SetQuadraticFinalCost(Q);
+        vector_t lin(12);
+        for (int i = 0; i < 12; ++i) lin(i) = -1 * q[i] * des_alg(i);
+        mpc.SetLinearFinalCost(lin);
+
+        const double ee_pos[4][3] = {{0.1526, 0.12523, 0.011089}, {0.1526, -0.12523, 0.011089}, {-0.208321844, 0.1363286, 0.01444},
+                                     {-0.208321844, -0.1363286, 0.01444}};   // test/mpc_test.cpp:97-101
+        std::vector<vector_3t> ee;
+        for (auto& p : ee_pos) ee.emplace_back(p[0], p[1], p[2]);
+        mpc.SetDefaultGaitTrajectory(Trot, 3, ee);
+
+        bool threw = false;   // wrong-sized cost matrix -> std::runtime_error (mpc.cpp:122-124)
+        try {
+            mpc.SetQuadraticFinalCost(matrix_t::Zero(3, 3));
+        } catch (const std::runtime_error&) {
+            threw = true;
+        }
+        std::printf("bad_cost_throws %d\n", threw ? 1 : 0);
+
+        Trajectory traj = mpc.CreateInitialRun(init_state, ee);
+        std::printf("initial_quality %d\n", static_cast<int>(mpc.GetSolveQuality()));
+        traj = mpc.GetRealTimeUpdate(init_state, 0.0, ee, false);
+        std::printf("rt_quality %d\n", static_cast<int>(mpc.GetSolveQuality()));
+        std::printf("num_decision_vars %d\n", mpc.GetNumDecisionVars());
+        std::printf("num_constraints %d\n", mpc.GetNumConstraints());
+        std::printf("cost %.12e\n", mpc.GetCost());
+        const QPData& data = mpc.GetQPData();
+        std::printf("qp_rows %d\nqp_cols %d\nqp_nnz %d\n", data.sparse_constraint_.rows, data.sparse_constraint_.cols, data.sparse_constraint_.nonZeros());
+        std::printf("num_equality %d\nnum_inequality %d\n", data.num_equality_, data.num_inequality_);
+        std::printf("state1_z %.12e\n", traj.GetState(1)(2));
+        std::printf("force_ee1_z_t01 %.12e\n", traj.GetForce(1, 0.1)(2));
+        std::printf("ee0_x_t04 %.12e\n", traj.GetEndEffectorLocation(0, 0.4)(0));
+        const std::vector<time_v> ct = traj.GetContactTimes();
+        std::printf("num_contact_nodes %d %d %d %d\n", traj.GetNumContactNodes(0), traj.GetNumContactNodes(1), traj.GetNumContactNodes(2),
+                    traj.GetNumContactNodes(3));
+
+        // a copy solves to the same cost (MPC is a value type; the line search depends on it, gait_optimizer.cpp:696)
+        MPCSingleRigidBody copy = mpc;
+        copy.GetRealTimeUpdate(init_state, 0.0, ee, false);
+        MPCSingleRigidBody again = mpc;
+        again.GetRealTimeUpdate(init_state, 0.0, ee, false);
+        std::printf("copy_cost_equal %d\n", copy.GetCost() == again.GetCost() ? 1 : 0);
+
+        // MPCController::GaitOpt
+        GaitOptimizer gait_opt(4, 10, mpc.GetNumDecisionVars(), mpc.GetNumConstraints(), 1.0, 0.05);
+        const bool ok = mpc.ComputeDerivativeTerms();
+        std::printf("derivative_terms %d\n", ok ? 1 : 0);
+        gait_opt.SetContactTimes(mpc.GetTrajectory().GetContactTimes());
+        gait_opt.UpdateSizes(mpc.GetNumDecisionVars(), mpc.GetNumConstraints());
+        mpc.GetQPPartials(gait_opt.GetQPPartials());
+        const Trajectory prev_traj = mpc.GetTrajectory();
+        for (int e = 0; e < 4; ++e) {
+            gait_opt.SetNumContactTimes(e, prev_traj.GetNumContactNodes(e));
+            for (int idx = 0; idx < prev_traj.GetNumContactNodes(e); ++idx)
+                mpc.ComputeParamPartialsClarabel(prev_traj, gait_opt.GetParameterPartials(e, idx), e, idx);
+        }
+        gait_opt.ModifyQPPartials(mpc.GetQPSolution());
+        gait_opt.ComputeCostFcnDerivWrtContactTimes();
+        std::printf("gradient");
+        for (double g : gait_opt.GetGradient()) std::printf(" %.10e", g);
+        std::printf("\n");
+        gait_opt.OptimizeContactTimes(0.0, 0.0);
+        std::printf("step");
+        for (double s : gait_opt.GetStep()) std::printf(" %.10e", s);
+        std::printf("\n");
+        auto res = gait_opt.LineSearch(mpc, 0.0, ee, init_state);
+        std::printf("ls_cost_min %.12e\n", res.second);
+        std::printf("ls_first_times");
+        for (const auto& t : res.first.at(0)) std::printf(" %.10e", t.GetTime());
+        std::printf("\n");
+        std::printf("done 1\n");
+    } catch (const std::exception& e) {
+        std::printf("exception %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

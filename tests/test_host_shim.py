@@ -1,0 +1,88 @@
+"""The C++ host shim (bilevel-gait-gen_b200/host): the reference's MPC / MPCSingleRigidBody / Trajectory / GaitOptimizer call
+surface over the C ABI.  CPU part: the shim library loads and its URDF reader reproduces the robot constants the tests
+use; GPU part: tests/cpp/test_shim.cpp (shaped like the reference's test/mpc_test.cpp set-up) against the oracle."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common
+from common import wl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "bilevel-gait-gen_b200")
+SHIM_SO = os.path.join(PKG, "libmpc_b200.so")
+TEST_BIN = os.path.join(ROOT, "tests", "cpp", "test_shim")
+A1_URDF = "/root/reference/models/a1_description/urdf/a1.urdf"
+
+
+def test_shim_library_loads_and_exports_the_urdf_entry_point():
+    assert os.path.exists(SHIM_SO), "build it with bilevel-gait-gen_b200/build.sh"
+    lib = C.CDLL(SHIM_SO)
+    assert hasattr(lib, "bgg_host_robot_consts_from_urdf")
+    assert os.path.exists(TEST_BIN)
+
+
+@pytest.mark.skipif(not os.path.exists(A1_URDF), reason="the reference's URDF is only present in the build container")
+def test_urdf_reader_matches_the_robot_constants_fixture():
+    import bgg_b200 as bg
+    lib = C.CDLL(SHIM_SO)
+    rb = bg.Robot()
+    assert lib.bgg_host_robot_consts_from_urdf(A1_URDF.encode(), C.byref(rb)) == 0
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "a1_robot_consts.json")))
+    assert abs(rb.mass - gold["mass"]) < 1e-12
+    assert np.abs(np.array(rb.Ir[:]).reshape(3, 3) - np.array(gold["Ir"])).max() < 1e-12
+    assert np.abs(np.array(rb.Ir_inv[:]).reshape(3, 3) - np.array(gold["Ir_inv"])).max() < 1e-9
+    assert np.abs(np.array(rb.hip_xy[:]).reshape(4, 2) - np.array(gold["hip_offsets_xy"])).max() < 1e-12
+
+
+@pytest.mark.gpu
+def test_shim_reproduces_the_oracle_on_the_reference_test_setup(tmp_path):
+    import gait_oracle as go
+    rb = wl.robot()
+    consts = [rb["mass"]] + list(np.ravel(rb["Ir"])) + list(np.ravel(rb["Ir_inv"])) + list(np.ravel(rb["hip_offsets_xy"]))
+    path = tmp_path / "robot.txt"
+    path.write_text(" ".join(repr(float(v)) for v in consts))
+    out = subprocess.run([TEST_BIN, str(path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    kv = {}
+    for line in out.stdout.splitlines():
+        parts = line.split()
+        if parts:
+            kv[parts[0]] = parts[1:]
+    assert kv["done"] == ["1"], out.stdout
+    assert kv["bad_cost_throws"] == ["1"]
+    assert kv["initial_quality"] == ["0"] and kv["rt_quality"] == ["0"]
+    assert kv["num_decision_vars"] == ["372"] and kv["num_constraints"] == ["1012"]      # SURVEY section 8 size table
+    assert kv["qp_rows"] == ["1012"] and kv["qp_cols"] == ["372"]
+    assert kv["num_equality"] == ["260"] and kv["num_inequality"] == ["752"]
+    assert kv["num_contact_nodes"] == ["5", "5", "5", "5"]
+    assert kv["copy_cost_equal"] == ["1"] and kv["derivative_terms"] == ["1"]
+
+    cfg_name = "a1_configuration"
+    cfg = wl.CONFIGS[cfg_name]
+    init = np.asarray(cfg["srb_init"], float)
+    ee = wl.EE_NOMINAL.copy()
+    o = common.make_oracle(cfg_name)
+    o.initial_run(init, ee)
+    o.solve(init, 0.0, ee, real_time=True)
+    # the two sides ran 11 solves each from their own trajectories: an entry that is exactly 0.0 on one side can be 1e-20 on
+    # the other (bit-exact sparsity on identical inputs is tested in test_gpu_parity.py)
+    assert abs(int(kv["qp_nnz"][0]) - o.sizes()["nnzA"]) <= 16
+    assert abs(float(kv["cost"][0]) - o.cost()) <= 1e-4 * max(1.0, abs(o.cost()))
+    assert abs(float(kv["state1_z"][0]) - o.states()[1][2]) < 1e-6
+    assert abs(float(kv["force_ee1_z_t01"][0]) - o.force_at(1, 0.1)[2]) <= 1e-4 * max(1.0, abs(o.force_at(1, 0.1)[2]))
+    assert abs(float(kv["ee0_x_t04"][0]) - o.ee_at(0, 0.4)[0]) < 1e-6
+    g_o = go.cost_gradient(o)
+    g = np.array([float(v) for v in kv["gradient"]])
+    assert np.abs(g - g_o).max() <= 1e-4 * max(1.0, np.abs(g_o).max())
+    ct = go.contact_times(o)
+    s_o = go.solve_gait_lp(ct, g_o, 0.0)
+    s = np.array([float(v) for v in kv["step"]])
+    assert np.abs(s - s_o).max() < 1e-6
+    xk = np.concatenate([t for t, _ in ct])
+    best, costs, q = go.line_search(o, init, 0.0, ee, ct, xk, s_o, ls_size=10)
+    assert abs(float(kv["ls_cost_min"][0]) - costs[best]) <= 1e-4 * max(1.0, abs(costs[best]))
