@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "bilevel-gait-gen_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
+import sharding  # noqa: E402
 import workloads as wl  # noqa: E402
 
 METRIC = "A1 SRB-MPC RTI solves/sec"
@@ -155,6 +156,10 @@ def main():
     ap.add_argument("--ipm-refine", type=int, default=0, help="0 = library default, -1 = no refinement")
     ap.add_argument("--max-spline-vars", type=int, default=0)
     ap.add_argument("--latency-solves", type=int, default=200)
+    ap.add_argument("--closed-loop", action="store_true",
+                    help="BASELINE config #5: --scenarios closed-loop scenarios cut across the ranks (strong scaling); a step is one "
+                         "closed-loop tick (plant step + RTI solve) of every scenario")
+    ap.add_argument("--scenarios", type=int, default=65536)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -163,6 +168,9 @@ def main():
     cores = os.cpu_count() or 1
     workload = (f"{args.config}: A1 trot SRB-MPC, N={cfg['num_nodes']} nodes x {cfg['integrator_dt']} s, "
                 f"{args.batch} synthetic initial states per GPU, t0=0")
+    if args.closed_loop:
+        workload = (f"{args.config}: disturbance-rejection sweep, N={cfg['num_nodes']} nodes x {cfg['integrator_dt']} s, "
+                    f"{args.scenarios} closed-loop scenarios cut across {world} GPU(s), plant = node 1 of the solved trajectory")
 
     if args.impl == "reference":
         if rank != 0:
@@ -198,7 +206,13 @@ def main():
         torch.cuda.synchronize()
 
     B, N = args.batch, cfg["num_nodes"]
-    states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=1000 + rank)
+    if args.closed_loop:
+        lo, hi = sharding.shard_range(args.scenarios, rank, world)
+        B = hi - lo
+        states, t0, ee = wl.disturbance_sweep_inputs(cfg, args.scenarios, seed=7)
+        states, t0, ee = states[lo:hi].copy(), t0[lo:hi].copy(), ee[lo:hi].copy()
+    else:
+        states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=1000 + rank)
     mpc = bg.BatchedMPC(N, cfg["integrator_dt"], wl.robot(), device=local_rank, ipm_refine=args.ipm_refine,
                         max_spline_vars=args.max_spline_vars, **wl.mpc_kwargs(cfg))
     mpc.AddQuadraticTrackingCost(wl.target_tangent(cfg), np.asarray(cfg["Q"], float))
@@ -206,9 +220,17 @@ def main():
     mpc.SetStateTrajectoryWarmStart(states)
 
     # ---- device-resident throughput: inputs already in HBM, K solves timed with CUDA events on the launching stream
-    mpc.upload(states, t0, ee)
-    for _ in range(args.warmup):
+    dt_plant = cfg["integrator_dt"]
+
+    def step():
+        if args.closed_loop:
+            mpc.advance_plant(dt_plant)
         mpc.solve_resident()
+
+    mpc.upload(states, t0, ee)
+    mpc.solve_resident()
+    for _ in range(args.warmup):
+        step()
     mpc.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -216,7 +238,7 @@ def main():
     l0 = mpc.launch_count()
     mpc.event_record(0)
     for _ in range(args.steps):
-        mpc.solve_resident()
+        step()
     mpc.event_record(1)
     ms_dev = mpc.event_elapsed_ms(0, 1)
     barrier()
@@ -228,7 +250,7 @@ def main():
     mpc.set_profiling(True)
     kms = {"prepare": 0.0, "condense": 0.0, "ipm": 0.0, "finish": 0.0}
     for _ in range(args.steps):
-        mpc.solve_resident()
+        step()
         for k, v in mpc.last_kernel_ms().items():
             kms[k] += v / args.steps
     mpc.set_profiling(False)
@@ -237,7 +259,12 @@ def main():
     barrier()
     t_start = time.perf_counter()
     for _ in range(args.steps):
-        res = mpc.GetRealTimeUpdate(states, t0, ee)
+        if args.closed_loop:   # the plant lives on the device: no inputs travel, the per-instance results do
+            mpc.advance_plant(dt_plant)
+            mpc.solve_resident()
+            res = mpc.download()
+        else:
+            res = mpc.GetRealTimeUpdate(states, t0, ee)
     mpc.synchronize()
     e2e_s = time.perf_counter() - t_start
     barrier()
@@ -263,17 +290,16 @@ def main():
                "what": "bgg_solve_batch with batch = 1 (host buffers in, results out), wall clock per call"}
         one.close()
 
+    total = args.scenarios if args.closed_loop else B * world
     if world > 1:
-        t = torch.tensor([ms_dev, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, e2e_s = float(t[0]), float(t[1])
+        ms_dev, e2e_s = sharding.max_over_ranks([ms_dev, e2e_s], dist, "cuda")
         # the only data-path collective: gather of the per-instance results (status) at the end of the batch
-        st = torch.from_numpy(res["status"].astype(np.int32)).cuda()
-        gathered = [torch.empty_like(st) for _ in range(world)] if rank == 0 else None
-        dist.gather(st, gathered, dst=0)
+        if args.closed_loop:
+            g = sharding.gather_to_root(res["status"].astype(np.int32), total, dist, "cuda")
+        else:   # weak scaling: every rank holds `B` instances
+            g = sharding.gather_to_root(res["status"].astype(np.int32), B * world, dist, "cuda")
         if rank == 0:
-            solved = int(sum(int(((g == 0) | (g == 1)).sum()) for g in gathered))
-    total = B * world
+            solved = int(np.isin(g, (0, 1)).sum())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -295,14 +321,14 @@ def main():
             traffic = json.load(f).get("dram_bytes_per_launch")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if args.closed_loop else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload, "decision_vars": sz["n"], "spline_vars": sz["nu"],
                    "ineq_rows": sz["m_ineq"], "eq_rows": 12 * (N + 1) + sz["n_eq"], "qp_solver": "interior point, tol 1e-8",
                    "l2": "inputs larger than L2 (instance + workspace state is > 1 GB per 4096 instances)",
                    "solved_fraction": solved / total, "mean_ipm_iters": float(np.mean(res["iters"]))},
         "clocks": clocks,
-        "e2e": {"value": total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * (13 + 1 + 12) * 8,
+        "e2e": {"value": total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0 if args.closed_loop else B * (13 + 1 + 12) * 8,
                 "d2h_bytes_per_step": B * 248, "timing": "wall clock around bgg_solve_batch, synchronised both sides"},
         "gpu_launches": int(launches),
         "kernel_ms": kms,

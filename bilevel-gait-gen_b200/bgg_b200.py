@@ -76,6 +76,7 @@ def lib():
         L.bgg_solve_resident.argtypes = [C.c_void_p]
         L.bgg_download_results.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp]
         L.bgg_synchronize.argtypes = [C.c_void_p]
+        L.bgg_advance_plant.argtypes = [C.c_void_p, C.c_double]
         L.bgg_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.bgg_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.bgg_kernel_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -105,7 +106,7 @@ def exported_symbols():
     """Names include/bgg.h declares; used by the CPU-side ABI test."""
     return ["bgg_last_error", "bgg_device_count", "bgg_measure_fp64_peak", "bgg_create", "bgg_destroy", "bgg_set_costs", "bgg_batch_reset",
             "bgg_set_warm_states", "bgg_set_contact_times", "bgg_solve_batch", "bgg_upload_inputs", "bgg_solve_resident",
-            "bgg_download_results", "bgg_synchronize", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count", "bgg_event_record", "bgg_event_elapsed_ms",
+            "bgg_download_results", "bgg_synchronize", "bgg_advance_plant", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count", "bgg_event_record", "bgg_event_elapsed_ms",
             "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_export_qp_csc", "bgg_gait_gradient_batch", "bgg_optimize_contact_times_batch",
             "bgg_line_search_batch", "bgg_get_adjoint",
             "bgg_get_contact_times", "bgg_set_solution", "bgg_get_solution", "bgg_instance_bytes",
@@ -249,6 +250,9 @@ class BatchedMPC:
         al, co = np.zeros(self.B), np.zeros(self.B)
         self._chk(self.L.bgg_download_results(self.h, _i(st), _i(it), _d(al), _d(co)))
         return dict(status=st, iters=it, alpha=al, cost=co)
+
+    def advance_plant(self, dt):
+        self._chk(self.L.bgg_advance_plant(self.h, dt))
 
     def synchronize(self):
         self._chk(self.L.bgg_synchronize(self.h))

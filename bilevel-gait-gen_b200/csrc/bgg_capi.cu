@@ -107,6 +107,22 @@ __global__ void k_eval_splines(const Instance* inst, int b, const double* __rest
     }
 }
 
+// Synthetic plant of the closed-loop sweeps: the next measured state is node 1 of the solved
+// trajectory (apps/mpc_demo.cpp:185, test/gait_opt_playground.cpp:128), time advances by dt and the measured feet are the
+// trajectory's own feet at the new time.  Writes the next solve's inputs in place on the device.
+__global__ void k_plant_step(const Instance* __restrict__ inst, int B, double dt, double* __restrict__ state, double* __restrict__ t0,
+                             double* __restrict__ ee) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * kNumEE) return;
+    const int b = i / kNumEE, e = i % kNumEE;
+    const double tn = inst[b].init_time + dt;
+    for (int c = 0; c < 3; ++c) ee[(b * kNumEE + e) * 3 + c] = value_at(inst[b].foot[e], false, c, tn);
+    if (e == 0) {
+        for (int c = 0; c < kNxMan; ++c) state[b * kNxMan + c] = inst[b].states[1][c];
+        t0[b] = tn;
+    }
+}
+
 // register-resident FP64 FMA chains: the ceiling the solver kernels are measured against (bench.py, "fp64" entry)
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
     double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -376,6 +392,16 @@ int bgg_solve_resident(bgg_handle* h) {
     if (!h->costs_set) return fail(BGG_ESTATE, "bgg_set_costs has not been called");
     CU(cudaSetDevice(h->device));
     return solve_pipeline(h, h->d_inst, h->d_ws, h->d_state, h->d_t0, h->d_ee, h->batch, h->profiling);
+}
+
+int bgg_advance_plant(bgg_handle* h, double dt) {
+    if (!h || !h->batch) return fail(BGG_EINVAL, "no batch");
+    CU(cudaSetDevice(h->device));
+    const int tot = h->batch * kNumEE;
+    k_plant_step<<<(tot + 127) / 128, 128, 0, h->stream>>>(h->d_inst, h->batch, dt, h->d_state, h->d_t0, h->d_ee);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return BGG_OK;
 }
 
 int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double* alpha, double* cost) {

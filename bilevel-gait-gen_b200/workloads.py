@@ -75,3 +75,17 @@ def batched_trot_inputs(cfg, batch, seed=0):
     ee = np.tile(EE_NOMINAL, (batch, 1, 1))
     ee[:, :, :2] += rng.uniform(-0.02, 0.02, (batch, 4, 2))
     return states, np.zeros(batch), ee
+
+
+def disturbance_sweep_inputs(cfg, batch, seed=0):
+    """Config #5: scenario_b starts from srb_init with the linear momentum 2.5 (cos phi, sin phi) U(.5, 1.5) kg m/s,
+    phi ~ U(0, 2 pi), nominal feet, t0 = 0."""
+    rng = np.random.default_rng(seed)
+    init = np.asarray(cfg["srb_init"], float)
+    states = np.tile(init, (batch, 1))
+    phi = rng.uniform(0, 2 * np.pi, batch)
+    mag = 2.5 * rng.uniform(0.5, 1.5, batch)
+    states[:, 3] = mag * np.cos(phi)
+    states[:, 4] = mag * np.sin(phi)
+    ee = np.tile(EE_NOMINAL, (batch, 1, 1))
+    return states, np.zeros(batch), ee

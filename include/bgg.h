@@ -108,6 +108,10 @@ int bgg_upload_inputs(bgg_handle* h, const double* state, const double* t0, cons
 int bgg_solve_resident(bgg_handle* h);
 int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double* alpha, double* cost);
 int bgg_synchronize(bgg_handle* h);
+/* Closed-loop sweeps on resident data: replace every instance's inputs by the model's own next step -- state = node 1 of
+ * the solved trajectory (the plant of apps/mpc_demo.cpp:185 and test/gait_opt_playground.cpp:128), t0 += dt, measured
+ * feet = the trajectory's feet at the new time.  Follow with bgg_solve_resident. */
+int bgg_advance_plant(bgg_handle* h, double dt);
 /* device milliseconds of the four kernels of the last bgg_solve_resident (prepare, condense, ipm, finish),
  * measured with CUDA events on the handle's stream; enable with bgg_set_profiling(h, 1). */
 int bgg_set_profiling(bgg_handle* h, int enable);

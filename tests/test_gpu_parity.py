@@ -385,3 +385,34 @@ def test_contact_time_lp_and_line_search_match_oracle(cfg_name):
                                                    np.concatenate([lp["step"][b, e, :counts[e]] for e in range(4)]), alpha))
         got = np.concatenate([t_after[b, e, :counts[e]] for e in range(4)])
         assert np.abs(got - want).max() < 1e-9
+
+
+def test_closed_loop_sweep_follows_the_oracle():
+    """Config #5 (disturbance rejection, N = 50): scenarios run closed loop on the device -- plant = node 1 of the solved
+    trajectory, feet = the trajectory's own feet at the new time (bgg_advance_plant) -- against the oracle doing the same
+    step by step.  No mirroring between steps, so the per-solve parity error (1e-4 bar) compounds through the loop: the
+    same solve statuses at every step and trajectories within 1e-3 relative after 4 closed-loop steps."""
+    cfg_name = "a1_config_distr_rejection"
+    cfg = wl.CONFIGS[cfg_name]
+    B, T, dt = 3, 4, cfg["integrator_dt"]
+    states, t0, ee = wl.disturbance_sweep_inputs(cfg, B, seed=4)
+    gpu = common.make_gpu(cfg_name, B, states)
+    gpu.upload(states, t0, ee)
+    gpu.solve_resident()
+    hist = [gpu.download()["status"].copy()]
+    for _ in range(T):
+        gpu.advance_plant(dt)
+        gpu.solve_resident()
+        hist.append(gpu.download()["status"].copy())
+    for b in range(B):
+        o = common.make_oracle(cfg_name, states[b])
+        s, e, t = states[b].copy(), ee[b].copy(), 0.0
+        st = [o.solve(s, t, e, real_time=True)]
+        for _ in range(T):
+            t = o.init_time() + dt
+            s = o.states()[1].copy()
+            e = np.array([o.ee_at(k, t) for k in range(4)])
+            st.append(o.solve(s, t, e, real_time=True))
+        assert [int(h[b]) for h in hist] == st
+        assert abs(gpu.get_instance(b)["init_time"] - T * dt) < 1e-12
+        assert np.abs(gpu.GetStates(b) - o.states()).max() < 1e-3 * max(1.0, np.abs(o.states()).max())
