@@ -224,40 +224,42 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             S.ckc[q] = -s;
         }
         __syncthreads();
-        // force columns: dense position rows + this foot's samples
-        for (int col = tid; col < nf; col += nth) {
-            double s = 0;
-            for (int q = 0; q < nkc; ++q) s += S.ckc[q] * S.phi[static_cast<size_t>(q) * S.phi_stride + col];
-            int e = 0;
-            while (e < kNumEE - 1 && col >= s_fbase[e + 1]) ++e;
-            const int loc = col - s_fbase[e], c = loc / s_nfv[e], i = loc % s_nfv[e];
-            for (int j = s_sb[e]; j < s_sb[e + 1]; ++j) {
-                const Sample& sp = S.smp[j];
-                const int a = i - sp.off;
-                if (a < 0 || a >= sp.cnt || !sp.active) continue;
-                const double* yy = y + 6 * j;
-                double coef;
-                if (c == 2) coef = (yy[0] - yy[1]) - mu_f * (yy[2] + yy[3] + yy[4] + yy[5]);
-                else if (c == 0) coef = yy[2] - yy[3];
-                else coef = yy[4] - yy[5];
-                s += coef * sp.w[a];
+        // Two threads per column (nu <= 160 < blockDim / 2 ... else one): the first takes the dense foot-box rows (force
+        // column) or the first half of the nodes (position column), the second the sample rows / the second half; the
+        // loops run over the column's own sample / node range only (ColInfo, csrc/bgg_kkt.cuh).
+        {
+            const int half = (2 * nu <= nth) ? 2 : 1;
+            for (int base = 0; base < half * nu; base += nth) {   // whole warps iterate together: the partner exchange is a shuffle
+                const int it = base + tid;
+                const bool act = it < half * nu;
+                const int col = act ? it / half : 0, part = it % half;
+                const ColInfo ci = S.col[col];
+                double s = 0;
+                if (!act) {
+                } else if (col < nf) {
+                    if (part == 0 || half == 1)
+                        for (int q = 0; q < nkc; ++q) s += S.ckc[q] * S.phi[static_cast<size_t>(q) * S.phi_stride + col];
+                    if (part == 1 || half == 1)
+                        for (int j = ci.lo; j < ci.hi; ++j) {
+                            const Sample& sp = S.smp[j];
+                            const double* yy = y + 6 * j;
+                            double coef;
+                            if (ci.coord == 2) coef = (yy[0] - yy[1]) - mu_f * (yy[2] + yy[3] + yy[4] + yy[5]);
+                            else if (ci.coord == 0) coef = yy[2] - yy[3];
+                            else coef = yy[4] - yy[5];
+                            s += coef * sp.w[ci.var - sp.off];
+                        }
+                } else {
+                    const int mid = (half == 2) ? (ci.lo + ci.hi + 1) / 2 : ci.hi;
+                    const int k0 = (part == 0) ? ci.lo : mid, k1 = (part == 0) ? mid : ci.hi;
+                    for (int kk = k0; kk < k1; ++kk) {
+                        const int kf = kk * 4 + ci.foot, e = kf * 2 + ci.coord;
+                        s += (y[6 * ns + 2 * e] - y[6 * ns + 2 * e + 1]) * S.pw[2 * kf + (ci.var - S.poff[kf])];
+                    }
+                }
+                if (half == 2) s += __shfl_xor_sync(0xffffffffu, s, 1);   // partner thread: adjacent lane
+                if (act && part == 0) out[col] += s;
             }
-            out[col] += s;
-        }
-        // position columns: the foot-box rows whose active segment contains the variable
-        for (int col = nf + tid; col < nu; col += nth) {
-            const int pc = col - nf;
-            int foot = 0;
-            while (foot < kNumEE - 1 && pc >= s_pbase[foot + 1]) ++foot;
-            const int loc = pc - s_pbase[foot], c = loc / s_npv[foot], v = loc % s_npv[foot];
-            double s = 0;
-            for (int kk = 0; kk < N - 3; ++kk) {
-                const int kf = kk * 4 + foot, a = v - S.poff[kf];
-                if (a < 0 || a >= S.pcnt[kf]) continue;
-                const int e = kf * 2 + c;
-                s += (y[6 * ns + 2 * e] - y[6 * ns + 2 * e + 1]) * S.pw[2 * kf + a];
-            }
-            out[col] += s;
         }
         __syncthreads();
     };
@@ -644,7 +646,8 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             add_Et(S.re, S.rhs, -inv_delta);
             for (int i = tid; i < nu; i += nth) S.du[i] = S.rhs[i];
             chol_solve(S.du);
-            for (int rf = 0; rf < P.ipm_refine; ++rf) {
+            // The predictor only steers the centring parameter sigma: it is solved without refinement.
+            for (int rf = 0; rf < (corrector ? P.ipm_refine : 0); ++rf) {
                 // iterative refinement against K = H + C'WC + E'E/delta applied matrix-free
                 apply_H(S.du, S.tmpn);
                 apply_C(S.du, S.ds);
