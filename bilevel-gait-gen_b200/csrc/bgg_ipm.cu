@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     }
     __shared__ int s_fbase[kNumEE], s_pbase[kNumEE], s_nfv[kNumEE], s_npv[kNumEE];
     __shared__ int s_flag;
+    __shared__ double s_invd[16];   // reciprocals of the current diagonal block's pivots
     __shared__ int s_sb[kNumEE + 1];   // per-foot sample ranges (samples are stored foot-major)
     __shared__ EqRow s_eq[kMaxEq];
     if (tid < neq) s_eq[tid] = eqs[tid];
@@ -299,109 +300,121 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     kv.smp = S.smp; kv.eq = s_eq; kv.col = S.col; kv.ckc = S.ckc; kv.mu_f = mu_f; kv.inv_delta = inv_delta; kv.sign = 1.0;
     auto build_and_factor = [&]() -> bool {
         kkt_assemble<true>(kv, s_fbase, s_nfv);
-        // Blocked right-looking Cholesky on the packed lower triangle: 8-column panels, 4 x 4 register tiles in the
-        // trailing update (3 barriers per panel instead of 3 per column).
+        // Blocked right-looking Cholesky on the packed lower triangle, NB-column panels, two barriers per panel:
+        //   (1) warp 0 factors the NB x NB diagonal block in registers (lane r owns row r, shuffles down the columns);
+        //   (2) every row below the block solves against it (one thread per row, the block read from shared memory);
+        //   (3) rank-NB trailing update in 4 x 4 register tiles.
+        // Look-ahead: inside (3) warp 0 takes the tiles of the NEXT diagonal block first and factors it while the
+        // other seven warps finish the trailing update, so the serial step (1) is off the critical path.
         if (tid == 0) s_flag = 0;
-        __syncthreads();
         constexpr int NB = 8;
-        for (int b0 = 0; b0 < nu; b0 += NB) {
+        auto factor_diag = [&](int b0) {   // warp 0 only
             const int bs = (nu - b0 < NB) ? nu - b0 : NB;
-            // (1) every warp factors the bs x bs diagonal block redundantly in registers (lane r owns row r,
-            // right-looking with shuffles): no barrier and no idle warps between the block and its panel.
-            double a8[NB];
+            double a[NB];
 #pragma unroll
-            for (int c = 0; c < NB; ++c) a8[c] = (lane < bs && c <= lane && c < bs) ? S.K[pk(b0 + lane, b0 + c)] : 0.0;
+            for (int c = 0; c < NB; ++c) a[c] = (lane < bs && c <= lane) ? S.K[pk(b0 + lane, b0 + c)] : 0.0;
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
                 if (c < bs) {
-                    const double d = __shfl_sync(0xffffffffu, a8[c], c);
+                    const double d = __shfl_sync(0xffffffffu, a[c], c);
                     const bool bad = !(d > 0.0);
-                    if (bad && tid == 0) s_flag = 1;
+                    if (bad && lane == 0) s_flag = 1;
                     const double inv = bad ? 1.0 : rsqrt(d);
-                    a8[c] = (lane == c) ? d * inv : a8[c] * inv;
+                    a[c] = (lane == c) ? d * inv : a[c] * inv;
+                    if (lane == c) s_invd[c] = inv;
 #pragma unroll
                     for (int c2 = c + 1; c2 < NB; ++c2) {
-                        const double t = __shfl_sync(0xffffffffu, a8[c], c2);   // L[c2][c]
-                        if (lane >= c2) a8[c2] -= a8[c] * t;
+                        const double t = __shfl_sync(0xffffffffu, a[c], c2);   // L[c2][c]
+                        if (lane >= c2) a[c2] -= a[c] * t;
                     }
                 }
             }
-            // (2) panel below the block: row i solves L[i, b] = A[i, b] L_bb^-T, one thread per row; L_bb comes from the
-            // warp's own registers through shuffles
-            for (int base = b0 + bs; base < nu; base += nth) {
-                const int i = base + tid;
-                const bool act = i < nu;
-                double* Li = S.K + pk(act ? i : nu - 1, b0);
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+                if (lane < bs && c <= lane) S.K[pk(b0 + lane, b0 + c)] = a[c];
+        };
+        __syncthreads();
+        if (wid == 0) factor_diag(0);
+        __syncthreads();
+        for (int b0 = 0; b0 < nu; b0 += NB) {
+            const int bs = (nu - b0 < NB) ? nu - b0 : NB;
+            const int t0 = b0 + bs;
+            if (t0 >= nu) break;
+            // (2) rows below the block: row i solves L[i, b] = A[i, b] L_bb^-T, right-looking so the updates are independent
+            for (int i = t0 + tid; i < nu; i += nth) {
+                double* Li = S.K + pk(i, b0);
                 double row[NB];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) row[c] = (act && c < bs) ? Li[c] : 0.0;
+                for (int c = 0; c < NB; ++c) row[c] = (c < bs) ? Li[c] : 0.0;
 #pragma unroll
                 for (int c = 0; c < NB; ++c) {
-                    double v = row[c];
+                    if (c < bs) {
+                        row[c] *= s_invd[c];
 #pragma unroll
-                    for (int k = 0; k < NB; ++k)
-                        if (k < c) v -= row[k] * __shfl_sync(0xffffffffu, a8[k], c);
-                    const double dcc = __shfl_sync(0xffffffffu, a8[c], c);
-                    row[c] = (c < bs) ? v / dcc : 0.0;
+                        for (int c2 = c + 1; c2 < NB; ++c2)
+                            if (c2 < bs) row[c2] -= row[c] * S.K[pk(b0 + c2, b0 + c)];
+                    }
                 }
-                if (act) {
-#pragma unroll
-                    for (int c = 0; c < NB; ++c)
-                        if (c < bs) Li[c] = row[c];
-                }
-            }
-            __syncthreads();
-            if (wid == 0) {   // the factored block itself (nobody reads it again before the final barrier)
 #pragma unroll
                 for (int c = 0; c < NB; ++c)
-                    if (lane < bs && c <= lane && c < bs) S.K[pk(b0 + lane, b0 + c)] = a8[c];
+                    if (c < bs) Li[c] = row[c];
             }
-            // (3) trailing update A[i][l] -= sum_c L[i][b0+c] L[l][b0+c], 4 x 4 tiles, 16 x 16 threads over the tile grid
-            const int t0 = b0 + bs;
-            if (t0 < nu) {
-                const int side = (nu - t0 + 3) >> 2;
-                const int ty = tid >> 4, tx = tid & 15;
-                for (int ti = ty; ti < side; ti += 16)
-                    for (int tl = tx; tl <= ti; tl += 16) {
-                        const int i0 = t0 + 4 * ti, l0 = t0 + 4 * tl;
-                        double acc[4][4];
+            __syncthreads();
+            // (3) trailing update A[i][l] -= sum_c L[i][b0+c] L[l][b0+c], 4 x 4 tiles over the lower triangle of the trailing block
+            const int side = (nu - t0 + 3) >> 2;
+            constexpr int LR = NB / 4;   // tile rows of the next diagonal block; they come first in the row-by-row enumeration
+            const int look = (side < LR) ? side * (side + 1) / 2 : LR * (LR + 1) / 2;
+            const int ntile = side * (side + 1) / 2;
+            auto do_tile = [&](int t) {
+                int ti = static_cast<int>((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+                while (ti * (ti + 1) / 2 > t) --ti;
+                const int tl = t - ti * (ti + 1) / 2;
+                const int i0 = t0 + 4 * ti, l0 = t0 + 4 * tl;
+                double acc[4][4];
 #pragma unroll
-                        for (int a2 = 0; a2 < 4; ++a2)
+                for (int a2 = 0; a2 < 4; ++a2)
 #pragma unroll
-                            for (int c2 = 0; c2 < 4; ++c2) acc[a2][c2] = 0.0;
+                    for (int c2 = 0; c2 < 4; ++c2) acc[a2][c2] = 0.0;
 #pragma unroll
-                        for (int h = 0; h < NB; h += 4) {
-                            double ra[4][4], rc[4][4];
+                for (int h = 0; h < NB; h += 4) {
+                    double ra[4][4], rc[4][4];
 #pragma unroll
-                            for (int a2 = 0; a2 < 4; ++a2) {
-                                const int ii = (i0 + a2 < nu) ? i0 + a2 : nu - 1, ll = (l0 + a2 < nu) ? l0 + a2 : nu - 1;
-                                const double* pa = S.K + pk(ii, b0 + h);
-                                const double* pc = S.K + pk(ll, b0 + h);
+                    for (int a2 = 0; a2 < 4; ++a2) {
+                        const int ii = (i0 + a2 < nu) ? i0 + a2 : nu - 1, ll = (l0 + a2 < nu) ? l0 + a2 : nu - 1;
+                        const double* pa = S.K + pk(ii, b0 + h);
+                        const double* pc = S.K + pk(ll, b0 + h);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    ra[a2][k] = (h + k < bs) ? pa[k] : 0.0;
-                                    rc[a2][k] = (h + k < bs) ? pc[k] : 0.0;
-                                }
-                            }
-#pragma unroll
-                            for (int a2 = 0; a2 < 4; ++a2)
-#pragma unroll
-                                for (int c2 = 0; c2 < 4; ++c2)
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) acc[a2][c2] += ra[a2][k] * rc[c2][k];
-                        }
-#pragma unroll
-                        for (int a2 = 0; a2 < 4; ++a2) {
-                            const int ii = i0 + a2;
-                            if (ii >= nu) continue;
-                            double* Ki = S.K + ii * (ii + 1) / 2;
-#pragma unroll
-                            for (int c2 = 0; c2 < 4; ++c2) {
-                                const int ll = l0 + c2;
-                                if (ll <= ii) Ki[ll] -= acc[a2][c2];
-                            }
+                        for (int k = 0; k < 4; ++k) {
+                            ra[a2][k] = (h + k < bs) ? pa[k] : 0.0;
+                            rc[a2][k] = (h + k < bs) ? pc[k] : 0.0;
                         }
                     }
+#pragma unroll
+                    for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; ++c2)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) acc[a2][c2] += ra[a2][k] * rc[c2][k];
+                }
+#pragma unroll
+                for (int a2 = 0; a2 < 4; ++a2) {
+                    const int ii = i0 + a2;
+                    if (ii >= nu) continue;
+                    double* Ki = S.K + ii * (ii + 1) / 2;
+#pragma unroll
+                    for (int c2 = 0; c2 < 4; ++c2) {
+                        const int ll = l0 + c2;
+                        if (ll <= ii) Ki[ll] -= acc[a2][c2];
+                    }
+                }
+            };
+            if (wid == 0) {
+                if (lane < look) do_tile(lane);
+                __syncwarp();
+                factor_diag(t0);
+            } else {
+                for (int t = look + tid - 32; t < ntile; t += nth - 32) do_tile(t);
             }
             __syncthreads();
         }
