@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256, 1) k_gradient(Params P, const Instance* _
     KktView kv;
     kv.K = K; kv.ld = nu; kv.Hg = Hg; kv.nu = nu; kv.nf = nf; kv.N = N; kv.ns = ns; kv.ne = ne; kv.neq = neq; kv.nkc = nkc;
     kv.wv = wv; kv.phi = phipos; kv.phi_stride = L.max_nu; kv.pw = s_pw; kv.pcnt = s_pcnt; kv.poff = s_poff;
-    kv.smp = samples; kv.eq = eqs; kv.col = col; kv.ckc = ckc; kv.mu_f = mu_f; kv.inv_delta = 0.0; kv.sign = -1.0;
+    kv.smp = samples; kv.eq = eqs; kv.col = col; kv.ckc = ckc; kv.mu_f = mu_f; kv.inv_delta = 0.0; kv.sign = -1.0; kv.tile = nullptr;
     kkt_assemble<false>(kv, s_fbase, s_nfv);
     for (int idx = tid; idx < nu * nu; idx += nth) {   // mirror the lower triangle
         const int i = idx / nu, j = idx % nu;

@@ -37,6 +37,17 @@ struct Smem {
 
 __device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 
+// 1 / sqrt(d) for a positive, normal d: single-precision seed and three Newton steps in double (the pivots of K are far
+// from the denormal range); the library rsqrt() sits on the serial path of the factorisation with its special-case code.
+__device__ __forceinline__ double fast_rsqrt(double d) {
+    double x = static_cast<double>(rsqrtf(static_cast<float>(d)));
+    const double h = 0.5 * d;
+    x = x * (1.5 - h * x * x);
+    x = x * (1.5 - h * x * x);
+    x = x * (1.5 - h * x * x);
+    return x;
+}
+
 }  // namespace
 
 struct IpmCaps {          // per-launch shared-memory sizing, from the actual maxima over the batch
@@ -134,6 +145,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     __shared__ int s_fbase[kNumEE], s_pbase[kNumEE], s_nfv[kNumEE], s_npv[kNumEE];
     __shared__ int s_flag;
     __shared__ double s_invd[16];   // reciprocals of the current diagonal block's pivots
+    __shared__ uint16_t s_tile[kTileTab];   // (ti << 8) | tl of the row-by-row enumeration of lower-triangle tiles
     __shared__ int s_sb[kNumEE + 1];   // per-foot sample ranges (samples are stored foot-major)
     __shared__ EqRow s_eq[kMaxEq];
     if (tid < neq) s_eq[tid] = eqs[tid];
@@ -173,6 +185,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     auto rhs_of = [&](int i) -> double { return (i < m_force) ? ((i % 6 == 0) ? fbound : 0.0) : S.d[i - m_force]; };
     __syncthreads();
     kkt_build_colinfo(S.col, nu, nf, N, s_fbase, s_pbase, s_nfv, s_npv, s_sb, S.smp, S.pcnt, S.poff);
+    kkt_build_tile_table(s_tile, (nu + 3) >> 2);
     __syncthreads();
 
     // ------------------------------------------------------------------------------------------------ operators
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     KktView kv;
     kv.K = S.K; kv.ld = 0; kv.Hg = Hg; kv.nu = nu; kv.nf = nf; kv.N = N; kv.ns = ns; kv.ne = ne; kv.neq = neq; kv.nkc = nkc;
     kv.wv = S.wv; kv.phi = S.phi; kv.phi_stride = S.phi_stride; kv.pw = S.pw; kv.pcnt = S.pcnt; kv.poff = S.poff;
-    kv.smp = S.smp; kv.eq = s_eq; kv.col = S.col; kv.ckc = S.ckc; kv.mu_f = mu_f; kv.inv_delta = inv_delta; kv.sign = 1.0;
+    kv.smp = S.smp; kv.eq = s_eq; kv.col = S.col; kv.ckc = S.ckc; kv.mu_f = mu_f; kv.inv_delta = inv_delta; kv.sign = 1.0; kv.tile = s_tile;
     auto build_and_factor = [&]() -> bool {
         kkt_assemble<true>(kv, s_fbase, s_nfv);
         // Blocked right-looking Cholesky on the packed lower triangle, NB-column panels, two barriers per panel:
@@ -319,7 +332,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
                     const double d = __shfl_sync(0xffffffffu, a[c], c);
                     const bool bad = !(d > 0.0);
                     if (bad && lane == 0) s_flag = 1;
-                    const double inv = bad ? 1.0 : rsqrt(d);
+                    const double inv = bad ? 1.0 : fast_rsqrt(d);
                     a[c] = (lane == c) ? d * inv : a[c] * inv;
                     if (lane == c) s_invd[c] = inv;
 #pragma unroll
@@ -366,10 +379,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             const int look = (side < LR) ? side * (side + 1) / 2 : LR * (LR + 1) / 2;
             const int ntile = side * (side + 1) / 2;
             auto do_tile = [&](int t) {
-                int ti = static_cast<int>((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-                while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-                while (ti * (ti + 1) / 2 > t) --ti;
-                const int tl = t - ti * (ti + 1) / 2;
+                const int ti = s_tile[t] >> 8, tl = s_tile[t] & 255;
                 const int i0 = t0 + 4 * ti, l0 = t0 + 4 * tl;
                 double acc[4][4];
 #pragma unroll

@@ -37,7 +37,19 @@ struct KktView {
     const ColInfo* col;        // [nu]
     double* ckc;               // scratch [nkc]
     double mu_f, inv_delta, sign;
+    const uint16_t* tile;      // optional tile table (kkt_build_tile_table); nullptr: decode by square root
 };
+
+constexpr int kTileTab = 41 * 42 / 2;   // tiles of a 164 x 164 lower triangle (max_spline_vars 160 + padding)
+
+// (ti << 8) | tl for t = 0 .. side (side + 1) / 2 - 1, tiles enumerated row by row
+__device__ inline void kkt_build_tile_table(uint16_t* tab, int side) {
+    for (int ti = threadIdx.x; ti < side; ti += blockDim.x)
+        for (int tl = 0; tl <= ti; ++tl) {
+            const int t = ti * (ti + 1) / 2 + tl;
+            if (t < kTileTab) tab[t] = static_cast<uint16_t>((ti << 8) | tl);
+        }
+}
 
 // Fills ColInfo for every spline variable (once per kernel; the tables do not change between iterations).
 __device__ inline void kkt_build_colinfo(ColInfo* col, int nu, int nf, int N, const int* fbase, const int* pbase, const int* nfv,
@@ -116,10 +128,16 @@ __device__ void kkt_assemble(const KktView& v, const int* fbase, const int* nfv)
     const int fside = (nf + 3) >> 2;
     const int ntile = fside * (fside + 1) / 2;
     for (int t = tid; t < ntile; t += nth) {
-        int ti = static_cast<int>((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);   // tile (ti, tl), tl <= ti, row by row
-        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-        while (ti * (ti + 1) / 2 > t) --ti;
-        const int tl = t - ti * (ti + 1) / 2;
+        int ti, tl;   // tile (ti, tl), tl <= ti, row by row
+        if (v.tile) {
+            ti = v.tile[t] >> 8;
+            tl = v.tile[t] & 255;
+        } else {
+            ti = static_cast<int>((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+            while (ti * (ti + 1) / 2 > t) --ti;
+            tl = t - ti * (ti + 1) / 2;
+        }
         const int i0 = 4 * ti, l0 = 4 * tl;
         double acc[4][4];
 #pragma unroll
