@@ -160,6 +160,9 @@ def main():
                     help="BASELINE config #5: --scenarios closed-loop scenarios cut across the ranks (strong scaling); a step is one "
                          "closed-loop tick (plant step + RTI solve) of every scenario")
     ap.add_argument("--scenarios", type=int, default=65536)
+    ap.add_argument("--gait-opt", type=int, default=0, metavar="K",
+                    help="BASELINE config #3: per step every instance does solve -> dH/dtheta -> contact-time LP -> line search over "
+                         "K candidates (K + 1 RTI solves per instance and step); use with --config a1_gait_opt_config --batch 64")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -168,6 +171,10 @@ def main():
     cores = os.cpu_count() or 1
     workload = (f"{args.config}: A1 trot SRB-MPC, N={cfg['num_nodes']} nodes x {cfg['integrator_dt']} s, "
                 f"{args.batch} synthetic initial states per GPU, t0=0")
+    if args.gait_opt:
+        workload = (f"{args.config}: gait optimisation, N={cfg['num_nodes']} nodes x {cfg['integrator_dt']} s, {args.batch} instances per GPU, "
+                    f"per step solve + dH/dtheta + contact-time LP + line search over {args.gait_opt} candidates "
+                    f"({1 + args.gait_opt} RTI solves per instance and step)")
     if args.closed_loop:
         workload = (f"{args.config}: disturbance-rejection sweep, N={cfg['num_nodes']} nodes x {cfg['integrator_dt']} s, "
                     f"{args.scenarios} closed-loop scenarios cut across {world} GPU(s), plant = node 1 of the solved trajectory")
@@ -221,11 +228,18 @@ def main():
 
     # ---- device-resident throughput: inputs already in HBM, K solves timed with CUDA events on the launching stream
     dt_plant = cfg["integrator_dt"]
+    gait_stats = {"grad_ok": 0, "best_hist": np.zeros(max(args.gait_opt, 1), np.int64)}
 
     def step():
         if args.closed_loop:
             mpc.advance_plant(dt_plant)
         mpc.solve_resident()
+        if args.gait_opt:   # MPCController::GaitOpt + GaitOptimizer::LineSearch for every instance of the batch
+            g = mpc.ComputeCostFcnDerivWrtContactTimes()
+            lp = mpc.OptimizeContactTimes(t0)
+            ls = mpc.LineSearch(states, t0, ee, lp["xk"], lp["step"], K=args.gait_opt)
+            gait_stats["grad_ok"] = int((g["status"] == 0).sum())
+            gait_stats["best_hist"] += np.bincount(np.maximum(ls["best"], 0), minlength=args.gait_opt)
 
     mpc.upload(states, t0, ee)
     mpc.solve_resident()
@@ -305,7 +319,8 @@ def main():
             dist.destroy_process_group()
         return
 
-    value = total * args.steps / (ms_dev * 1e-3)
+    solves_per_instance = 1 + args.gait_opt
+    value = total * solves_per_instance * args.steps / (ms_dev * 1e-3)
     sz = mpc.sizes(0)
     peaks = {}
     if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
@@ -328,9 +343,12 @@ def main():
                    "l2": "inputs larger than L2 (instance + workspace state is > 1 GB per 4096 instances)",
                    "solved_fraction": solved / total, "mean_ipm_iters": float(np.mean(res["iters"]))},
         "clocks": clocks,
-        "e2e": {"value": total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0 if args.closed_loop else B * (13 + 1 + 12) * 8,
+        "e2e": {"value": total * (1 if not args.gait_opt else 1) * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0 if args.closed_loop else B * (13 + 1 + 12) * 8,
                 "d2h_bytes_per_step": B * 248, "timing": "wall clock around bgg_solve_batch, synchronised both sides"},
         "gpu_launches": int(launches),
+        "gait_opt": ({"candidates": args.gait_opt, "instances_with_gradient": gait_stats["grad_ok"],
+                      "argmin_histogram": gait_stats["best_hist"].tolist(),
+                      "gait_steps_per_s": total * args.steps / (ms_dev * 1e-3)} if args.gait_opt else None),
         "kernel_ms": kms,
         "latency": lat,
         "roofline": {"kernel": "k_ipm", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

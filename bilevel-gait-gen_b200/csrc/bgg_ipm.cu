@@ -37,14 +37,13 @@ struct Smem {
 
 __device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 
-// 1 / sqrt(d) for a positive, normal d: single-precision seed and three Newton steps in double (the pivots of K are far
+// 1 / sqrt(d) for a positive, normal d: single-precision seed and two Newton steps in double (the pivots of K are far
 // from the denormal range); the library rsqrt() sits on the serial path of the factorisation with its special-case code.
 __device__ __forceinline__ double fast_rsqrt(double d) {
     double x = static_cast<double>(rsqrtf(static_cast<float>(d)));
     const double h = 0.5 * d;
-    x = x * (1.5 - h * x * x);
-    x = x * (1.5 - h * x * x);
-    x = x * (1.5 - h * x * x);
+    x = x * (1.5 - h * x * x);   // 2^-22 -> 2^-43
+    x = x * (1.5 - h * x * x);   // -> below double rounding
     return x;
 }
 
@@ -420,7 +419,23 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
                 }
             };
             if (wid == 0) {
-                if (lane < look) do_tile(lane);
+                // next diagonal block, one lane per entry (36 entries of the 8 x 8 lower triangle): short dependent chains
+                // instead of three whole tiles on three lanes
+                for (int e = lane; e < NB * (NB + 1) / 2; e += 32) {
+                    int r = 0;
+                    while ((r + 1) * (r + 2) / 2 <= e) ++r;
+                    const int c = e - r * (r + 1) / 2;
+                    const int i = t0 + r, l = t0 + c;
+                    if (i < nu) {
+                        const double* pa = S.K + pk(i, b0);
+                        const double* pc = S.K + pk(l, b0);
+                        double acc = 0.0;
+#pragma unroll
+                        for (int h = 0; h < NB; ++h)
+                            if (h < bs) acc += pa[h] * pc[h];
+                        S.K[pk(i, l)] -= acc;
+                    }
+                }
                 __syncwarp();
                 factor_diag(t0);
             } else {
