@@ -320,30 +320,36 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         // other seven warps finish the trailing update, so the serial step (1) is off the critical path.
         if (tid == 0) s_flag = 0;
         constexpr int NB = 8;
-        auto factor_diag = [&](int b0) {   // warp 0 only
+        auto factor_diag = [&](int b0) {   // warp 0 only; lane 0 holds the whole NB x NB triangle in registers: no shuffles on
+            if (lane != 0) return;         // the serial path, the independent updates of a step overlap its rsqrt chain
             const int bs = (nu - b0 < NB) ? nu - b0 : NB;
-            double a[NB];
+            double a[NB][NB];
 #pragma unroll
-            for (int c = 0; c < NB; ++c) a[c] = (lane < bs && c <= lane) ? S.K[pk(b0 + lane, b0 + c)] : 0.0;
+            for (int r = 0; r < NB; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) a[r][c] = (r < bs) ? S.K[pk(b0 + r, b0 + c)] : ((r == c) ? 1.0 : 0.0);
+            bool bad_any = false;
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
-                if (c < bs) {
-                    const double d = __shfl_sync(0xffffffffu, a[c], c);
-                    const bool bad = !(d > 0.0);
-                    if (bad && lane == 0) s_flag = 1;
-                    const double inv = bad ? 1.0 : fast_rsqrt(d);
-                    a[c] = (lane == c) ? d * inv : a[c] * inv;
-                    if (lane == c) s_invd[c] = inv;
+                const double d = a[c][c];
+                const bool bad = !(d > 0.0);
+                bad_any |= bad;
+                const double inv = bad ? 1.0 : fast_rsqrt(d);
+                a[c][c] = d * inv;
+                s_invd[c] = inv;
 #pragma unroll
-                    for (int c2 = c + 1; c2 < NB; ++c2) {
-                        const double t = __shfl_sync(0xffffffffu, a[c], c2);   // L[c2][c]
-                        if (lane >= c2) a[c2] -= a[c] * t;
-                    }
-                }
+                for (int r = c + 1; r < NB; ++r) a[r][c] *= inv;
+#pragma unroll
+                for (int c2 = c + 1; c2 < NB; ++c2)
+#pragma unroll
+                    for (int r = c2; r < NB; ++r) a[r][c2] -= a[r][c] * a[c2][c];
             }
+            if (bad_any) s_flag = 1;
 #pragma unroll
-            for (int c = 0; c < NB; ++c)
-                if (lane < bs && c <= lane) S.K[pk(b0 + lane, b0 + c)] = a[c];
+            for (int r = 0; r < NB; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c)
+                    if (r < bs) S.K[pk(b0 + r, b0 + c)] = a[r][c];
         };
         __syncthreads();
         if (wid == 0) factor_diag(0);
