@@ -4,7 +4,9 @@
 #include "mpc_b200.h"
 
 #include <cmath>
+#include <chrono>
 #include <cstring>
+#include <ctime>
 #include <cstdio>
 
 #include "../csrc/bgg_spline.cuh"
@@ -227,7 +229,9 @@ Trajectory MPC::Solve(const vector_t& state, double init_time, const std::vector
     double ee[12];
     FlattenEE(ee_start_locations, ee);
     int32_t status = 0, iters = 0;
+    const auto tic = std::chrono::steady_clock::now();   // utils::Timer, utils/timer.cpp:16-23
     Check(bgg_solve_batch(h_, state.data(), &init_time, ee, &status, &iters, &alpha_, &cost_));
+    last_solve_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tic).count();
     quality_ = static_cast<SolveQuality>(status);
     iters_ = iters;
     cost_sum_ += cost_;
@@ -343,11 +347,42 @@ void MPC::PrintStats() const {
     std::printf("solves: %d, last cost: %g, avg cost: %g, last alpha: %g, last qp iterations: %d, solve quality: %d\n", solves_, cost_,
                 GetAvgCost(), alpha_, iters_, static_cast<int>(quality_));
 }
-void MPC::PrintStatLineToFile(std::ofstream& log_file) const {   // the columns of mpc.cpp:901-989 that this path produces
+void MPC::PrintStatLineToFile(std::ofstream& log_file) const {
+    // Same header and the same ten 15-wide columns as the reference's log (mpc.cpp:901-989), so its log readers keep working.
+    char buf[512];
+    const int col = 15, table = 10 * col;
+    auto put = [&](const char* s, int n) { log_file.write(s, n); };
+    auto rule = [&]() {
+        std::string r(table, '-');
+        r += "\n";
+        put(r.c_str(), static_cast<int>(r.size()));
+    };
+    if (!used_log_file_) {
+        const std::time_t now = std::time(nullptr);
+        rule();
+        int n = std::snprintf(buf, sizeof buf, "%*sMPC Statistics\nMPC started at: %s", table / 2 - 7, "", std::ctime(&now));
+        put(buf, n);
+        n = std::snprintf(buf, sizeof buf,
+                          "Number of nodes: %d\nMPC time step: %g\nForce bounds: %g\nEnd Effector box size: %g %g\nForce cost: %g\n"
+                          "Foot offset: %g\nSwing height: %g\n",
+                          info_.num_nodes, info_.integrator_dt, info_.force_bound, info_.ee_box_size(0), info_.ee_box_size(1), info_.force_cost,
+                          info_.foot_offset, info_.swing_height);
+        put(buf, n);
+        rule();
+        n = std::snprintf(buf, sizeof buf, "%-15s%-15s%-15s%-15s%-15s%-15s%-15s%-15s%-15s%-15s\n", "Solve #", "Time (ms)", "Constraints",
+                          "Step Norm", "Alpha", "Cost", "Merit", "Merit dd", "Solve Type", "QP Cost");
+        put(buf, n);
+        rule();
+        used_log_file_ = true;
+    }
+    static const char* names[] = {"Solved", "Solved Inacc", "Max Iter", "P - Infeasible", "D - Infeasible", "P - Infeasible Inacc",
+                                  "D - Infeasible Inacc", "Unsolved", "Other"};
     bgg_sizes sz;
     Check(bgg_get_sizes(h_, 0, &sz));
-    log_file << solves_ << " " << static_cast<int>(quality_) << " " << sz.eq_violation << " " << sz.step_norm << " " << sz.alpha << " "
-             << sz.cost << " " << sz.merit << " " << sz.merit_dd << std::endl;
+    const int n = std::snprintf(buf, sizeof buf, "%-15d%-15g%-15g%-15g%-15g%-15g%-15g%-15g%-15s%-15g\n", solves_ - 1, last_solve_ms_,
+                                sz.eq_violation, sz.step_norm, sz.alpha, sz.cost, sz.merit, sz.merit_dd,
+                                names[quality_ <= Other ? quality_ : Other], sz.qp_cost);
+    put(buf, n);
 }
 
 // ------------------------------------------------------------------------------------------------------ MPCSingleRigidBody

@@ -212,7 +212,8 @@ protected:
     bgg_robot robot_{};
     bgg_handle* h_ = nullptr;
     SolveQuality quality_ = Unsolved;
-    double cost_ = 0, cost_sum_ = 0, alpha_ = 0;
+    double cost_ = 0, cost_sum_ = 0, alpha_ = 0, last_solve_ms_ = 0;
+    mutable bool used_log_file_ = false;
     int solves_ = 0, iters_ = 0;
     double Q_[12], xdes_[12], Phi_[12], Phi_w_[12];
     bool have_Q_ = false, have_Phi_ = false, have_Phi_w_ = false;

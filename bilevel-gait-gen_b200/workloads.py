@@ -20,14 +20,14 @@ CONFIGS = {
                              Q=[340, 340, 4000, 0.100, 0.100, 10, 3000, 3000, 3000, 1, 1, 1],
                              srb_init=[0, 0, 0.3, 0, 0, 0, 0, 0, 0, 1.0, 0, 0, 0],
                              srb_target=[0, 0, 0.3, 0, 0, 0, 0, 0, 0, 1.0, 0, 0, 0]),
-    # apps/a1_gait_opt_config.yaml
+    # apps/a1_gait_opt_config.yaml (it has no srb_target entry: the target is the initial state)
     "a1_gait_opt_config": dict(num_nodes=50, integrator_dt=0.02, friction_coef=0.6, force_bound=200.0, swing_height=0.1,
                                foot_offset=0.001, ee_box_size=(0.15, 0.15), force_cost=0.0,
                                Q=[55, 40, 500, 0.1, 0.1, 0.1, 5000, 5000, 5000, 0.1, 0.1, 0.1],
-                               srb_init=[0, 0, 0.3, 0, 0, 0, 0, 0, 0, 1.0, 0, 0, 0],
-                               srb_target=[0, 0, 0.3, 0, 0, 0, 0, 0, 0, 1.0, 0, 0, 0]),
+                               srb_init=[0, 0, 0.34, 0, 0, 0, 0, 0, 0, 1.0, 0, 0, 0],
+                               srb_target=[0, 0, 0.34, 0, 0, 0, 0, 0, 0, 1.0, 0, 0, 0]),
     # apps/a1_config_distr_rejection.yaml
-    "a1_config_distr_rejection": dict(num_nodes=50, integrator_dt=0.02, friction_coef=0.5, force_bound=150.0, swing_height=0.075,
+    "a1_config_distr_rejection": dict(num_nodes=50, integrator_dt=0.02, friction_coef=0.6, force_bound=200.0, swing_height=0.075,
                                       foot_offset=0.015, ee_box_size=(0.15, 0.15), force_cost=0.001,
                                       Q=[140, 140, 12000, 0.015, 0.015, 10, 3000, 3000, 3000, 1, 1, 1],
                                       srb_init=[0, 0, 0.3, 2.5, 0, 0, 0, 0, 0, 1.0, 0, 0, 0],

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <iostream>
 
+#include "config_parser.h"
 #include "mpc_b200.h"
 
 using namespace mpc;
@@ -120,6 +121,20 @@ int main(int argc, char** argv) {
         std::printf("ls_first_times");
         for (const auto& t : res.first.at(0)) std::printf(" %.10e", t.GetTime());
         std::printf("\n");
+        {   // per-solve statistics log in the reference's layout (mpc.cpp:901-989)
+            std::ofstream log(std::string(argv[1]) + ".log");
+            mpc.PrintStatLineToFile(log);
+            mpc.GetRealTimeUpdate(init_state, 0.05, ee, false);
+            mpc.PrintStatLineToFile(log);
+        }
+        {   // configuration file in the reference's YAML layout -> MPCInfo (test/mpc_test.cpp:43-83)
+            if (argc > 2) {
+                utils::ConfigParser config(argv[2]);
+                const MPCInfo from_file = MPCInfoFromConfig(config);
+                std::printf("yaml_num_nodes %d\nyaml_friction %.6f\nyaml_frames %zu\n", from_file.num_nodes, from_file.friction_coef,
+                            from_file.ee_frames.size());
+            }
+        }
         std::printf("done 1\n");
     } catch (const std::exception& e) {
         std::printf("exception %s\n", e.what());

@@ -333,31 +333,53 @@ def test_contact_time_lp_and_line_search_match_oracle(cfg_name):
     ee[0] = wl.EE_NOMINAL
     gpu, oracles, out, go = _gradient_case(cfg_name, states, ee)
     res = gpu.ComputeCostFcnDerivWrtContactTimes()
-    lp = gpu.OptimizeContactTimes(0.0)            # on the CUDA path's own gradient
+    # LP kernel on the ORACLE's gradient (the gradient kernel has its own parity tests; a component of size 1e-6 whose
+    # sign differs between the two gradients would move the LP to another vertex)
+    grads = np.zeros((B, 4, 12))
+    g_os = []
+    for b in range(B):
+        o = oracles[b]
+        ok = res["status"][b] == 0 and o.qp_solution()["status"] == 0
+        g_os.append(go.cost_gradient(o) if ok else None)
+        if ok:
+            k = 0
+            for e, (t, _) in enumerate(go.contact_times(o)):
+                grads[b, e, :len(t)] = g_os[b][k:k + len(t)]
+                k += len(t)
+    lp = gpu.OptimizeContactTimes(0.0, dHdtheta=grads)
     assert np.all(lp["status"] == 0)
-    # LP: against the oracle's LP optimum for the oracle's gradient (the two gradients agree to 1e-7, the optimum is a vertex)
     steps_o, xk_o = [], []
     for b in range(B):
         o = oracles[b]
-        if res["status"][b] != 0 or o.qp_solution()["status"] != 0:
+        if g_os[b] is None:
             steps_o.append(None)
             xk_o.append(None)
             continue
         ct = go.contact_times(o)
-        g_o = go.cost_gradient(o)
+        g_o = g_os[b]
         s_o = go.solve_gait_lp(ct, g_o, 0.0)
         counts = [len(t) for t, _ in ct]
         s_g = np.concatenate([lp["step"][b, e, :counts[e]] for e in range(4)])
         x_g = np.concatenate([lp["xk"][b, e, :counts[e]] for e in range(4)])
-        assert np.abs(s_g - s_o).max() < 1e-6, (s_g, s_o)
+        A, lb, ub = go.gait_lp(ct, g_o, 0.0)
+        r = A @ s_g
+        assert np.all(r <= ub + 1e-9) and np.all(r >= lb - 1e-9), "the CUDA LP step violates the reference's constraints"
+        # same optimal value; the same vertex unless the optimum is a face (a gradient entry that is numerically zero)
+        assert abs(g_o @ s_g - g_o @ s_o) <= 1e-9 * max(1.0, np.abs(g_o).max())
+        differs = np.abs(s_g - s_o) > 1e-6
+        assert np.all(np.abs(g_o[differs]) <= 1e-6 * max(1.0, np.abs(g_o).max())), (s_g, s_o, g_o)
         assert np.array_equal(x_g, np.concatenate([t for t, _ in ct]))
-        nt_o = np.concatenate(go.contact_times_for(ct, x_g, s_o, 1.0))
+        nt_o = np.concatenate(go.contact_times_for(ct, x_g, s_g, 1.0))
         nt_g = np.concatenate([lp["new_times"][b, e, :counts[e]] for e in range(4)])
-        assert np.abs(nt_g - nt_o).max() < 1e-6
-        steps_o.append(s_o)
+        assert np.abs(nt_g - nt_o).max() < 1e-9
+        steps_o.append(s_g)     # the line search below runs from the CUDA step on both sides
         xk_o.append(x_g)
-    # line search with LS_SIZE = 10 from the same step on both sides
+    # line search with LS_SIZE = 10 from the same step and -- mirrored -- the same parent trajectory on both sides (a child
+    # QP whose contact times moved by up to 0.1 s amplifies a 1e-7 difference of the parents a thousandfold)
     K = 10
+    for b in range(B):
+        if steps_o[b] is not None:
+            common.mirror_oracle_to_gpu(oracles[b], gpu, b)
     ls = gpu.LineSearch(states, np.zeros(B), ee, lp["xk"], lp["step"], K=K)
     checked = 0
     for b in range(B):

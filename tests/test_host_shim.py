@@ -39,6 +39,26 @@ def test_urdf_reader_matches_the_robot_constants_fixture():
     assert np.abs(np.array(rb.hip_xy[:]).reshape(4, 2) - np.array(gold["hip_offsets_xy"])).max() < 1e-12
 
 
+@pytest.mark.skipif(not os.path.exists("/root/reference/apps"), reason="the reference's YAML files are only present in the build container")
+@pytest.mark.parametrize("name", ["a1_configuration", "a1_gait_opt_config", "a1_config_distr_rejection"])
+def test_config_parser_reads_the_reference_yaml_and_pins_the_named_workloads(name):
+    """utils::ConfigParser + the MPCInfo fill of test/mpc_test.cpp:46-83 on the reference's own configuration files; the
+    values must be the ones bilevel-gait-gen_b200/workloads.py (bench.py, tests) carries for the same name."""
+    lib = C.CDLL(SHIM_SO)
+    out = (C.c_double * 47)()
+    assert lib.bgg_host_parse_config(f"/root/reference/apps/{name}.yaml".encode(), out) == 0
+    v = list(out)
+    cfg = wl.CONFIGS[name]
+    assert int(v[0]) == cfg["num_nodes"]
+    got = dict(integrator_dt=v[1], friction_coef=v[2], force_bound=v[3], swing_height=v[4], foot_offset=v[5], force_cost=v[8])
+    for k, x in got.items():
+        assert x == cfg[k], (k, x, cfg[k])
+    assert tuple(v[6:8]) == tuple(cfg["ee_box_size"])
+    assert v[9:21] == [float(x) for x in cfg["Q"]]
+    assert v[21:34] == [float(x) for x in cfg["srb_init"]]
+    assert v[34:47] == [float(x) for x in cfg["srb_target"]]
+
+
 @pytest.mark.gpu
 def test_shim_reproduces_the_oracle_on_the_reference_test_setup(tmp_path):
     import gait_oracle as go
@@ -46,7 +66,29 @@ def test_shim_reproduces_the_oracle_on_the_reference_test_setup(tmp_path):
     consts = [rb["mass"]] + list(np.ravel(rb["Ir"])) + list(np.ravel(rb["Ir_inv"])) + list(np.ravel(rb["hip_offsets_xy"]))
     path = tmp_path / "robot.txt"
     path.write_text(" ".join(repr(float(v)) for v in consts))
-    out = subprocess.run([TEST_BIN, str(path)], capture_output=True, text=True, timeout=300)
+    yaml = tmp_path / "cfg.yaml"   # the reference's YAML layout: scalars, strings, multi-line flow sequences, comments
+    yaml.write_text("""robot_urdf: "/somewhere/a1.urdf"
+collision_frames: ["FL_foot", "FR_foot", "RL_foot", "RR_foot"]    # for pinocchio
+init_config: [0., 0., 0.3, 0.0, 0.0, 0.0, 1.0, # base
+              -0.02, 0.9, -1.6,       # front left
+              0.02, 0.9, -1.6, 0.02, 0.9, -1.6, -0.02, 0.9, -1.6]
+friction_coef: 0.5 #0.3
+discretization_steps: 1
+num_nodes: 20 #30
+integrator_dt: 0.05
+num_qp: 1
+vel_bounds: [10, 10, 10]
+joint_bounds_lb: [-0.8, -3.0]
+joint_bounds_ub: [0.8, 4.1]
+num_switches: 2
+force_bound: 150
+swing_height: 0.075
+ee_box_size: [0.15, 0.15]
+run_time_iterations: 6000
+foot_offset: 0.015
+force_cost: 0.000
+""")
+    out = subprocess.run([TEST_BIN, str(path), str(yaml)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     kv = {}
     for line in out.stdout.splitlines():
@@ -61,6 +103,13 @@ def test_shim_reproduces_the_oracle_on_the_reference_test_setup(tmp_path):
     assert kv["num_equality"] == ["260"] and kv["num_inequality"] == ["752"]
     assert kv["num_contact_nodes"] == ["5", "5", "5", "5"]
     assert kv["copy_cost_equal"] == ["1"] and kv["derivative_terms"] == ["1"]
+    assert kv["yaml_num_nodes"] == ["20"] and kv["yaml_friction"] == ["0.500000"] and kv["yaml_frames"] == ["4"]
+    log = open(str(path) + ".log").read().splitlines()
+    assert log[0] == "-" * 150 and "MPC Statistics" in log[1] and log[3] == "Number of nodes: 20"
+    header = [i for i, l in enumerate(log) if l.startswith("Solve #")][0]
+    assert log[header].split()[:4] == ["Solve", "#", "Time", "(ms)"] and len(log[header]) == 150
+    rows = log[header + 2:]
+    assert len(rows) == 2 and rows[0][:15].strip() == "10" and rows[1][:15].strip() == "11" and "Solved" in rows[0]
 
     cfg_name = "a1_configuration"
     cfg = wl.CONFIGS[cfg_name]
