@@ -9,7 +9,8 @@ mkdir -p build
 # bgg_prepare.cu is compiled without FMA contraction so that exact zeros stay exact (sparsity parity).
 $NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_prepare.o csrc/bgg_prepare.cu 2> build/ptxas_prepare.log
 $NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_condense.o csrc/bgg_condense.cu 2> build/ptxas_condense.log
-$NVCC $ARCH $COMMON -dc -o build/bgg_ipm.o csrc/bgg_ipm.cu 2> build/ptxas_ipm.log
+# chol::factor / chol::solve are __noinline__: cap their registers at the kernel's 2-CTAs-per-SM bound
+$NVCC $ARCH $COMMON -maxrregcount=128 -dc -o build/bgg_ipm.o csrc/bgg_ipm.cu 2> build/ptxas_ipm.log
 $NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_finish.o csrc/bgg_finish.cu 2> build/ptxas_finish.log
 $NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_assemble.o csrc/bgg_assemble.cu 2> build/ptxas_assemble.log
 $NVCC $ARCH $COMMON -dc -o build/bgg_gradient.o csrc/bgg_gradient.cu 2> build/ptxas_gradient.log

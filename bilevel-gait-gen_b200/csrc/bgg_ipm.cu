@@ -14,19 +14,33 @@
 //   6 ns + 2 e + 0 : -p_c(k) + w.u_pos <=  hip_c + box_c/2     e = ((k-4)*4 + foot)*2 + c   (mpc_single_rigid_body.cpp:381-443)
 //   6 ns + 2 e + 1 :  p_c(k) - w.u_pos <= -(hip_c - box_c/2)
 #include "bgg_kernels.cuh"
+#include "bgg_chol.cuh"
 #include "bgg_kkt.cuh"
 
 namespace bgg {
 
+// Phase clocks (tools/profile_phases.py): compiled in only with -DBGG_IPM_PROF into a separate library, never into
+// libbgg_b200.so.  Thread 0 of CTA 0 accumulates clock64() deltas between barrier-delimited phases.
+#ifdef BGG_IPM_PROF
+__device__ long long g_ipm_prof[32];
+#define PROF_DECL __shared__ long long s_prof[32]; long long prof_t = 0; if (threadIdx.x == 0) { for (int i_ = 0; i_ < 32; ++i_) s_prof[i_] = 0; prof_t = clock64(); }
+#define PROF(k) do { if (threadIdx.x == 0) { const long long t_ = clock64(); s_prof[k] += t_ - prof_t; prof_t = t_; } } while (0)
+#define PROF_DUMP do { if (threadIdx.x == 0 && blockIdx.x == 0) for (int i_ = 0; i_ < 32; ++i_) g_ipm_prof[i_] = s_prof[i_]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(k) do { } while (0)
+#define PROF_DUMP do { } while (0)
+#endif
+
 namespace {
 
 struct Smem {
-    double* K;       // packed lower triangle nu(nu+1)/2
+    double* K;       // lower triangle in 8 x 8 blocks (csrc/bgg_chol.cuh)
     double *u, *du, *rd, *rhs, *g, *tmpn;            // nu
     double *s, *lam, *ds, *dl, *rp, *wv, *d;         // m
     double *tkc, *ckc;                               // 2(N-3)
     double *nueq, *re, *dnu;                         // kMaxEq
-    double* red;                                     // 40
+    double* red;                                     // 72
     double* pw;                                      // [(N-3)*4][2] foot-box position weights
     int *pcnt, *poff;                                // [(N-3)*4]
     Sample* smp;                                     // staged force samples
@@ -35,26 +49,160 @@ struct Smem {
     int phi_stride;
 };
 
-__device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
+}  // namespace
 
-// 1 / sqrt(d) for a positive, normal d: single-precision seed and two Newton steps in double (the pivots of K are far
-// from the denormal range); the library rsqrt() sits on the serial path of the factorisation with its special-case code.
-__device__ __forceinline__ double fast_rsqrt(double d) {
-    double x = static_cast<double>(rsqrtf(static_cast<float>(d)));
-    const double h = 0.5 * d;
-    x = x * (1.5 - h * x * x);   // 2^-22 -> 2^-43
-    x = x * (1.5 - h * x * x);   // -> below double rounding
-    return x;
+// What the operators below need.  They are force-inlined: measured on B200, calling them as __noinline__ functions
+// (one copy in the binary, 330 KB of SASS instead of 540 KB) was 20 % slower with the context passed by reference
+// (fields re-read from local memory after every store) and 80 % slower with it passed by value.
+struct IpmCtx {
+    Smem S;
+    const double* Hg;
+    const EqRow* eq;
+    const int *fbase, *pbase, *nfv, *npv;
+    int N, nu, nf, ns, ne, neq, nkc;
+    double mu_f;
+};
+
+// out[0..m) = C v   (v: nu-vector in shared memory)
+static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double* v, double* out) {
+    const Smem& S = c.S;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
+    const int nf = c.nf, ns = c.ns, ne = c.ne, nkc = c.nkc;
+    const double mu_f = c.mu_f;
+    for (int q = wid; q < nkc; q += nwarp) {     // dense position rows: one warp per (node, coord)
+        const double* row = S.phi + static_cast<size_t>(q) * S.phi_stride;
+        double s = 0;
+        for (int i = lane; i < nf; i += 32) s += row[i] * v[i];
+        s = warp_sum(s);
+        if (lane == 0) S.tkc[q] = s;
+    }
+    for (int j = tid; j < ns; j += nth) {
+        const Sample& sp = S.smp[j];
+        double fv[3];
+        for (int cc = 0; cc < 3; ++cc) {
+            const double* vv = v + c.fbase[sp.ee] + cc * c.nfv[sp.ee] + sp.off;
+            double s = 0;
+            for (int i = 0; i < sp.cnt; ++i) s += sp.w[i] * vv[i];
+            fv[cc] = s;
+        }
+        double* o = out + 6 * j;
+        o[0] = fv[2];
+        o[1] = -fv[2];
+        o[2] = fv[0] - mu_f * fv[2];
+        o[3] = -fv[0] - mu_f * fv[2];
+        o[4] = fv[1] - mu_f * fv[2];
+        o[5] = -fv[1] - mu_f * fv[2];
+    }
+    __syncthreads();
+    for (int e = tid; e < ne; e += nth) {
+        const int cc = e & 1, foot = (e >> 1) & 3, kk = e >> 3, kf = kk * 4 + foot;
+        const double* vv = v + nf + c.pbase[foot] + cc * c.npv[foot] + S.poff[kf];
+        double s = -S.tkc[kk * 2 + cc];
+        for (int i = 0; i < S.pcnt[kf]; ++i) s += S.pw[2 * kf + i] * vv[i];
+        out[6 * ns + 2 * e] = s;
+        out[6 * ns + 2 * e + 1] = -s;
+    }
+    __syncthreads();
 }
 
-}  // namespace
+// out[0..nu) += C' y   (y: m-vector; inactive rows carry y == 0).  Every output entry is owned by one thread.
+static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double* y, double* out) {
+    const Smem& S = c.S;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int nu = c.nu, nf = c.nf, ns = c.ns, nkc = c.nkc;
+    const double mu_f = c.mu_f;
+    for (int q = tid; q < nkc; q += nth) {
+        const int kk = q >> 1, cc = q & 1;
+        double s = 0;
+        for (int foot = 0; foot < kNumEE; ++foot) {
+            const int e = (kk * 4 + foot) * 2 + cc;
+            s += y[6 * ns + 2 * e] - y[6 * ns + 2 * e + 1];
+        }
+        S.ckc[q] = -s;
+    }
+    __syncthreads();
+    // Two threads per column (nu <= 160 < blockDim / 2 ... else one): the first takes the dense foot-box rows (force
+    // column) or the first half of the nodes (position column), the second the sample rows / the second half; the
+    // loops run over the column's own sample / node range only (ColInfo, csrc/bgg_kkt.cuh).
+    {
+        const int half = (2 * nu <= nth) ? 2 : 1;
+        for (int base = 0; base < half * nu; base += nth) {   // whole warps iterate together: the partner exchange is a shuffle
+            const int it = base + tid;
+            const bool act = it < half * nu;
+            const int col = act ? it / half : 0, part = it % half;
+            const ColInfo ci = S.col[col];
+            double s = 0;
+            if (!act) {
+            } else if (col < nf) {
+                if (part == 0 || half == 1)
+                    for (int q = 0; q < nkc; ++q) s += S.ckc[q] * S.phi[static_cast<size_t>(q) * S.phi_stride + col];
+                if (part == 1 || half == 1)
+                    for (int j = ci.lo; j < ci.hi; ++j) {
+                        const Sample& sp = S.smp[j];
+                        const double* yy = y + 6 * j;
+                        double coef;
+                        if (ci.coord == 2) coef = (yy[0] - yy[1]) - mu_f * (yy[2] + yy[3] + yy[4] + yy[5]);
+                        else if (ci.coord == 0) coef = yy[2] - yy[3];
+                        else coef = yy[4] - yy[5];
+                        s += coef * sp.w[ci.var - sp.off];
+                    }
+            } else {
+                const int mid = (half == 2) ? (ci.lo + ci.hi + 1) / 2 : ci.hi;
+                const int k0 = (part == 0) ? ci.lo : mid, k1 = (part == 0) ? mid : ci.hi;
+                for (int kk = k0; kk < k1; ++kk) {
+                    const int kf = kk * 4 + ci.foot, e = kf * 2 + ci.coord;
+                    s += (y[6 * ns + 2 * e] - y[6 * ns + 2 * e + 1]) * S.pw[2 * kf + (ci.var - S.poff[kf])];
+                }
+            }
+            if (half == 2) s += __shfl_xor_sync(0xffffffffu, s, 1);   // partner thread: adjacent lane
+            if (act && part == 0) out[col] += s;
+        }
+    }
+    __syncthreads();
+}
+
+// out[0..nu) = H v, H full symmetric in HBM/L2, read column-wise (coalesced across threads)
+static __device__ __forceinline__ void ipm_apply_H(const IpmCtx& c, const double* v, double* out) {
+    const int tid = threadIdx.x, nth = blockDim.x, nu = c.nu;
+    const double* Hg = c.Hg;
+    for (int i = tid; i < nu; i += nth) {
+        double s = 0;
+        for (int j = 0; j < nu; ++j) s += Hg[static_cast<size_t>(j) * nu + i] * v[j];
+        out[i] = s;
+    }
+    __syncthreads();
+}
+
+// out = E v - e (or E v when with_rhs == false)
+static __device__ __forceinline__ void ipm_apply_E(const IpmCtx& c, const double* v, double* out, bool with_rhs) {
+    const int tid = threadIdx.x;
+    if (tid < c.neq) {
+        const EqRow& q = c.eq[tid];
+        double s = with_rhs ? -q.rhs : 0.0;
+        for (int i = 0; i < q.cnt; ++i) s += q.w[i] * v[q.col[i]];
+        out[tid] = s;
+    }
+    __syncthreads();
+}
+
+// out += scale E' y
+static __device__ __forceinline__ void ipm_add_Et(const IpmCtx& c, const double* y, double* out, double scale) {
+    const int tid = threadIdx.x;
+    if (tid < kNumEE * 2)   // one thread per (foot, coord): rows of different groups touch different columns
+        for (int r = 0; r < c.neq; ++r) {
+            const EqRow& q = c.eq[r];
+            if (q.pad != tid) continue;
+            for (int i = 0; i < q.cnt; ++i) out[q.col[i]] += scale * y[r] * q.w[i];
+        }
+    __syncthreads();
+}
 
 struct IpmCaps {          // per-launch shared-memory sizing, from the actual maxima over the batch
     int nu, rows, ns, stage_phi;
 };
 static size_t ipm_smem_core(int N, int nu, int rows, int ns) {
     const size_t kc = 2 * (N - 3), eb = 4 * (N - 3);
-    return 8 * (static_cast<size_t>(nu) * (nu + 1) / 2 + 6 * nu + 6 * static_cast<size_t>(rows) + 2 * eb * 2 + 2 * kc + 3 * kMaxEq + 40 + 2 * eb) +
+    return 8 * (chol::doubles(nu / 8) + 6 * nu + 6 * static_cast<size_t>(rows) + 2 * eb * 2 + 2 * kc + 3 * kMaxEq + 72 + 2 * eb) +
            8 * eb + sizeof(Sample) * static_cast<size_t>(ns) + sizeof(ColInfo) * static_cast<size_t>(nu) + 64;
 }
 static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max) {
@@ -102,10 +250,11 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     const double mu_f = P.friction_coef, delta = P.ipm_eq_delta, inv_delta = 1.0 / P.ipm_eq_delta;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    PROF_DECL
     Smem S;
     {
         double* p = reinterpret_cast<double*>(smem_raw);
-        S.K = p; p += cap_nu * (cap_nu + 1) / 2;
+        S.K = p; p += chol::doubles(cap_nu >> 3);
         S.u = p; p += cap_nu; S.du = p; p += cap_nu; S.rd = p; p += cap_nu;
         S.rhs = p; p += cap_nu; S.g = p; p += cap_nu; S.tmpn = p; p += cap_nu;
         S.s = p; p += cap_rows; S.lam = p; p += cap_rows; S.ds = p; p += cap_rows; S.dl = p; p += cap_rows;
@@ -113,7 +262,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         S.d = p; p += 2 * 8 * (N - 3);   // right-hand sides of the foot-box rows only (force rows: see rhs_of)
         S.tkc = p; p += nkc; S.ckc = p; p += nkc;
         S.nueq = p; p += kMaxEq; S.re = p; p += kMaxEq; S.dnu = p; p += kMaxEq;
-        S.red = p; p += 40;
+        S.red = p; p += 72;   // block_reduce scratch (33) / chol::solve scratch (64)
         S.pw = p; p += 2 * 4 * (N - 3);
         S.pcnt = reinterpret_cast<int*>(p);
         S.poff = S.pcnt + 4 * (N - 3);
@@ -143,8 +292,6 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     }
     __shared__ int s_fbase[kNumEE], s_pbase[kNumEE], s_nfv[kNumEE], s_npv[kNumEE];
     __shared__ int s_flag;
-    __shared__ double s_invd[16];   // reciprocals of the current diagonal block's pivots
-    __shared__ uint16_t s_tile[kTileTab];   // (ti << 8) | tl of the row-by-row enumeration of lower-triangle tiles
     __shared__ int s_sb[kNumEE + 1];   // per-foot sample ranges (samples are stored foot-major)
     __shared__ EqRow s_eq[kMaxEq];
     if (tid < neq) s_eq[tid] = eqs[tid];
@@ -155,6 +302,8 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         s_npv[tid] = Hd->npv[tid];
     }
     for (int i = tid; i < nu; i += nth) S.g[i] = gg[i];
+    for (int i = tid; i < 6 * cap_nu; i += nth)   // u du rd rhs g tmpn: the padding up to 8 nb stays zero (chol::solve)
+        if (i % cap_nu >= nu) S.u[i] = 0.0;
     if (tid == 0) {
         int e = 0;
         s_sb[0] = 0;
@@ -184,348 +333,43 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     auto rhs_of = [&](int i) -> double { return (i < m_force) ? ((i % 6 == 0) ? fbound : 0.0) : S.d[i - m_force]; };
     __syncthreads();
     kkt_build_colinfo(S.col, nu, nf, N, s_fbase, s_pbase, s_nfv, s_npv, s_sb, S.smp, S.pcnt, S.poff);
-    kkt_build_tile_table(s_tile, (nu + 3) >> 2);
     __syncthreads();
+    PROF(0);
 
     // ------------------------------------------------------------------------------------------------ operators
-    // out[0..m) = C v   (v: nu-vector in shared memory)
-    auto apply_C = [&](const double* v, double* out) {
-        for (int q = wid; q < nkc; q += nwarp) {     // dense position rows: one warp per (node, coord)
-            const double* row = S.phi + static_cast<size_t>(q) * S.phi_stride;
-            double s = 0;
-            for (int i = lane; i < nf; i += 32) s += row[i] * v[i];
-            s = warp_sum(s);
-            if (lane == 0) S.tkc[q] = s;
-        }
-        for (int j = tid; j < ns; j += nth) {
-            const Sample& sp = S.smp[j];
-            double fv[3];
-            for (int c = 0; c < 3; ++c) {
-                const double* vv = v + s_fbase[sp.ee] + c * s_nfv[sp.ee] + sp.off;
-                double s = 0;
-                for (int i = 0; i < sp.cnt; ++i) s += sp.w[i] * vv[i];
-                fv[c] = s;
-            }
-            double* o = out + 6 * j;
-            o[0] = fv[2];
-            o[1] = -fv[2];
-            o[2] = fv[0] - mu_f * fv[2];
-            o[3] = -fv[0] - mu_f * fv[2];
-            o[4] = fv[1] - mu_f * fv[2];
-            o[5] = -fv[1] - mu_f * fv[2];
-        }
-        __syncthreads();
-        for (int e = tid; e < ne; e += nth) {
-            const int c = e & 1, foot = (e >> 1) & 3, kk = e >> 3, kf = kk * 4 + foot;
-            const double* vv = v + nf + s_pbase[foot] + c * s_npv[foot] + S.poff[kf];
-            double s = -S.tkc[kk * 2 + c];
-            for (int i = 0; i < S.pcnt[kf]; ++i) s += S.pw[2 * kf + i] * vv[i];
-            out[6 * ns + 2 * e] = s;
-            out[6 * ns + 2 * e + 1] = -s;
-        }
-        __syncthreads();
-    };
-    // out[0..nu) += C' y   (y: m-vector; inactive rows carry y == 0).  Every output entry is owned by one thread.
-    auto add_Ct = [&](const double* y, double* out) {
-        for (int q = tid; q < nkc; q += nth) {
-            const int kk = q >> 1, c = q & 1;
-            double s = 0;
-            for (int foot = 0; foot < kNumEE; ++foot) {
-                const int e = (kk * 4 + foot) * 2 + c;
-                s += y[6 * ns + 2 * e] - y[6 * ns + 2 * e + 1];
-            }
-            S.ckc[q] = -s;
-        }
-        __syncthreads();
-        // Two threads per column (nu <= 160 < blockDim / 2 ... else one): the first takes the dense foot-box rows (force
-        // column) or the first half of the nodes (position column), the second the sample rows / the second half; the
-        // loops run over the column's own sample / node range only (ColInfo, csrc/bgg_kkt.cuh).
-        {
-            const int half = (2 * nu <= nth) ? 2 : 1;
-            for (int base = 0; base < half * nu; base += nth) {   // whole warps iterate together: the partner exchange is a shuffle
-                const int it = base + tid;
-                const bool act = it < half * nu;
-                const int col = act ? it / half : 0, part = it % half;
-                const ColInfo ci = S.col[col];
-                double s = 0;
-                if (!act) {
-                } else if (col < nf) {
-                    if (part == 0 || half == 1)
-                        for (int q = 0; q < nkc; ++q) s += S.ckc[q] * S.phi[static_cast<size_t>(q) * S.phi_stride + col];
-                    if (part == 1 || half == 1)
-                        for (int j = ci.lo; j < ci.hi; ++j) {
-                            const Sample& sp = S.smp[j];
-                            const double* yy = y + 6 * j;
-                            double coef;
-                            if (ci.coord == 2) coef = (yy[0] - yy[1]) - mu_f * (yy[2] + yy[3] + yy[4] + yy[5]);
-                            else if (ci.coord == 0) coef = yy[2] - yy[3];
-                            else coef = yy[4] - yy[5];
-                            s += coef * sp.w[ci.var - sp.off];
-                        }
-                } else {
-                    const int mid = (half == 2) ? (ci.lo + ci.hi + 1) / 2 : ci.hi;
-                    const int k0 = (part == 0) ? ci.lo : mid, k1 = (part == 0) ? mid : ci.hi;
-                    for (int kk = k0; kk < k1; ++kk) {
-                        const int kf = kk * 4 + ci.foot, e = kf * 2 + ci.coord;
-                        s += (y[6 * ns + 2 * e] - y[6 * ns + 2 * e + 1]) * S.pw[2 * kf + (ci.var - S.poff[kf])];
-                    }
-                }
-                if (half == 2) s += __shfl_xor_sync(0xffffffffu, s, 1);   // partner thread: adjacent lane
-                if (act && part == 0) out[col] += s;
-            }
-        }
-        __syncthreads();
-    };
-    // out[0..nu) = H v, H full symmetric in HBM/L2, read column-wise (coalesced across threads)
-    auto apply_H = [&](const double* v, double* out) {
-        for (int i = tid; i < nu; i += nth) {
-            double s = 0;
-            for (int j = 0; j < nu; ++j) s += Hg[static_cast<size_t>(j) * nu + i] * v[j];
-            out[i] = s;
-        }
-        __syncthreads();
-    };
-    // re = E v - e (or E v when rhs == false) ; out += E' y
-    auto apply_E = [&](const double* v, double* out, bool with_rhs) {
-        if (tid < neq) {
-            const EqRow& q = s_eq[tid];
-            double s = with_rhs ? -q.rhs : 0.0;
-            for (int i = 0; i < q.cnt; ++i) s += q.w[i] * v[q.col[i]];
-            out[tid] = s;
-        }
-        __syncthreads();
-    };
-    auto add_Et = [&](const double* y, double* out, double scale) {
-        if (tid < kNumEE * 2)   // one thread per (foot, coord): rows of different groups touch different columns
-            for (int r = 0; r < neq; ++r) {
-                const EqRow& q = s_eq[r];
-                if (q.pad != tid) continue;
-                for (int i = 0; i < q.cnt; ++i) out[q.col[i]] += scale * y[r] * q.w[i];
-            }
-        __syncthreads();
-    };
+    IpmCtx ctx;
+    ctx.S = S; ctx.Hg = Hg; ctx.eq = s_eq; ctx.fbase = s_fbase; ctx.pbase = s_pbase; ctx.nfv = s_nfv; ctx.npv = s_npv;
+    ctx.N = N; ctx.nu = nu; ctx.nf = nf; ctx.ns = ns; ctx.ne = ne; ctx.neq = neq; ctx.nkc = nkc; ctx.mu_f = mu_f;
+    auto apply_C = [&](const double* v, double* out) { PROF(10); ipm_apply_C(ctx, v, out); PROF(6); };
+    auto add_Ct = [&](const double* y, double* out) { PROF(10); ipm_add_Ct(ctx, y, out); PROF(7); };
+    auto apply_H = [&](const double* v, double* out) { PROF(10); ipm_apply_H(ctx, v, out); PROF(8); };
+    auto apply_E = [&](const double* v, double* out, bool with_rhs) { PROF(10); ipm_apply_E(ctx, v, out, with_rhs); PROF(9); };
+    auto add_Et = [&](const double* y, double* out, double scale) { PROF(10); ipm_add_Et(ctx, y, out, scale); PROF(9); };
 
     // K = H + C' diag(wv) C + E'E/delta (packed lower triangle in shared memory, csrc/bgg_kkt.cuh), then in-place Cholesky.
     KktView kv;
     kv.K = S.K; kv.ld = 0; kv.Hg = Hg; kv.nu = nu; kv.nf = nf; kv.N = N; kv.ns = ns; kv.ne = ne; kv.neq = neq; kv.nkc = nkc;
     kv.wv = S.wv; kv.phi = S.phi; kv.phi_stride = S.phi_stride; kv.pw = S.pw; kv.pcnt = S.pcnt; kv.poff = S.poff;
-    kv.smp = S.smp; kv.eq = s_eq; kv.col = S.col; kv.ckc = S.ckc; kv.mu_f = mu_f; kv.inv_delta = inv_delta; kv.sign = 1.0; kv.tile = s_tile;
+    kv.smp = S.smp; kv.eq = s_eq; kv.col = S.col; kv.ckc = S.ckc; kv.mu_f = mu_f; kv.inv_delta = inv_delta; kv.sign = 1.0; kv.tile = nullptr;
+    const int nb = (nu + 7) >> 3;   // 8 x 8 blocks per side; rows nu .. 8 nb - 1 are padded with the identity
     auto build_and_factor = [&]() -> bool {
+        PROF(10);
         kkt_assemble<true>(kv, s_fbase, s_nfv);
-        // Blocked right-looking Cholesky on the packed lower triangle, NB-column panels, two barriers per panel:
-        //   (1) warp 0 factors the NB x NB diagonal block in registers (lane r owns row r, shuffles down the columns);
-        //   (2) every row below the block solves against it (one thread per row, the block read from shared memory);
-        //   (3) rank-NB trailing update in 4 x 4 register tiles.
-        // Look-ahead: inside (3) warp 0 takes the tiles of the NEXT diagonal block first and factors it while the
-        // other seven warps finish the trailing update, so the serial step (1) is off the critical path.
-        if (tid == 0) s_flag = 0;
-        constexpr int NB = 8;
-        auto factor_diag = [&](int b0) {   // warp 0 only; lane 0 holds the whole NB x NB triangle in registers: no shuffles on
-            if (lane != 0) return;         // the serial path, the independent updates of a step overlap its rsqrt chain
-            const int bs = (nu - b0 < NB) ? nu - b0 : NB;
-            double a[NB][NB];
-#pragma unroll
-            for (int r = 0; r < NB; ++r)
-#pragma unroll
-                for (int c = 0; c <= r; ++c) a[r][c] = (r < bs) ? S.K[pk(b0 + r, b0 + c)] : ((r == c) ? 1.0 : 0.0);
-            bool bad_any = false;
-#pragma unroll
-            for (int c = 0; c < NB; ++c) {
-                const double d = a[c][c];
-                const bool bad = !(d > 0.0);
-                bad_any |= bad;
-                const double inv = bad ? 1.0 : fast_rsqrt(d);
-                a[c][c] = d * inv;
-                s_invd[c] = inv;
-#pragma unroll
-                for (int r = c + 1; r < NB; ++r) a[r][c] *= inv;
-#pragma unroll
-                for (int c2 = c + 1; c2 < NB; ++c2)
-#pragma unroll
-                    for (int r = c2; r < NB; ++r) a[r][c2] -= a[r][c] * a[c2][c];
-            }
-            if (bad_any) s_flag = 1;
-#pragma unroll
-            for (int r = 0; r < NB; ++r)
-#pragma unroll
-                for (int c = 0; c <= r; ++c)
-                    if (r < bs) S.K[pk(b0 + r, b0 + c)] = a[r][c];
-        };
-        __syncthreads();
-        if (wid == 0) factor_diag(0);
-        __syncthreads();
-        for (int b0 = 0; b0 < nu; b0 += NB) {
-            const int bs = (nu - b0 < NB) ? nu - b0 : NB;
-            const int t0 = b0 + bs;
-            if (t0 >= nu) break;
-            // (2) rows below the block: row i solves L[i, b] = A[i, b] L_bb^-T, right-looking so the updates are independent
-            for (int i = t0 + tid; i < nu; i += nth) {
-                double* Li = S.K + pk(i, b0);
-                double row[NB];
-#pragma unroll
-                for (int c = 0; c < NB; ++c) row[c] = (c < bs) ? Li[c] : 0.0;
-#pragma unroll
-                for (int c = 0; c < NB; ++c) {
-                    if (c < bs) {
-                        row[c] *= s_invd[c];
-#pragma unroll
-                        for (int c2 = c + 1; c2 < NB; ++c2)
-                            if (c2 < bs) row[c2] -= row[c] * S.K[pk(b0 + c2, b0 + c)];
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < NB; ++c)
-                    if (c < bs) Li[c] = row[c];
-            }
-            __syncthreads();
-            // (3) trailing update A[i][l] -= sum_c L[i][b0+c] L[l][b0+c], 4 x 4 tiles over the lower triangle of the trailing block
-            const int side = (nu - t0 + 3) >> 2;
-            constexpr int LR = NB / 4;   // tile rows of the next diagonal block; they come first in the row-by-row enumeration
-            const int look = (side < LR) ? side * (side + 1) / 2 : LR * (LR + 1) / 2;
-            const int ntile = side * (side + 1) / 2;
-            auto do_tile = [&](int t) {
-                const int ti = s_tile[t] >> 8, tl = s_tile[t] & 255;
-                const int i0 = t0 + 4 * ti, l0 = t0 + 4 * tl;
-                double acc[4][4];
-#pragma unroll
-                for (int a2 = 0; a2 < 4; ++a2)
-#pragma unroll
-                    for (int c2 = 0; c2 < 4; ++c2) acc[a2][c2] = 0.0;
-#pragma unroll
-                for (int h = 0; h < NB; h += 4) {
-                    double ra[4][4], rc[4][4];
-#pragma unroll
-                    for (int a2 = 0; a2 < 4; ++a2) {
-                        const int ii = (i0 + a2 < nu) ? i0 + a2 : nu - 1, ll = (l0 + a2 < nu) ? l0 + a2 : nu - 1;
-                        const double* pa = S.K + pk(ii, b0 + h);
-                        const double* pc = S.K + pk(ll, b0 + h);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            ra[a2][k] = (h + k < bs) ? pa[k] : 0.0;
-                            rc[a2][k] = (h + k < bs) ? pc[k] : 0.0;
-                        }
-                    }
-#pragma unroll
-                    for (int a2 = 0; a2 < 4; ++a2)
-#pragma unroll
-                        for (int c2 = 0; c2 < 4; ++c2)
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) acc[a2][c2] += ra[a2][k] * rc[c2][k];
-                }
-#pragma unroll
-                for (int a2 = 0; a2 < 4; ++a2) {
-                    const int ii = i0 + a2;
-                    if (ii >= nu) continue;
-                    double* Ki = S.K + ii * (ii + 1) / 2;
-#pragma unroll
-                    for (int c2 = 0; c2 < 4; ++c2) {
-                        const int ll = l0 + c2;
-                        if (ll <= ii) Ki[ll] -= acc[a2][c2];
-                    }
-                }
-            };
-            if (wid == 0) {
-                // next diagonal block, one lane per entry (36 entries of the 8 x 8 lower triangle): short dependent chains
-                // instead of three whole tiles on three lanes
-                for (int e = lane; e < NB * (NB + 1) / 2; e += 32) {
-                    int r = 0;
-                    while ((r + 1) * (r + 2) / 2 <= e) ++r;
-                    const int c = e - r * (r + 1) / 2;
-                    const int i = t0 + r, l = t0 + c;
-                    if (i < nu) {
-                        const double* pa = S.K + pk(i, b0);
-                        const double* pc = S.K + pk(l, b0);
-                        double acc = 0.0;
-#pragma unroll
-                        for (int h = 0; h < NB; ++h)
-                            if (h < bs) acc += pa[h] * pc[h];
-                        S.K[pk(i, l)] -= acc;
-                    }
-                }
-                __syncwarp();
-                factor_diag(t0);
-            } else {
-                for (int t = look + tid - 32; t < ntile; t += nth - 32) do_tile(t);
-            }
-            __syncthreads();
-        }
-        // Invert the 16 x 16 diagonal blocks of the factor in place (they are only ever used through their inverse by
-        // the blocked substitutions below): half a warp per block, lane = column.
-        constexpr int SB = 16;
-        const int nblk = (nu + SB - 1) / SB;
-        for (int bb = wid; bb < nblk; bb += nwarp) {
-            const int r0 = bb * SB, bsz = (nu - r0 < SB) ? nu - r0 : SB;
-            double x[SB];
-            if (lane < bsz) {
-#pragma unroll
-                for (int rr = 0; rr < SB; ++rr) {
-                    x[rr] = 0.0;
-                    if (rr < bsz && rr >= lane) {
-                        const double* Lr = S.K + pk(r0 + rr, r0);
-                        double acc = (rr == lane) ? 1.0 : 0.0;
-#pragma unroll
-                        for (int k = 0; k < SB; ++k)
-                            if (k < rr && k >= lane) acc -= Lr[k] * x[k];
-                        x[rr] = acc / Lr[rr];
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane < bsz) {
-#pragma unroll
-                for (int rr = 0; rr < SB; ++rr)
-                    if (rr < bsz && rr >= lane) S.K[pk(r0 + rr, r0 + lane)] = x[rr];
-            }
+        for (int idx = tid; idx < (8 * nb - nu) * 8 * nb; idx += nth) {
+            const int i = nu + idx / (8 * nb), j = idx % (8 * nb);
+            if (j <= i) S.K[chol::at(i, j)] = (i == j) ? 1.0 : 0.0;
         }
         __syncthreads();
+        PROF(1);
+        chol::factor(S.K, nb, &s_flag);   // csrc/bgg_chol.cuh: DMMA block Cholesky, diagonal super-blocks inverted
+        PROF(3);
         return s_flag == 0;
     };
-    // Solve K x = v in place with the packed factor whose 16 x 16 diagonal blocks hold their inverses: blocked forward
-    // and backward substitution, 16 rows x 16 threads per block step, half-warp shuffle reductions.
-    auto red16 = [](double v) {
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        return v;
-    };
+    // Solve K x = v in place (v padded with zeros to 8 nb entries)
     auto chol_solve = [&](double* v) {
-        constexpr int SB = 16;
-        const int nblk = (nu + SB - 1) / SB;
-        const int r = tid >> 4, sx = tid & 15;
-        double* tb = S.red;   // 16 doubles of scratch (block_reduce is not running concurrently)
-        __syncthreads();
-        for (int bb = 0; bb < nblk; ++bb) {   // L y = v
-            const int i = bb * SB + r;
-            double acc = 0;
-            if (i < nu) {
-                const double* Li = S.K + i * (i + 1) / 2;
-                for (int j = sx; j < bb * SB; j += 16) acc += Li[j] * v[j];
-            }
-            acc = red16(acc);
-            if (sx == 0 && i < nu) tb[r] = v[i] - acc;
-            __syncthreads();
-            double y = 0;
-            if (i < nu && sx <= r) y = S.K[pk(i, bb * SB + sx)] * tb[sx];
-            y = red16(y);
-            if (sx == 0 && i < nu) v[i] = y;
-            __syncthreads();
-        }
-        for (int bb = nblk - 1; bb >= 0; --bb) {   // L' x = y
-            const int i = bb * SB + r;
-            double acc = 0;
-            if (i < nu)
-                for (int j = (bb + 1) * SB + sx; j < nu; j += 16) acc += S.K[pk(j, i)] * v[j];
-            acc = red16(acc);
-            if (sx == 0 && i < nu) tb[r] = v[i] - acc;
-            __syncthreads();
-            double y = 0;
-            const int jj = bb * SB + sx;
-            if (i < nu && jj < nu && sx >= r) y = S.K[pk(jj, i)] * tb[sx];   // X' : entry (r, sx) = X[sx][r]
-            y = red16(y);
-            if (sx == 0 && i < nu) v[i] = y;
-            __syncthreads();
-        }
+        PROF(10);
+        chol::solve(S.K, nb, v, S.red);
+        PROF(5);
     };
 
     // ------------------------------------------------------------------------------------------------ start point
@@ -773,6 +617,8 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         so[i] = (S.lam[i] > 0.0 || S.s[i] != 1.0) ? S.s[i] : rhs_of(i);   // inactive rows: slack = d (row is 0 <= d)
     }
     if (tid < neq) no[tid] = S.nueq[tid];
+    PROF(10);
+    PROF_DUMP;
     if (tid == 0) {
         Hd->status = status;
         Hd->iters = it;
@@ -797,3 +643,13 @@ void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max,
 }
 
 }  // namespace bgg
+
+#ifdef BGG_IPM_PROF
+extern "C" int bgg_debug_ipm_prof(long long* out32) {
+    int rc = static_cast<int>(cudaMemcpyFromSymbol(out32, bgg::g_ipm_prof, 16 * sizeof(long long)));
+    if (rc == 0) rc = static_cast<int>(cudaMemcpyFromSymbol(out32 + 16, bgg::chol::g_chol_prof, 16 * sizeof(long long)));
+    const long long zero[16] = {0};
+    cudaMemcpyToSymbol(bgg::chol::g_chol_prof, zero, sizeof(zero));
+    return rc;
+}
+#endif

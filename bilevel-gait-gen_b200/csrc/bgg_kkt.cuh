@@ -11,6 +11,7 @@
 //   pos   x pos   : H + sum_k om pw pw  +  touch-down / foot-start rows / delta          (same foot and coordinate only)
 // Row order of w: see csrc/bgg_ipm.cu.
 #pragma once
+#include "bgg_chol.cuh"
 #include "bgg_kernels.cuh"
 
 namespace bgg {
@@ -22,7 +23,7 @@ struct ColInfo {      // per spline variable: which foot / coordinate / local in
 };
 
 struct KktView {
-    double* K;                 // output: packed lower triangle (PACKED) or dense row-major with leading dimension ld
+    double* K;                 // output: lower triangle in 8 x 8 blocks (PACKED, csrc/bgg_chol.cuh) or dense row-major with leading dimension ld
     int ld;
     const double* Hg;          // condensed Hessian, full symmetric nu x nu in HBM / L2
     int nu, nf, N, ns, ne, neq, nkc;
@@ -100,7 +101,7 @@ __device__ inline void kkt_build_colinfo(ColInfo* col, int nu, int nf, int N, co
 
 template <bool PACKED>
 __device__ __forceinline__ double& kkt_at(const KktView& v, int i, int j) {
-    return PACKED ? v.K[i * (i + 1) / 2 + j] : v.K[static_cast<size_t>(i) * v.ld + j];
+    return PACKED ? v.K[chol::at(i, j)] : v.K[static_cast<size_t>(i) * v.ld + j];
 }
 
 // Every thread of the CTA must call this; it ends with a barrier.  Only the lower triangle (j <= i) is written.
