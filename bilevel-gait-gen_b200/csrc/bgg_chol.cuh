@@ -37,6 +37,10 @@ __device__ __forceinline__ int at(int i, int j) { return blk(i >> 3, j >> 3) + (
 __host__ __device__ inline size_t doubles(int nb) { return static_cast<size_t>(nb) * (nb + 1) / 2 * 64; }
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+#ifdef BGG_NO_DMMA   // timing experiment only (wrong results): one DFMA instead of the tensor-core instruction
+    c0 = fma(a, b, c0);
+    return;
+#endif
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 // entries [g][2t], [g][2t+1] of a row-major 8 x 8 block

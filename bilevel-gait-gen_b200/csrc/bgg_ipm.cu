@@ -16,6 +16,7 @@
 #include "bgg_kernels.cuh"
 #include "bgg_chol.cuh"
 #include "bgg_kkt.cuh"
+#include "bgg_kkt_mma.cuh"
 
 namespace bgg {
 
@@ -211,6 +212,9 @@ static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max) {
     if (c.nu > L.max_nu) c.nu = L.max_nu;
     c.ns = ns_max < 1 ? 1 : ns_max;
     c.rows = 6 * c.ns + 2 * (L.N - 3) * 8;
+    // the KKT assembly stages phi chunks and a per-sample table in the ds / dl vectors (csrc/bgg_kkt_mma.cuh)
+    const int scratch = kkt_scratch_doubles(c.nu / 8, c.ns);
+    if (2 * c.rows < scratch) c.rows = (scratch + 1) / 2;
     const size_t core = ipm_smem_core(L.N, c.nu, c.rows, c.ns);
     const size_t phi = 8 * static_cast<size_t>(2 * (L.N - 3)) * c.nu;
     // two CTAs per SM when the core fits twice into the 227 KB; the dense position rows are staged on chip only
@@ -291,7 +295,8 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         S.pw[2 * i + 1] = nl.pw[foot][1];
     }
     __shared__ int s_fbase[kNumEE], s_pbase[kNumEE], s_nfv[kNumEE], s_npv[kNumEE];
-    __shared__ int s_flag;
+    __shared__ int s_flag, s_nitems, s_nwork;
+    __shared__ KktWork s_work[kMaxKktWork];
     __shared__ int s_sb[kNumEE + 1];   // per-foot sample ranges (samples are stored foot-major)
     __shared__ EqRow s_eq[kMaxEq];
     if (tid < neq) s_eq[tid] = eqs[tid];
@@ -334,6 +339,13 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     __syncthreads();
     kkt_build_colinfo(S.col, nu, nf, N, s_fbase, s_pbase, s_nfv, s_npv, s_sb, S.smp, S.pcnt, S.poff);
     __syncthreads();
+    KktItem* kitems = reinterpret_cast<KktItem*>(ws + L.ktab);
+    kkt_mma_setup(s_work, &s_nwork, (nu + 7) >> 3, kitems, &s_nitems, s_fbase, s_nfv, S.col, S.smp);
+    if (s_nitems > kMaxKktItems) {   // cannot happen within max_spline_vars = 160; refuse rather than drop terms
+        if (tid == 0) Hd->status = kOther;
+        return;
+    }
+    __syncthreads();
     PROF(0);
 
     // ------------------------------------------------------------------------------------------------ operators
@@ -346,20 +358,16 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     auto apply_E = [&](const double* v, double* out, bool with_rhs) { PROF(10); ipm_apply_E(ctx, v, out, with_rhs); PROF(9); };
     auto add_Et = [&](const double* y, double* out, double scale) { PROF(10); ipm_add_Et(ctx, y, out, scale); PROF(9); };
 
-    // K = H + C' diag(wv) C + E'E/delta (packed lower triangle in shared memory, csrc/bgg_kkt.cuh), then in-place Cholesky.
-    KktView kv;
-    kv.K = S.K; kv.ld = 0; kv.Hg = Hg; kv.nu = nu; kv.nf = nf; kv.N = N; kv.ns = ns; kv.ne = ne; kv.neq = neq; kv.nkc = nkc;
-    kv.wv = S.wv; kv.phi = S.phi; kv.phi_stride = S.phi_stride; kv.pw = S.pw; kv.pcnt = S.pcnt; kv.poff = S.poff;
-    kv.smp = S.smp; kv.eq = s_eq; kv.col = S.col; kv.ckc = S.ckc; kv.mu_f = mu_f; kv.inv_delta = inv_delta; kv.sign = 1.0; kv.tile = nullptr;
+    // K = H + C' diag(wv) C + E'E/delta in 8 x 8 blocks in shared memory (csrc/bgg_kkt_mma.cuh), then chol::factor in place.
     const int nb = (nu + 7) >> 3;   // 8 x 8 blocks per side; rows nu .. 8 nb - 1 are padded with the identity
+    KktMma km;
+    km.K = S.K; km.Hg = Hg; km.phig = phipos; km.phi_ld = L.max_nu; km.nu = nu; km.nf = nf; km.nb = nb; km.ns = ns; km.ne = ne;
+    km.neq = neq; km.nkc = nkc; km.wv = S.wv; km.pw = S.pw; km.pcnt = S.pcnt; km.poff = S.poff; km.smp = S.smp; km.eq = s_eq;
+    km.col = S.col; km.ckc = S.ckc; km.scratch = S.ds; km.work = s_work; km.nwork = s_nwork; km.items = kitems; km.nitems = s_nitems;
+    km.mu_f = mu_f; km.inv_delta = inv_delta;
     auto build_and_factor = [&]() -> bool {
         PROF(10);
-        kkt_assemble<true>(kv, s_fbase, s_nfv);
-        for (int idx = tid; idx < (8 * nb - nu) * 8 * nb; idx += nth) {
-            const int i = nu + idx / (8 * nb), j = idx % (8 * nb);
-            if (j <= i) S.K[chol::at(i, j)] = (i == j) ? 1.0 : 0.0;
-        }
-        __syncthreads();
+        kkt_assemble_mma(km);   // csrc/bgg_kkt_mma.cuh (also writes the identity padding)
         PROF(1);
         chol::factor(S.K, nb, &s_flag);   // csrc/bgg_chol.cuh: DMMA block Cholesky, diagonal super-blocks inverted
         PROF(3);
@@ -648,7 +656,9 @@ void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max,
 extern "C" int bgg_debug_ipm_prof(long long* out32) {
     int rc = static_cast<int>(cudaMemcpyFromSymbol(out32, bgg::g_ipm_prof, 16 * sizeof(long long)));
     if (rc == 0) rc = static_cast<int>(cudaMemcpyFromSymbol(out32 + 16, bgg::chol::g_chol_prof, 16 * sizeof(long long)));
+    if (rc == 0) rc = static_cast<int>(cudaMemcpyFromSymbol(out32 + 24, bgg::g_kkt_prof, 8 * sizeof(long long)));
     const long long zero[16] = {0};
+    cudaMemcpyToSymbol(bgg::g_kkt_prof, zero, 8 * sizeof(long long));
     cudaMemcpyToSymbol(bgg::chol::g_chol_prof, zero, sizeof(zero));
     return rc;
 }

@@ -112,9 +112,19 @@ __device__ __forceinline__ double& kkt_at(const KktView& v, int i, int j) {
 //   2. force-sample rows: one work item per (foot, coordinate pair, knot pair, value/derivative pair) -- the only K
 //      entries two samples can share belong to the same or to neighbouring knots -- summing over the few samples
 //      that contain both variables.
+#ifdef BGG_IPM_PROF
+static __device__ long long g_kkt_prof[8];
+#define KPROF(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_kkt_prof[k] += t_ - kprof_t; kprof_t = t_; } } while (0)
+#else
+#define KPROF(k) do { } while (0)
+#endif
+
 template <bool PACKED>
 __device__ void kkt_assemble(const KktView& v, const int* fbase, const int* nfv) {
     const int tid = threadIdx.x, nth = blockDim.x, wid = tid >> 5;
+#ifdef BGG_IPM_PROF
+    long long kprof_t = clock64();
+#endif
     const int nu = v.nu, nf = v.nf, np = nu - nf, m_force = 6 * v.ns;
     for (int q = tid; q < v.nkc; q += nth) {   // weight of the dense (node, coord) row pair, summed over the feet
         const int kk = q >> 1, c = q & 1;
@@ -170,6 +180,7 @@ __device__ void kkt_assemble(const KktView& v, const int* fbase, const int* nfv)
                 if (i < nf && j <= i) kkt_at<PACKED>(v, i, j) = acc[a][b];
             }
     }
+    KPROF(0);
     {
         // position rows: the warps that did not get a tile in the last (partial) round start here right away
         const int rem = ntile % nth;
@@ -210,7 +221,9 @@ __device__ void kkt_assemble(const KktView& v, const int* fbase, const int* nfv)
                 kkt_at<PACKED>(v, i, j) = v.Hg[static_cast<size_t>(i) * nu + j] + v.sign * term + v.inv_delta * eq;
             }
     }
+    KPROF(1);
     __syncthreads();
+    KPROF(2);
     // force-sample rows
     int ib[kNumEE + 1];
     ib[0] = 0;
@@ -244,7 +257,9 @@ __device__ void kkt_assemble(const KktView& v, const int* fbase, const int* nfv)
         }
         if (hi > lo) kkt_at<PACKED>(v, row, colj) += v.sign * acc;
     }
+    KPROF(3);
     __syncthreads();
+    KPROF(4);
 }
 
 }  // namespace bgg

@@ -72,6 +72,7 @@ struct WsLayout {             // byte offsets inside one instance's workspace
     size_t stride;
     size_t hdr, nodes, samples, eq, zprev, H, g, phipos, xoff, u, lam, slack, nueq, zqp, dualx;
     size_t gdx, gdz, gdlam, gdnu, gdnue, gdH, ginfo;   // gait-gradient outputs (csrc/bgg_gradient.cu)
+    size_t ktab;                                       // item table of the KKT assembly (csrc/bgg_kkt_mma.cuh)
     int32_t N, max_nu, max_rows, pad;
 };
 
@@ -105,6 +106,7 @@ inline WsLayout make_layout(int N, int max_nu) {
     L.gdnue = take(8 * kMaxEq);                                       // dnu of the touch-down / foot-start rows
     L.gdH = take(8 * kNumEE * kMaxContacts);                          // dH/dtheta, foot-major
     L.ginfo = take(sizeof(GradInfo));
+    L.ktab = take(12 * 1536);                                         // kMaxKktItems x sizeof(KktItem)
     L.stride = o;
     return L;
 }

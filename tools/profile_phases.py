@@ -39,3 +39,6 @@ for B in [int(x) for x in os.environ.get("BS", "1,296,4096").split(",")]:
     nfac = 2 * (it + 1)   # two solves were run; the counters accumulate over both
     for k in range(6):
         print(f"    chol::factor {CN[k]:36s} {p[16 + k] / nfac:9.0f} cyc per factorisation")
+    KN = ["tables", "dense part (kkt_dense_mma)", "-", "position x position", "force-sample items + barrier", "  dense: H blocks + first chunk staged", "  dense: chunk loop", "-"]
+    for k in range(8):
+        print(f"    kkt_assemble {KN[k]:36s} {p[24 + k] / nfac:9.0f} cyc per assembly")
