@@ -202,6 +202,8 @@ __device__ __forceinline__ bool factor_invert_diag_v0(double* D, int lane) {
 // On exit: blocks outside the 64 x 64 diagonal super-blocks hold L, the super-blocks hold the inverse of L's.
 // *flag (shared) is set to 1 when a pivot was not positive.  Ends with a barrier.
 static __device__ __noinline__ void factor(double* K, int nb, int* flag) {
+    __builtin_assume(__isShared(K));
+    __builtin_assume(__isShared(flag));
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
     if (tid == 0) *flag = 0;
     __syncthreads();
@@ -302,6 +304,9 @@ static __device__ __noinline__ void factor(double* K, int nb, int* flag) {
 // dependent steps of two phases: (a) y_s = X_ss v_s, one warp per block row, the up to eight block fragments and
 // vector pieces loaded before the first FMA; (b) the rows below take L(i, s) y_s.  Starts and ends with a barrier.
 static __device__ __noinline__ void solve(const double* K, int nb, double* v, double* ys) {
+    __builtin_assume(__isShared(K));
+    __builtin_assume(__isShared(v));
+    __builtin_assume(__isShared(ys));
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int nsup = (nb + 7) >> 3;

@@ -52,9 +52,10 @@ struct Smem {
 
 }  // namespace
 
-// What the operators below need.  They are force-inlined: measured on B200, calling them as __noinline__ functions
-// (one copy in the binary, 330 KB of SASS instead of 540 KB) was 20 % slower with the context passed by reference
-// (fields re-read from local memory after every store) and 80 % slower with it passed by value.
+// What the operators below need.  They are force-inlined.  Measured on B200 (4096 solves): inlined 37.2 ms; as
+// __noinline__ functions (one copy of each in the binary: ncu shows the 0.4 MB kernel stalling on instruction fetch) with
+// the context by reference and every field copied to locals 41.1 ms, the same plus __isShared assumptions 39.2 ms,
+// context by value 83 ms -- the call boundary costs more than the instruction-cache misses it saves.
 struct IpmCtx {
     Smem S;
     const double* Hg;
@@ -66,7 +67,12 @@ struct IpmCtx {
 
 // out[0..m) = C v   (v: nu-vector in shared memory)
 static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double* v, double* out) {
-    const Smem& S = c.S;
+    const Smem S = c.S;
+    const int *fbase = c.fbase, *pbase = c.pbase, *nfv = c.nfv, *npv = c.npv;
+    __builtin_assume(__isShared(v)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(S.tkc));
+    __builtin_assume(__isShared(S.smp)); __builtin_assume(__isShared(S.pw)); __builtin_assume(__isShared(S.pcnt));
+    __builtin_assume(__isShared(S.poff)); __builtin_assume(__isShared(fbase)); __builtin_assume(__isShared(pbase));
+    __builtin_assume(__isShared(nfv)); __builtin_assume(__isShared(npv));
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
     const int nf = c.nf, ns = c.ns, ne = c.ne, nkc = c.nkc;
     const double mu_f = c.mu_f;
@@ -81,7 +87,7 @@ static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double
         const Sample& sp = S.smp[j];
         double fv[3];
         for (int cc = 0; cc < 3; ++cc) {
-            const double* vv = v + c.fbase[sp.ee] + cc * c.nfv[sp.ee] + sp.off;
+            const double* vv = v + fbase[sp.ee] + cc * nfv[sp.ee] + sp.off;
             double s = 0;
             for (int i = 0; i < sp.cnt; ++i) s += sp.w[i] * vv[i];
             fv[cc] = s;
@@ -97,7 +103,7 @@ static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double
     __syncthreads();
     for (int e = tid; e < ne; e += nth) {
         const int cc = e & 1, foot = (e >> 1) & 3, kk = e >> 3, kf = kk * 4 + foot;
-        const double* vv = v + nf + c.pbase[foot] + cc * c.npv[foot] + S.poff[kf];
+        const double* vv = v + nf + pbase[foot] + cc * npv[foot] + S.poff[kf];
         double s = -S.tkc[kk * 2 + cc];
         for (int i = 0; i < S.pcnt[kf]; ++i) s += S.pw[2 * kf + i] * vv[i];
         out[6 * ns + 2 * e] = s;
@@ -108,7 +114,10 @@ static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double
 
 // out[0..nu) += C' y   (y: m-vector; inactive rows carry y == 0).  Every output entry is owned by one thread.
 static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double* y, double* out) {
-    const Smem& S = c.S;
+    const Smem S = c.S;
+    __builtin_assume(__isShared(y)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(S.ckc));
+    __builtin_assume(__isShared(S.smp)); __builtin_assume(__isShared(S.pw)); __builtin_assume(__isShared(S.col));
+    __builtin_assume(__isShared(S.poff));
     const int tid = threadIdx.x, nth = blockDim.x;
     const int nu = c.nu, nf = c.nf, ns = c.ns, nkc = c.nkc;
     const double mu_f = c.mu_f;
@@ -166,6 +175,7 @@ static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double*
 static __device__ __forceinline__ void ipm_apply_H(const IpmCtx& c, const double* v, double* out) {
     const int tid = threadIdx.x, nth = blockDim.x, nu = c.nu;
     const double* Hg = c.Hg;
+    __builtin_assume(__isShared(v)); __builtin_assume(__isShared(out)); __builtin_assume(__isGlobal(Hg));
     for (int i = tid; i < nu; i += nth) {
         double s = 0;
         for (int j = 0; j < nu; ++j) s += Hg[static_cast<size_t>(j) * nu + i] * v[j];
@@ -177,8 +187,10 @@ static __device__ __forceinline__ void ipm_apply_H(const IpmCtx& c, const double
 // out = E v - e (or E v when with_rhs == false)
 static __device__ __forceinline__ void ipm_apply_E(const IpmCtx& c, const double* v, double* out, bool with_rhs) {
     const int tid = threadIdx.x;
+    const EqRow* eq = c.eq;
+    __builtin_assume(__isShared(v)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(eq));
     if (tid < c.neq) {
-        const EqRow& q = c.eq[tid];
+        const EqRow& q = eq[tid];
         double s = with_rhs ? -q.rhs : 0.0;
         for (int i = 0; i < q.cnt; ++i) s += q.w[i] * v[q.col[i]];
         out[tid] = s;
@@ -188,10 +200,12 @@ static __device__ __forceinline__ void ipm_apply_E(const IpmCtx& c, const double
 
 // out += scale E' y
 static __device__ __forceinline__ void ipm_add_Et(const IpmCtx& c, const double* y, double* out, double scale) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, neq = c.neq;
+    const EqRow* eq = c.eq;
+    __builtin_assume(__isShared(y)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(eq));
     if (tid < kNumEE * 2)   // one thread per (foot, coord): rows of different groups touch different columns
-        for (int r = 0; r < c.neq; ++r) {
-            const EqRow& q = c.eq[r];
+        for (int r = 0; r < neq; ++r) {
+            const EqRow& q = eq[r];
             if (q.pad != tid) continue;
             for (int i = 0; i < q.cnt; ++i) out[q.col[i]] += scale * y[r] * q.w[i];
         }
