@@ -17,6 +17,7 @@
 #include "bgg_chol.cuh"
 #include "bgg_kkt.cuh"
 #include "bgg_kkt_mma.cuh"
+#include "bgg_l2ops.cuh"
 
 namespace bgg {
 
@@ -73,16 +74,10 @@ static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double
     __builtin_assume(__isShared(S.smp)); __builtin_assume(__isShared(S.pw)); __builtin_assume(__isShared(S.pcnt));
     __builtin_assume(__isShared(S.poff)); __builtin_assume(__isShared(fbase)); __builtin_assume(__isShared(pbase));
     __builtin_assume(__isShared(nfv)); __builtin_assume(__isShared(npv));
-    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
+    const int tid = threadIdx.x, nth = blockDim.x;
     const int nf = c.nf, ns = c.ns, ne = c.ne, nkc = c.nkc;
     const double mu_f = c.mu_f;
-    for (int q = wid; q < nkc; q += nwarp) {     // dense position rows: one warp per (node, coord)
-        const double* row = S.phi + static_cast<size_t>(q) * S.phi_stride;
-        double s = 0;
-        for (int i = lane; i < nf; i += 32) s += row[i] * v[i];
-        s = warp_sum(s);
-        if (lane == 0) S.tkc[q] = s;
-    }
+    l2_phi_rows_dot(S.phi, S.phi_stride, nkc, nf, smem_addr(v), smem_addr(S.tkc));   // dense position rows (csrc/bgg_l2ops.cuh)
     for (int j = tid; j < ns; j += nth) {
         const Sample& sp = S.smp[j];
         double fv[3];
@@ -131,6 +126,7 @@ static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double*
         S.ckc[q] = -s;
     }
     __syncthreads();
+    l2_phi_cols_dot(S.phi, S.phi_stride, nkc, nf, smem_addr(S.ckc), smem_addr(out));   // dense foot-box rows (csrc/bgg_l2ops.cuh)
     // Two threads per column (nu <= 160 < blockDim / 2 ... else one): the first takes the dense foot-box rows (force
     // column) or the first half of the nodes (position column), the second the sample rows / the second half; the
     // loops run over the column's own sample / node range only (ColInfo, csrc/bgg_kkt.cuh).
@@ -144,8 +140,6 @@ static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double*
             double s = 0;
             if (!act) {
             } else if (col < nf) {
-                if (part == 0 || half == 1)
-                    for (int q = 0; q < nkc; ++q) s += S.ckc[q] * S.phi[static_cast<size_t>(q) * S.phi_stride + col];
                 if (part == 1 || half == 1)
                     for (int j = ci.lo; j < ci.hi; ++j) {
                         const Sample& sp = S.smp[j];
@@ -173,15 +167,7 @@ static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double*
 
 // out[0..nu) = H v, H full symmetric in HBM/L2, read column-wise (coalesced across threads)
 static __device__ __forceinline__ void ipm_apply_H(const IpmCtx& c, const double* v, double* out) {
-    const int tid = threadIdx.x, nth = blockDim.x, nu = c.nu;
-    const double* Hg = c.Hg;
-    __builtin_assume(__isShared(v)); __builtin_assume(__isShared(out)); __builtin_assume(__isGlobal(Hg));
-    for (int i = tid; i < nu; i += nth) {
-        double s = 0;
-        for (int j = 0; j < nu; ++j) s += Hg[static_cast<size_t>(j) * nu + i] * v[j];
-        out[i] = s;
-    }
-    __syncthreads();
+    l2_apply_H(c.Hg, c.nu, smem_addr(v), smem_addr(out));   // csrc/bgg_l2ops.cuh
 }
 
 // out = E v - e (or E v when with_rhs == false)
