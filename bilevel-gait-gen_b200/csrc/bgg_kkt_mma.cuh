@@ -153,13 +153,17 @@ static __device__ __noinline__ void kkt_dense_mma(const KktDenseArgs a, const do
             const double aA = (lenA > 0) ? a_val(iA, q, wq, row_s, loA, hiA, footA, coordA, varA) : 0.0;
             const double aB = (lenB > 0) ? a_val(iB, q, wq, row_s, loB, hiB, footB, coordB, varB) : 0.0;
             const unsigned pA = row_s + 8u * (8 * jA0 + g), pB = row_s + 8u * (8 * (jB0 - lenA) + g);
+            // One B operand ahead of the DMMA that uses it, all sixteen slots unconditionally (an empty slot multiplies by a
+            // zero A operand and reads a valid address): no branch, no warp-convergence bookkeeping between the DMMAs.
+            const double aBz = (lenB > 0) ? aB : 0.0;
+            double b_cur = lds64(((0 < lenA) ? pA : pB));
 #pragma unroll
-            for (int u = 0; u < kAccMax; ++u)
-                if (u < nslot) {
-                    const bool isA = u < lenA;
-                    const double bv = lds64((isA ? pA : pB) + 64u * u);
-                    chol::dmma(acc[u].x, acc[u].y, isA ? aA : aB, bv);
-                }
+            for (int u = 0; u < kAccMax; ++u) {
+                double b_next = 0.0;
+                if (u + 1 < kAccMax) b_next = lds64(((u + 1 < lenA) ? pA : pB) + 64u * (u + 1));
+                chol::dmma(acc[u].x, acc[u].y, (u < lenA) ? aA : aBz, b_cur);
+                b_cur = b_next;
+            }
             if (ch + 1 < nchunk) stage((ch + 1) & 1, pf);
             __syncthreads();
         }
