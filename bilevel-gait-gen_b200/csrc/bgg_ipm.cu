@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             S.phi_stride = L.max_nu;
         }
     }
+    #pragma unroll 1
     for (int i = tid; i < ns * static_cast<int>(sizeof(Sample) / 8); i += nth)
         reinterpret_cast<double*>(S.smp)[i] = reinterpret_cast<const double*>(samples)[i];
     for (int i = tid; i < 4 * (N - 3); i += nth) {
@@ -306,7 +307,9 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         s_nfv[tid] = Hd->nfv[tid];
         s_npv[tid] = Hd->npv[tid];
     }
+    #pragma unroll 1
     for (int i = tid; i < nu; i += nth) S.g[i] = gg[i];
+    #pragma unroll 1
     for (int i = tid; i < 6 * cap_nu; i += nth)   // u du rd rhs g tmpn: the padding up to 8 nb stays zero (chol::solve)
         if (i % cap_nu >= nu) S.u[i] = 0.0;
     if (tid == 0) {
@@ -322,10 +325,12 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     const double box0 = Hd->ee_box[0] / 2, box1 = Hd->ee_box[1] / 2;
     const double fbound = P.force_bound;
     const int m_force = 6 * ns;
+    #pragma unroll 1
     for (int j = tid; j < ns; j += nth) {
         const bool act = samples[j].active != 0;
         for (int r = 0; r < 6; ++r) S.wv[6 * j + r] = act ? 1.0 : 0.0;
     }
+    #pragma unroll 1
     for (int e = tid; e < ne; e += nth) {
         const int c = e & 1, foot = (e >> 1) & 3, kk = e >> 3;   // node k = kk + 4
         const double bx = c ? box1 : box0;
@@ -383,16 +388,20 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     // ------------------------------------------------------------------------------------------------ start point
     // u0 = argmin of the equality/inequality-penalised quadratic: (H + C'C + E'E/delta) u = -g + C'd + E'e/delta
     bool ok = build_and_factor();
+    #pragma unroll 1
     for (int i = tid; i < nu; i += nth) S.rhs[i] = -S.g[i];
+    #pragma unroll 1
     for (int i = tid; i < m; i += nth) S.rp[i] = (S.wv[i] != 0.0) ? rhs_of(i) : 0.0;
     if (tid < neq) S.re[tid] = s_eq[tid].rhs;
     __syncthreads();
     add_Ct(S.rp, S.rhs);
     add_Et(S.re, S.rhs, inv_delta);
+    #pragma unroll 1
     for (int i = tid; i < nu; i += nth) S.u[i] = S.rhs[i];
     chol_solve(S.u);
     apply_C(S.u, S.ds);
     double mn = 1e300;
+    #pragma unroll 1
     for (int i = tid; i < m; i += nth)
         if (S.wv[i] != 0.0) {
             S.s[i] = rhs_of(i) - S.ds[i];
@@ -401,6 +410,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     mn = block_reduce<kMin>(mn, S.red);
     const double shift = fmax(0.0, -1.5 * mn);
     double sl = 0, ss = 0, xi = 0;
+    #pragma unroll 1
     for (int i = tid; i < m; i += nth) {
         if (S.wv[i] != 0.0) {
             const double v = fmax(S.s[i] + shift, 1e-2);
@@ -415,6 +425,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     }
     xi = block_reduce<kSum>(xi, S.red);
     sl = block_reduce<kSum>(sl, S.red);
+    #pragma unroll 1
     for (int i = tid; i < m; i += nth)
         if (S.wv[i] != 0.0) {
             S.s[i] += 0.5 * xi / sl;
@@ -422,6 +433,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         }
     ss = block_reduce<kSum>(ss, S.red);
     int m_act = 0;
+    #pragma unroll 1
     for (int i = tid; i < m; i += nth)
         if (S.wv[i] != 0.0) {
             S.lam[i] += 0.5 * xi / ss;
@@ -435,6 +447,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     for (int r = 0; r < kNx; ++r) nrm_q = fmax(nrm_q, fmax(fabs(P.w[r]), fabs(P.Phi_w[r])));
     {
         double v = 0;
+        #pragma unroll 1
         for (int i = tid; i < m; i += nth)
             if (S.wv[i] != 0.0) v = fmax(v, fabs(rhs_of(i)));
         nrm_d = fmax(1.0, block_reduce<kMax>(v, S.red));
@@ -447,6 +460,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         // residuals: rd = H u + g + C'lam + E'nu ; rp = C u + s - d ; re = E u - e
         apply_H(S.u, S.rd);
         double pobj = 0;
+        #pragma unroll 1
         for (int i = tid; i < nu; i += nth) {
             pobj += S.u[i] * (0.5 * S.rd[i] + S.g[i]);
             S.rd[i] += S.g[i];
@@ -458,7 +472,9 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         apply_C(S.u, S.rp);
         apply_E(S.u, S.re, true);
         double a = 0, c = 0, dsum = 0;
+        #pragma unroll 1
         for (int i = tid; i < nu; i += nth) a = fmax(a, fabs(S.rd[i]));
+        #pragma unroll 1
         for (int i = tid; i < m; i += nth) {
             if (S.lam[i] > 0.0) {   // active row (inactive rows keep lam == 0 exactly)
                 S.rp[i] = S.rp[i] + S.s[i] - rhs_of(i);
@@ -513,6 +529,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         if (it == P.ipm_max_iter) break;
 
         // scaling W = lam / s (inactive rows keep 0), factorisation
+        #pragma unroll 1
         for (int i = tid; i < m; i += nth) S.wv[i] = (S.lam[i] > 0.0) ? S.lam[i] / S.s[i] : 0.0;
         __syncthreads();
         ok = build_and_factor();
@@ -524,6 +541,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         // one Newton solve for complementarity target rc (dl holds -rc on entry, see callers):
         //   K du = -rd - C'((-rc + lam rp)/s) - E' re / delta ; ds = -rp - C du ; dl = (-rc - lam ds)/s
         auto newton = [&](bool corrector, double sig_mu) {
+            #pragma unroll 1
             for (int i = tid; i < m; i += nth) {
                 if (S.wv[i] == 0.0) {
                     S.dl[i] = 0.0;
@@ -534,12 +552,15 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
                 S.dl[i] = rc;                                           // keep rc
             }
             __syncthreads();
+            #pragma unroll 1
             for (int i = tid; i < m; i += nth)
                 S.ds[i] = (S.wv[i] != 0.0) ? -(-S.dl[i] + S.lam[i] * S.rp[i]) / S.s[i] : 0.0;
+            #pragma unroll 1
             for (int i = tid; i < nu; i += nth) S.rhs[i] = -S.rd[i];
             __syncthreads();
             add_Ct(S.ds, S.rhs);
             add_Et(S.re, S.rhs, -inv_delta);
+            #pragma unroll 1
             for (int i = tid; i < nu; i += nth) S.du[i] = S.rhs[i];
             chol_solve(S.du);
             // The predictor only steers the centring parameter sigma: it is solved without refinement.
@@ -547,17 +568,21 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
                 // iterative refinement against K = H + C'WC + E'E/delta applied matrix-free
                 apply_H(S.du, S.tmpn);
                 apply_C(S.du, S.ds);
+                #pragma unroll 1
                 for (int i = tid; i < m; i += nth) S.ds[i] *= S.wv[i];
                 __syncthreads();
                 add_Ct(S.ds, S.tmpn);
                 apply_E(S.du, S.dnu, false);
                 add_Et(S.dnu, S.tmpn, inv_delta);
+                #pragma unroll 1
                 for (int i = tid; i < nu; i += nth) S.tmpn[i] = S.rhs[i] - S.tmpn[i];
                 chol_solve(S.tmpn);
+                #pragma unroll 1
                 for (int i = tid; i < nu; i += nth) S.du[i] += S.tmpn[i];
                 __syncthreads();
             }
             apply_C(S.du, S.ds);
+            #pragma unroll 1
             for (int i = tid; i < m; i += nth) {
                 if (S.wv[i] == 0.0) {
                     S.ds[i] = 0.0;
@@ -574,6 +599,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         };
         auto max_step = [&]() -> double {
             double al = 1e300;
+            #pragma unroll 1
             for (int i = tid; i < m; i += nth)
                 if (S.wv[i] != 0.0) {
                     if (S.ds[i] < 0.0) al = fmin(al, -S.s[i] / S.ds[i]);
@@ -584,6 +610,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         newton(false, 0.0);
         const double a_aff = fmin(1.0, max_step());
         double mu_aff = 0;
+        #pragma unroll 1
         for (int i = tid; i < m; i += nth)
             if (S.wv[i] != 0.0) mu_aff += (S.s[i] + a_aff * S.ds[i]) * (S.lam[i] + a_aff * S.dl[i]);
         mu_aff = block_reduce<kSum>(mu_aff, S.red) / m_act;
@@ -591,7 +618,9 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         const double sigma = sr * sr * sr;
         newton(true, sigma * mu);
         const double alpha = fmin(1.0, 0.99 * max_step());
+        #pragma unroll 1
         for (int i = tid; i < nu; i += nth) S.u[i] += alpha * S.du[i];
+        #pragma unroll 1
         for (int i = tid; i < m; i += nth)
             if (S.wv[i] != 0.0) {
                 S.s[i] += alpha * S.ds[i];
@@ -619,7 +648,9 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     double* lo = reinterpret_cast<double*>(ws + L.lam);
     double* so = reinterpret_cast<double*>(ws + L.slack);
     double* no = reinterpret_cast<double*>(ws + L.nueq);
+    #pragma unroll 1
     for (int i = tid; i < nu; i += nth) uo[i] = S.u[i];
+    #pragma unroll 1
     for (int i = tid; i < m; i += nth) {
         lo[i] = S.lam[i];
         so[i] = (S.lam[i] > 0.0 || S.s[i] != 1.0) ? S.s[i] : rhs_of(i);   // inactive rows: slack = d (row is 0 <= d)

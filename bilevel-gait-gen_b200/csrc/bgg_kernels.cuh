@@ -27,7 +27,7 @@ __device__ __forceinline__ double warp_min(double v) {
 }
 enum RedOp { kSum, kMax, kMin };
 template <int OP>
-__device__ __forceinline__ double block_reduce(double v, double* scratch) {
+__device__ __noinline__ double block_reduce(double v, double* scratch) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     v = (OP == kSum) ? warp_sum(v) : (OP == kMax ? warp_max(v) : warp_min(v));
     __syncthreads();   // protect scratch from the previous use
