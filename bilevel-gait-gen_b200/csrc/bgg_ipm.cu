@@ -78,6 +78,7 @@ static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double
     const int nf = c.nf, ns = c.ns, ne = c.ne, nkc = c.nkc;
     const double mu_f = c.mu_f;
     l2_phi_rows_dot(S.phi, S.phi_stride, nkc, nf, smem_addr(v), smem_addr(S.tkc));   // dense position rows (csrc/bgg_l2ops.cuh)
+    #pragma unroll 1
     for (int j = tid; j < ns; j += nth) {
         const Sample& sp = S.smp[j];
         double fv[3];
@@ -96,6 +97,7 @@ static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double
         o[5] = -fv[1] - mu_f * fv[2];
     }
     __syncthreads();
+    #pragma unroll 1
     for (int e = tid; e < ne; e += nth) {
         const int cc = e & 1, foot = (e >> 1) & 3, kk = e >> 3, kf = kk * 4 + foot;
         const double* vv = v + nf + pbase[foot] + cc * npv[foot] + S.poff[kf];
@@ -116,6 +118,7 @@ static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double*
     const int tid = threadIdx.x, nth = blockDim.x;
     const int nu = c.nu, nf = c.nf, ns = c.ns, nkc = c.nkc;
     const double mu_f = c.mu_f;
+    #pragma unroll 1
     for (int q = tid; q < nkc; q += nth) {
         const int kk = q >> 1, cc = q & 1;
         double s = 0;
@@ -132,6 +135,7 @@ static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double*
     // loops run over the column's own sample / node range only (ColInfo, csrc/bgg_kkt.cuh).
     {
         const int half = (2 * nu <= nth) ? 2 : 1;
+        #pragma unroll 1
         for (int base = 0; base < half * nu; base += nth) {   // whole warps iterate together: the partner exchange is a shuffle
             const int it = base + tid;
             const bool act = it < half * nu;
@@ -141,6 +145,7 @@ static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double*
             if (!act) {
             } else if (col < nf) {
                 if (part == 1 || half == 1)
+                    #pragma unroll 1
                     for (int j = ci.lo; j < ci.hi; ++j) {
                         const Sample& sp = S.smp[j];
                         const double* yy = y + 6 * j;
@@ -153,6 +158,7 @@ static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double*
             } else {
                 const int mid = (half == 2) ? (ci.lo + ci.hi + 1) / 2 : ci.hi;
                 const int k0 = (part == 0) ? ci.lo : mid, k1 = (part == 0) ? mid : ci.hi;
+                #pragma unroll 1
                 for (int kk = k0; kk < k1; ++kk) {
                     const int kf = kk * 4 + ci.foot, e = kf * 2 + ci.coord;
                     s += (y[6 * ns + 2 * e] - y[6 * ns + 2 * e + 1]) * S.pw[2 * kf + (ci.var - S.poff[kf])];
@@ -190,6 +196,7 @@ static __device__ __forceinline__ void ipm_add_Et(const IpmCtx& c, const double*
     const EqRow* eq = c.eq;
     __builtin_assume(__isShared(y)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(eq));
     if (tid < kNumEE * 2)   // one thread per (foot, coord): rows of different groups touch different columns
+        #pragma unroll 1
         for (int r = 0; r < neq; ++r) {
             const EqRow& q = eq[r];
             if (q.pad != tid) continue;
