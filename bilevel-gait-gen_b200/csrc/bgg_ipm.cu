@@ -614,17 +614,25 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
                 }
             return block_reduce<kMin>(al, S.red);
         };
-        newton(false, 0.0);
-        const double a_aff = fmin(1.0, max_step());
-        double mu_aff = 0;
-        #pragma unroll 1
-        for (int i = tid; i < m; i += nth)
-            if (S.wv[i] != 0.0) mu_aff += (S.s[i] + a_aff * S.ds[i]) * (S.lam[i] + a_aff * S.dl[i]);
-        mu_aff = block_reduce<kSum>(mu_aff, S.red) / m_act;
-        const double sr = mu_aff / mu;
-        const double sigma = sr * sr * sr;
-        newton(true, sigma * mu);
-        const double alpha = fmin(1.0, 0.99 * max_step());
+        // predictor, then corrector: one copy of the Newton step in the binary (instruction-cache footprint)
+        double sig_mu = 0.0, alpha = 1.0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            newton(pass == 1, sig_mu);
+            const double amax = max_step();
+            if (pass == 0) {
+                const double a_aff = fmin(1.0, amax);
+                double mu_aff = 0;
+#pragma unroll 1
+                for (int i = tid; i < m; i += nth)
+                    if (S.wv[i] != 0.0) mu_aff += (S.s[i] + a_aff * S.ds[i]) * (S.lam[i] + a_aff * S.dl[i]);
+                mu_aff = block_reduce<kSum>(mu_aff, S.red) / m_act;
+                const double sr = mu_aff / mu;
+                sig_mu = sr * sr * sr * mu;
+            } else {
+                alpha = fmin(1.0, 0.99 * amax);
+            }
+        }
         #pragma unroll 1
         for (int i = tid; i < nu; i += nth) S.u[i] += alpha * S.du[i];
         #pragma unroll 1
