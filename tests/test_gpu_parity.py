@@ -248,7 +248,12 @@ def test_gait_gradient_matches_oracle(cfg_name):
         nd = 12 * (N + 1)
         # dz itself is tiny (|dz| ~ 1e-3 against multipliers of 1e3) and moves by percents with the last digits of the
         # solver's final (lam, s); it is checked on identical inputs in test_gait_gradient_kernel_on_injected_solution
+        # dual solution of the QP (north_star: primal / dual within 1e-4 relative): inequality multipliers in the reference's
+        # row order, multipliers of the dynamics rows (recovered by the adjoint recursion) and of the touch-down / foot-start rows
+        assert _rel(sol["lam"][order], terms["lam"]) < 1e-4
         assert _rel(adj["nu_dyn"], terms["nu"][:nd]) < 1e-6
+        n_eq_extra = len(terms["nu"]) - nd
+        assert np.abs(sol["nu_eq"][:n_eq_extra] - terms["nu"][nd:]).max() <= 1e-4 * max(1.0, np.abs(terms["nu"]).max())
         assert _rel(adj["dnu_dyn"], terms["dnu"][:nd]) < 1e-4
         assert _rel(adj["dnu_eq"], terms["dnu"][nd:]) < 1e-4
         assert np.abs(adj["dlam"][order] * sol["lam"][order] - terms["dlam"] * terms["lam"]).max() <= 1e-4 * max(
