@@ -443,3 +443,73 @@ def test_closed_loop_sweep_follows_the_oracle():
         assert [int(h[b]) for h in hist] == st
         assert abs(gpu.get_instance(b)["init_time"] - T * dt) < 1e-12
         assert np.abs(gpu.GetStates(b) - o.states()).max() < 1e-3 * max(1.0, np.abs(o.states()).max())
+
+
+def test_controller_three_mode_schedule_follows_the_oracle():
+    """SURVEY 8f row 1 -- controller::MPCController::MPCUpdate (controllers/mpc_controller.cpp:286-399, 518-573): the
+    solve / solve + gait derivative / line-search schedule on the batched CUDA path against the same loop on the oracle,
+    closed loop on the model's own next node, gait_opt_freq = 3 so that every mode runs twice in 7 ticks.  The GPU
+    instance is overwritten with the oracle's trajectory before every tick (identical inputs), and the line search runs
+    from the CUDA path's LP step on both sides (the LP has its own parity test; a gradient entry that is numerically zero
+    may pick another vertex)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import controller_oracle as co
+    import gait_oracle as go
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "bilevel-gait-gen_b200"))
+    import mpc_controller as mc
+    cfg_name = "a1_configuration"
+    cfg = wl.CONFIGS[cfg_name]
+    dt = cfg["integrator_dt"]
+    B, T, K = 2, 7, 10
+    states, _, ee = wl.batched_trot_inputs(cfg, B, seed=33)
+    states[0] = cfg["srb_init"]
+    ee[0] = wl.EE_NOMINAL
+    gpu = common.make_gpu(cfg_name, B, states)
+    ctrl = mc.MPCController(gpu, gait_opt_freq=3, ls_size=K)
+    oracles, octrl = [], []
+    for b in range(B):
+        o = common.make_oracle(cfg_name, states[b])
+        o.initial_run(states[b], ee[b])
+        oracles.append(o)
+        octrl.append(co.ControllerOracle(o, 3, ls_size=K))
+    state, ee_now, t = states.copy(), ee.copy(), 0.0
+    modes = []
+    for tick in range(T):
+        for b in range(B):
+            common.mirror_oracle_to_gpu(oracles[b], gpu, b)
+        mode = ctrl.mode()
+        assert all(oc.mode() == mode or (mode == "line_search" and not oc.deriv_ready) for oc in octrl), (mode, [oc.mode() for oc in octrl])
+        res = ctrl.MPCUpdate(state, np.full(B, t), ee_now)
+        modes.append(res["mode"])
+        for b in range(B):
+            o, oc = oracles[b], octrl[b]
+            if mode == "line_search":
+                if not oc.deriv_ready:      # the reference runs a plain update for this robot; so does a zero step
+                    oc.tick(state[b], t, ee_now[b])
+                    continue
+                counts = [len(tt) for tt, _ in go.contact_times(o)]
+                step_g = np.concatenate([ctrl.lp["step"][b, e, :counts[e]] for e in range(4)])
+                r = oc.tick(state[b], t, ee_now[b], step_override=step_g)
+                ok = r["quality"] != 3
+                assert np.array_equal(res["quality"][b], r["quality"])
+                assert np.abs(res["ls_costs"][b][ok] - r["ls_costs"][ok]).max() <= 1e-4 * max(1.0, np.abs(r["ls_costs"][ok]).max())
+                if res["best"][b] != r["best"]:
+                    assert abs(r["ls_costs"][res["best"][b]] - r["ls_costs"][r["best"]]) <= 1e-4 * max(1.0, abs(r["ls_costs"][r["best"]]))
+            else:
+                r = oc.tick(state[b], t, ee_now[b])
+                assert res["status"][b] == r["status"]
+                if r["status"] == 0:
+                    assert abs(res["cost"][b] - r["cost"]) <= 1e-4 * max(1.0, abs(r["cost"]))
+                    assert np.abs(gpu.GetStates(b) - o.states()).max() < 1e-4 * max(1.0, np.abs(o.states()).max())
+                if mode == "solve_and_gait_opt":
+                    assert bool(ctrl.deriv_ready[b]) == bool(oc.deriv_ready)
+                    if oc.deriv_ready:
+                        g, g_o = res["dHdtheta"][b], r["dHdtheta"]
+                        assert np.abs(g - g_o).max() <= 1e-4 * max(1.0, np.abs(g_o).max())
+        # plant: the model's own next node (apps/mpc_demo.cpp:185); feet from the trajectory at the new time
+        t += dt
+        for b in range(B):
+            state[b] = oracles[b].states()[1]
+            ee_now[b] = np.array([oracles[b].ee_at(e, t) for e in range(4)])
+    assert modes == ["solve", "solve", "solve_and_gait_opt", "line_search", "solve", "solve_and_gait_opt", "line_search"], modes
