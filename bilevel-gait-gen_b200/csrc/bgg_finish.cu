@@ -20,7 +20,7 @@ __device__ __forceinline__ void cross3f(const double a[3], const double b[3], do
 
 static size_t finish_smem_bytes(const WsLayout& L) {
     const size_t n_max = static_cast<size_t>(kNx) * (L.N + 1) + L.max_nu;
-    return 2 * sizeof(FootSpline) * kNumEE + 8 * (4 * n_max + static_cast<size_t>(kNx) * (L.N + 1) + 64);
+    return 2 * sizeof(FootSpline) * kNumEE + 8 * (4 * n_max + static_cast<size_t>(kNx) * (L.N + 1) + 64 + static_cast<size_t>(kNumEE) * 6 * L.N);
 }
 
 __global__ void __launch_bounds__(128) k_finish(Params P, Instance* __restrict__ inst, WsLayout L, char* __restrict__ ws_base) {
@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(128) k_finish(Params P, Instance* __restrict__
     double* zt = pd + n_max;                                     // trial point
     double* xt = zt + n_max;                                     // round-tripped tangent states of the trial [N+1][12]
     double* red = xt + kNx * (L.N + 1);
+    double* fp = red + 64;                                       // [N][4][6]: foot force and position at the node times (defects_of)
     __shared__ int s_fbase[kNumEE], s_pbase[kNumEE], s_nfv[kNumEE], s_npv[kNumEE];
 
     {
@@ -97,12 +98,18 @@ __global__ void __launch_bounds__(128) k_finish(Params P, Instance* __restrict__
     }
     if (tid < kNx) zq[tid] = xoff[tid];
     __syncthreads();
-    if (tid < 32) {
+    if (tid < 32) {   // 12 lanes, one state row each; the next node's row of Ad travels from L2 while this node is multiplied
+        double a_cur[kNx], a_next[kNx];
+        if (tid < kNx)
+            for (int q = 0; q < kNx; ++q) a_cur[q] = nodes[0].Ad[tid * kNx + q];
         for (int k = 0; k < N; ++k) {
             if (tid < kNx) {
+                if (k + 1 < N)
+                    for (int q = 0; q < kNx; ++q) a_next[q] = nodes[k + 1].Ad[tid * kNx + q];
                 double s = xt[k * kNx + tid];
-                for (int q = 0; q < kNx; ++q) s += nodes[k].Ad[tid * kNx + q] * zq[k * kNx + q];
+                for (int q = 0; q < kNx; ++q) s += a_cur[q] * zq[k * kNx + q];
                 zq[(k + 1) * kNx + tid] = s;
+                for (int q = 0; q < kNx; ++q) a_cur[q] = a_next[q];
             }
             __syncwarp();
         }
@@ -167,11 +174,20 @@ __global__ void __launch_bounds__(128) k_finish(Params P, Instance* __restrict__
             }
         }
         __syncthreads();
+        // the 24 spline evaluations of a node (4 feet x 3 coordinates x force / position) are spread over the CTA: one
+        // work item per (node, foot, coordinate); the defects are then formed by one thread per node in the same order
+        // of operations as before
+        for (int it = tid; it < N * kNumEE * 3; it += nth) {
+            const int k = it / (kNumEE * 3), e = (it / 3) % kNumEE, c = it % 3;
+            const double tk = k * P.dt + t0;
+            fp[(k * kNumEE + e) * 6 + c] = value_at(sf[e], true, c, tk);
+            fp[(k * kNumEE + e) * 6 + 3 + c] = value_at(sf[e], false, c, tk);
+        }
+        __syncthreads();
         double l1 = 0;
         for (int k = tid; k < N; k += nth) {
             const double* x = xt + k * kNx;
             const double* xn = xt + (k + 1) * kNx;
-            const double tk = k * P.dt + t0;
             const double* om = x + 9;
             double fd[kNx];
             for (int i = 0; i < 3; ++i) fd[i] = x[3 + i] / P.mass;
@@ -184,8 +200,8 @@ __global__ void __launch_bounds__(128) k_finish(Params P, Instance* __restrict__
             for (int e = 0; e < kNumEE; ++e) {
                 double f[3], rel[3], tq[3];
                 for (int c = 0; c < 3; ++c) {
-                    f[c] = value_at(sf[e], true, c, tk);
-                    rel[c] = value_at(sf[e], false, c, tk) - x[c];
+                    f[c] = fp[(k * kNumEE + e) * 6 + c];
+                    rel[c] = fp[(k * kNumEE + e) * 6 + 3 + c] - x[c];
                 }
                 cross3f(rel, f, tq);
                 for (int i = 0; i < 3; ++i) {
