@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         S.pw[2 * i + 1] = nl.pw[foot][1];
     }
     __shared__ int s_fbase[kNumEE], s_pbase[kNumEE], s_nfv[kNumEE], s_npv[kNumEE];
-    __shared__ int s_flag, s_nitems, s_nwork;
+    __shared__ int s_flag, s_nitems, s_nwork, s_npos;
     __shared__ KktWork s_work[kMaxKktWork];
     __shared__ int s_sb[kNumEE + 1];   // per-foot sample ranges (samples are stored foot-major)
     __shared__ EqRow s_eq[kMaxEq];
@@ -352,8 +352,9 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     kkt_build_colinfo(S.col, nu, nf, N, s_fbase, s_pbase, s_nfv, s_npv, s_sb, S.smp, S.pcnt, S.poff);
     __syncthreads();
     KktItem* kitems = reinterpret_cast<KktItem*>(ws + L.ktab);
-    kkt_mma_setup(s_work, &s_nwork, (nu + 7) >> 3, kitems, &s_nitems, s_fbase, s_nfv, S.col, S.smp);
-    if (s_nitems > kMaxKktItems) {   // cannot happen within max_spline_vars = 160; refuse rather than drop terms
+    KktPos* kpos = reinterpret_cast<KktPos*>(ws + L.ktab + sizeof(KktItem) * kMaxKktItems);
+    kkt_mma_setup(s_work, &s_nwork, (nu + 7) >> 3, kitems, &s_nitems, s_fbase, s_nfv, S.col, S.smp, kpos, &s_npos, nu, nf, s_eq, neq);
+    if (s_nitems > kMaxKktItems || s_npos > kMaxKktPos) {   // cannot happen within max_spline_vars = 160; refuse rather than drop terms
         if (tid == 0) Hd->status = kOther;
         return;
     }
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     KktMma km;
     km.K = S.K; km.Hg = Hg; km.phig = phipos; km.phi_ld = L.max_nu; km.nu = nu; km.nf = nf; km.nb = nb; km.ns = ns; km.ne = ne;
     km.neq = neq; km.nkc = nkc; km.wv = S.wv; km.pw = S.pw; km.pcnt = S.pcnt; km.poff = S.poff; km.smp = S.smp; km.eq = s_eq;
-    km.col = S.col; km.ckc = S.ckc; km.scratch = S.ds; km.work = s_work; km.nwork = s_nwork; km.items = kitems; km.nitems = s_nitems;
+    km.col = S.col; km.ckc = S.ckc; km.scratch = S.ds; km.work = s_work; km.nwork = s_nwork; km.items = kitems; km.nitems = s_nitems; km.pos = kpos; km.npos = s_npos;
     km.mu_f = mu_f; km.inv_delta = inv_delta;
     auto build_and_factor = [&]() -> bool {
         PROF(10);

@@ -30,6 +30,17 @@ static_assert(sizeof(KktItem) == 12, "KktItem is read as three 32-bit words");
 static_assert(kMaxSamples <= 255, "sample indices are stored in 8 bits");
 constexpr int kMaxKktItems = 1536;
 
+struct KktPos {           // one position x position entry of K (same foot and coordinate): sum_kk om pw_i pw_j + eq / delta
+    int32_t koff;
+    int16_t lo, hi;       // foot-box nodes kk - 4 that contain both variables
+    int16_t vi, vj;       // local indices of the two variables
+    int8_t foot, coord;
+    int16_t pad;
+    double eq;            // sum over the touch-down / foot-start rows of w_i w_j (constant over the solve)
+};
+static_assert(sizeof(KktPos) == 24, "KktPos layout");
+constexpr int kMaxKktPos = 512;
+
 constexpr int kAccMax = 16;   // K blocks per warp and pass
 
 // row stride (doubles) of a staged phi chunk: >= 8 nb and = 4 mod 16, so that the fragment loads of lanes (g, t) at
@@ -59,6 +70,11 @@ __device__ __forceinline__ unsigned lds32(unsigned addr) {
 __device__ __forceinline__ void sts64(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 __device__ __forceinline__ void sts128(unsigned addr, double2 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ double2 ldg128(const double* p) {   // H blocks: issued in program order, see kkt_dense_mma
+    double2 v;
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
 }
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 
@@ -108,16 +124,24 @@ static __device__ __noinline__ void kkt_dense_mma(const KktDenseArgs a, const do
         }
         const int nslot = lenA + lenB;
         fetch(0, pf);
+        // accumulators <- blocks of H: sixteen 16-byte loads issued back to back (clamped addresses, no branch per load; the
+        // compiler otherwise turns the guarded loads into sixteen dependent L2 round trips), then the identity padding
         double2 acc[kAccMax];
 #pragma unroll
         for (int u = 0; u < kAccMax; ++u) {
-            acc[u] = make_double2(0.0, 0.0);
-            if (u < nslot) {
-                const int ib = (u < lenA) ? rowA : rowB, jb = (u < lenA) ? jA0 + u : jB0 + u - lenA;
-                const int i = 8 * ib + g, j = 8 * jb + 2 * t;
-                if (i < nu && j < nu) acc[u] = *reinterpret_cast<const double2*>(Hg + static_cast<size_t>(i) * nu + j);
-                else if (i >= nu) acc[u] = make_double2(i == j ? 1.0 : 0.0, i == j + 1 ? 1.0 : 0.0);
-            }
+            const int uu = (u < nslot) ? u : 0;
+            const int ib = (uu < lenA) ? rowA : rowB, jb = (uu < lenA) ? jA0 + uu : jB0 + uu - lenA;
+            const int i = min(8 * ib + g, nu - 1), j = min(8 * jb + 2 * t, nu - 2);
+            acc[u] = ldg128(Hg + static_cast<size_t>(i) * nu + j);
+        }
+#pragma unroll
+        for (int u = 0; u < kAccMax; ++u) {
+            const int uu = (u < nslot) ? u : 0;
+            const int ib = (uu < lenA) ? rowA : rowB, jb = (uu < lenA) ? jA0 + uu : jB0 + uu - lenA;
+            const int i = 8 * ib + g, j = 8 * jb + 2 * t;
+            if (i >= nu) acc[u] = make_double2(i == j ? 1.0 : 0.0, i == j + 1 ? 1.0 : 0.0);
+            else if (j >= nu) acc[u] = make_double2(0.0, 0.0);
+            if (u >= nslot) acc[u] = make_double2(0.0, 0.0);
         }
         const int iA = 8 * rowA + g, iB = 8 * rowB + g;
         // position variable i: foot, coordinate, node range and local index (ColInfo, 8 bytes)
@@ -198,12 +222,15 @@ struct KktMma {
     int nwork;
     const KktItem* items;      // HBM / L2
     int nitems;
+    const KktPos* pos;         // HBM / L2
+    int npos;
     double mu_f, inv_delta;
 };
 
 // Once per solve: the block map and the item table.  Every thread of the CTA; ends with a barrier.
 __device__ inline void kkt_mma_setup(KktWork* work, int* nwork_shared, int nb, KktItem* items, int* nitems_shared, const int* fbase,
-                                     const int* nfv, const ColInfo* col, const Sample* smp) {
+                                     const int* nfv, const ColInfo* col, const Sample* smp, KktPos* pos, int* npos_shared, int nu, int nf,
+                                     const EqRow* eqrows, int neq) {
     const int tid = threadIdx.x, nth = blockDim.x;
     if (tid == 0) {
         int n = 0;
@@ -226,8 +253,41 @@ __device__ inline void kkt_mma_setup(KktWork* work, int* nwork_shared, int nb, K
         }
         *nwork_shared = n;
     }
-    if (tid == 0) *nitems_shared = 0;
+    if (tid == 0) {
+        *nitems_shared = 0;
+        *npos_shared = 0;
+    }
     __syncthreads();
+    {   // position x position entries: pairs of position variables of the same foot and coordinate
+        const int np = nu - nf;
+        for (int idx = tid; idx < np * np; idx += nth) {
+            const int i = nf + idx / np, j = nf + idx % np;
+            if (j > i) continue;
+            const ColInfo ci = col[i], cj = col[j];
+            if (cj.foot != ci.foot || cj.coord != ci.coord) continue;
+            KktPos e;
+            e.koff = chol::at(i, j);
+            e.lo = ci.lo > cj.lo ? ci.lo : cj.lo;
+            e.hi = ci.hi < cj.hi ? ci.hi : cj.hi;
+            e.vi = ci.var;
+            e.vj = cj.var;
+            e.foot = ci.foot;
+            e.coord = ci.coord;
+            e.pad = 0;
+            double eq = 0.0;
+            const int grp = ci.foot * 2 + ci.coord;
+            for (int r = 0; r < neq; ++r) {
+                const EqRow& q = eqrows[r];
+                if (q.pad != grp) continue;
+                const int ai = i - q.col[0], aj = j - q.col[0];
+                if (ai >= 0 && ai < q.cnt && aj >= 0 && aj < q.cnt) eq += q.w[ai] * q.w[aj];
+            }
+            e.eq = eq;
+            if (e.hi <= e.lo && eq == 0.0) continue;
+            const int k = atomicAdd(npos_shared, 1);
+            if (k < kMaxKktPos) pos[k] = e;
+        }
+    }
     int ib[kNumEE + 1];
     ib[0] = 0;
 #pragma unroll
@@ -306,29 +366,16 @@ __device__ inline void kkt_assemble_mma(const KktMma& v) {
     }
     KPROF(1);
     KPROF(2);
-    // ---- sparse part: position x position (same foot and coordinate only) and E'E / delta
-    const int np = nu - nf;
-    for (int idx = tid; idx < np * np; idx += nth) {
-        const int i = nf + idx / np, j = nf + idx % np;
-        if (j > i) continue;
-        const ColInfo ci = v.col[i], cj = v.col[j];
-        if (cj.foot != ci.foot || cj.coord != ci.coord) continue;
-        const int foot = ci.foot, c = ci.coord;
-        double term = 0.0, eq = 0.0;
-        const int lo = ci.lo > cj.lo ? ci.lo : cj.lo, hi = ci.hi < cj.hi ? ci.hi : cj.hi;
-        for (int kk = lo; kk < hi; ++kk) {
-            const int kf = kk * kNumEE + foot, e = kf * 2 + c;
-            const double om = v.wv[m_force + 2 * e] + v.wv[m_force + 2 * e + 1];
-            term += om * v.pw[2 * kf + (ci.var - v.poff[kf])] * v.pw[2 * kf + (cj.var - v.poff[kf])];
+    // ---- sparse part: position x position (same foot and coordinate only) and E'E / delta, from the entry table
+    for (int idx = tid; idx < v.npos; idx += nth) {
+        const KktPos e = v.pos[idx];
+        double term = 0.0;
+        for (int kk = e.lo; kk < e.hi; ++kk) {
+            const int kf = kk * kNumEE + e.foot, r = kf * 2 + e.coord;
+            const double om = v.wv[m_force + 2 * r] + v.wv[m_force + 2 * r + 1];
+            term += om * v.pw[2 * kf + (e.vi - v.poff[kf])] * v.pw[2 * kf + (e.vj - v.poff[kf])];
         }
-        const int grp = foot * 2 + c;
-        for (int r = 0; r < v.neq; ++r) {
-            const EqRow& q = v.eq[r];
-            if (q.pad != grp) continue;
-            const int ai = i - q.col[0], aj = j - q.col[0];
-            if (ai >= 0 && ai < q.cnt && aj >= 0 && aj < q.cnt) eq += q.w[ai] * q.w[aj];
-        }
-        v.K[chol::at(i, j)] += term + v.inv_delta * eq;
+        v.K[e.koff] += term + v.inv_delta * e.eq;
     }
     KPROF(3);
     // ---- sparse part: force-sample rows

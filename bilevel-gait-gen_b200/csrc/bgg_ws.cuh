@@ -106,7 +106,7 @@ inline WsLayout make_layout(int N, int max_nu) {
     L.gdnue = take(8 * kMaxEq);                                       // dnu of the touch-down / foot-start rows
     L.gdH = take(8 * kNumEE * kMaxContacts);                          // dH/dtheta, foot-major
     L.ginfo = take(sizeof(GradInfo));
-    L.ktab = take(12 * 1536);                                         // kMaxKktItems x sizeof(KktItem)
+    L.ktab = take(12 * 1536 + 24 * 512);                              // kMaxKktItems x sizeof(KktItem) + kMaxKktPos x sizeof(KktPos)
     L.stride = o;
     return L;
 }
