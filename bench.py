@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--config", default="a1_configuration", choices=sorted(wl.CONFIGS))
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--ipm-refine", type=int, default=0, help="0 = library default, -1 = no refinement")
+    ap.add_argument("--ipm-refine-after", type=int, default=0, help="refine once mu <= 10^-k of its first value (0 = library default, -1 = always)")
     ap.add_argument("--max-spline-vars", type=int, default=0)
     ap.add_argument("--latency-solves", type=int, default=200)
     ap.add_argument("--closed-loop", action="store_true",
@@ -220,7 +221,7 @@ def main():
         states, t0, ee = states[lo:hi].copy(), t0[lo:hi].copy(), ee[lo:hi].copy()
     else:
         states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=1000 + rank)
-    mpc = bg.BatchedMPC(N, cfg["integrator_dt"], wl.robot(), device=local_rank, ipm_refine=args.ipm_refine,
+    mpc = bg.BatchedMPC(N, cfg["integrator_dt"], wl.robot(), device=local_rank, ipm_refine=args.ipm_refine, ipm_refine_after=args.ipm_refine_after,
                         max_spline_vars=args.max_spline_vars, **wl.mpc_kwargs(cfg))
     mpc.AddQuadraticTrackingCost(wl.target_tangent(cfg), np.asarray(cfg["Q"], float))
     mpc.Reset(B)
@@ -287,7 +288,7 @@ def main():
     # ---- single-instance latency (BASELINE metric's second half): one MPC, host buffers in, results out, per call
     lat = None
     if rank == 0:
-        one = bg.BatchedMPC(N, cfg["integrator_dt"], wl.robot(), device=local_rank, ipm_refine=args.ipm_refine, **wl.mpc_kwargs(cfg))
+        one = bg.BatchedMPC(N, cfg["integrator_dt"], wl.robot(), device=local_rank, ipm_refine=args.ipm_refine, ipm_refine_after=args.ipm_refine_after, **wl.mpc_kwargs(cfg))
         one.AddQuadraticTrackingCost(wl.target_tangent(cfg), np.asarray(cfg["Q"], float))
         one.Reset(1)
         init = np.asarray(cfg["srb_init"], float)[None]

@@ -27,7 +27,7 @@ class BggError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("num_nodes", C.c_int32), ("max_spline_vars", C.c_int32), ("device", C.c_int32), ("ipm_max_iter", C.c_int32),
-                ("ipm_refine", C.c_int32), ("reserved_", C.c_int32), ("integrator_dt", C.c_double), ("friction_coef", C.c_double),
+                ("ipm_refine", C.c_int32), ("ipm_refine_after", C.c_int32), ("integrator_dt", C.c_double), ("friction_coef", C.c_double),
                 ("force_bound", C.c_double), ("swing_height", C.c_double), ("foot_offset", C.c_double),
                 ("ee_box_size", C.c_double * 2), ("force_cost", C.c_double), ("ipm_tol_feas", C.c_double),
                 ("ipm_tol_gap", C.c_double), ("ipm_eq_delta", C.c_double)]
@@ -137,7 +137,7 @@ class BatchedMPC:
 
     def __init__(self, num_nodes, integrator_dt, robot, friction_coef=0.5, force_bound=150.0, swing_height=0.075,
                  foot_offset=0.015, ee_box_size=(0.15, 0.15), force_cost=0.0, device=0, max_spline_vars=0,
-                 ipm_tol=0.0, ipm_max_iter=0, ipm_refine=0, ipm_tol_gap=0.0):
+                 ipm_tol=0.0, ipm_max_iter=0, ipm_refine=0, ipm_tol_gap=0.0, ipm_refine_after=0):
         self.L = lib()
         self.N = num_nodes
         cfg = Config()
@@ -147,6 +147,7 @@ class BatchedMPC:
         cfg.device = device
         cfg.ipm_max_iter = ipm_max_iter
         cfg.ipm_refine = ipm_refine
+        cfg.ipm_refine_after = ipm_refine_after
         cfg.integrator_dt = integrator_dt
         cfg.friction_coef = friction_coef
         cfg.force_bound = force_bound

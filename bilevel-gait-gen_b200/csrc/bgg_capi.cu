@@ -212,6 +212,7 @@ int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) 
     P.ipm_eq_delta = cfg->ipm_eq_delta > 0 ? cfg->ipm_eq_delta : 1e-8;
     P.ipm_max_iter = cfg->ipm_max_iter > 0 ? cfg->ipm_max_iter : 50;
     P.ipm_refine = cfg->ipm_refine < 0 ? 0 : (cfg->ipm_refine == 0 ? 1 : cfg->ipm_refine);
+    P.ipm_refine_mu_frac = cfg->ipm_refine_after < 0 ? 1e300 : pow(10.0, -static_cast<double>(cfg->ipm_refine_after == 0 ? 4 : cfg->ipm_refine_after));
     h->L = make_layout(P.N, P.max_nu);
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);

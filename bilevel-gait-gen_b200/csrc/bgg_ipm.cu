@@ -463,6 +463,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
 
     // ------------------------------------------------------------------------------------------------ main loop
     int it = 0, status = kMaxIter;
+    double mu_first = 0.0;
     double n_rd = 0, n_rp = 0, n_re = 0, mu = 0, gap_scale = 1, qp_obj = 0, last_rp = 0, last_re = 0, last_rd = 0, last_mu = 0;
     for (it = 0; it <= P.ipm_max_iter; ++it) {
         // residuals: rd = H u + g + C'lam + E'nu ; rp = C u + s - d ; re = E u - e
@@ -536,6 +537,11 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         }
         if (it == P.ipm_max_iter) break;
 
+        // Iterative refinement of the corrector pays for itself only once W = lam / s has spread over many decades: it starts
+        // when mu has fallen to ipm_refine_mu_frac of its first value (measured on 4096 instances: always 32.0 ms, never
+        // 27.7 ms with 0.8 % more unsolved instances)
+        if (it == 0) mu_first = mu;
+        const bool refine_now = mu <= P.ipm_refine_mu_frac * mu_first;
         // scaling W = lam / s (inactive rows keep 0), factorisation
         #pragma unroll 1
         for (int i = tid; i < m; i += nth) S.wv[i] = (S.lam[i] > 0.0) ? S.lam[i] / S.s[i] : 0.0;
@@ -572,7 +578,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             for (int i = tid; i < nu; i += nth) S.du[i] = S.rhs[i];
             chol_solve(S.du);
             // The predictor only steers the centring parameter sigma: it is solved without refinement.
-            for (int rf = 0; rf < (corrector ? P.ipm_refine : 0); ++rf) {
+            for (int rf = 0; rf < ((corrector && refine_now) ? P.ipm_refine : 0); ++rf) {
                 // iterative refinement against K = H + C'WC + E'E/delta applied matrix-free
                 apply_H(S.du, S.tmpn);
                 apply_C(S.du, S.ds);

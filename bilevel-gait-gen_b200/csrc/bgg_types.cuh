@@ -75,6 +75,7 @@ struct Params {
     // interior-point settings (the live reference solver is Clarabel, clarabel_interface.cpp:18-27)
     double ipm_tol_feas, ipm_tol_gap, ipm_eq_delta;
     int32_t ipm_max_iter, ipm_refine;
+    double ipm_refine_mu_frac;   // iterative refinement starts once mu <= this fraction of the first iteration's mu
 };
 
 enum SolveStatus : int32_t {    // mpc::SolveQuality, qp_interface.h:12-22

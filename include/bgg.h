@@ -44,7 +44,8 @@ typedef struct bgg_config {
     int32_t device;           /* CUDA device ordinal */
     int32_t ipm_max_iter;     /* 0 = default 50 */
     int32_t ipm_refine;       /* iterative-refinement steps per Newton solve (default 1; negative = 0) */
-    int32_t reserved_;
+    int32_t ipm_refine_after; /* refine only once the complementarity gap mu has fallen below 10^-k of its first value, k = this field
+                                 (0: library default 4; negative: refine from the first iteration) */
     double integrator_dt;
     double friction_coef;
     double force_bound;
