@@ -176,12 +176,12 @@ static __device__ __forceinline__ void ipm_apply_H(const IpmCtx& c, const double
     l2_apply_H(c.Hg, c.nu, smem_addr(v), smem_addr(out));   // csrc/bgg_l2ops.cuh
 }
 
-// out = E v - e (or E v when with_rhs == false)
-static __device__ __forceinline__ void ipm_apply_E(const IpmCtx& c, const double* v, double* out, bool with_rhs) {
+// out = E v - e (or E v when with_rhs == false).  The two equality-row operators take scalars only and are out of line:
+// nine call sites per Newton iteration, one copy in the binary.
+static __device__ __noinline__ void ipm_apply_E(const EqRow* eq, int neq, const double* v, double* out, bool with_rhs) {
     const int tid = threadIdx.x;
-    const EqRow* eq = c.eq;
     __builtin_assume(__isShared(v)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(eq));
-    if (tid < c.neq) {
+    if (tid < neq) {
         const EqRow& q = eq[tid];
         double s = with_rhs ? -q.rhs : 0.0;
         for (int i = 0; i < q.cnt; ++i) s += q.w[i] * v[q.col[i]];
@@ -191,12 +191,11 @@ static __device__ __forceinline__ void ipm_apply_E(const IpmCtx& c, const double
 }
 
 // out += scale E' y
-static __device__ __forceinline__ void ipm_add_Et(const IpmCtx& c, const double* y, double* out, double scale) {
-    const int tid = threadIdx.x, neq = c.neq;
-    const EqRow* eq = c.eq;
+static __device__ __noinline__ void ipm_add_Et(const EqRow* eq, int neq, const double* y, double* out, double scale) {
+    const int tid = threadIdx.x;
     __builtin_assume(__isShared(y)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(eq));
     if (tid < kNumEE * 2)   // one thread per (foot, coord): rows of different groups touch different columns
-        #pragma unroll 1
+#pragma unroll 1
         for (int r = 0; r < neq; ++r) {
             const EqRow& q = eq[r];
             if (q.pad != tid) continue;
@@ -368,8 +367,8 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     auto apply_C = [&](const double* v, double* out) { PROF(10); ipm_apply_C(ctx, v, out); PROF(6); };
     auto add_Ct = [&](const double* y, double* out) { PROF(10); ipm_add_Ct(ctx, y, out); PROF(7); };
     auto apply_H = [&](const double* v, double* out) { PROF(10); ipm_apply_H(ctx, v, out); PROF(8); };
-    auto apply_E = [&](const double* v, double* out, bool with_rhs) { PROF(10); ipm_apply_E(ctx, v, out, with_rhs); PROF(9); };
-    auto add_Et = [&](const double* y, double* out, double scale) { PROF(10); ipm_add_Et(ctx, y, out, scale); PROF(9); };
+    auto apply_E = [&](const double* v, double* out, bool with_rhs) { PROF(10); ipm_apply_E(s_eq, neq, v, out, with_rhs); PROF(9); };
+    auto add_Et = [&](const double* y, double* out, double scale) { PROF(10); ipm_add_Et(s_eq, neq, y, out, scale); PROF(9); };
 
     // K = H + C' diag(wv) C + E'E/delta in 8 x 8 blocks in shared memory (csrc/bgg_kkt_mma.cuh), then chol::factor in place.
     const int nb = (nu + 7) >> 3;   // 8 x 8 blocks per side; rows nu .. 8 nb - 1 are padded with the identity
