@@ -513,3 +513,56 @@ def test_controller_three_mode_schedule_follows_the_oracle():
             state[b] = oracles[b].states()[1]
             ee_now[b] = np.array([oracles[b].ee_at(e, t) for e in range(4)])
     assert modes == ["solve", "solve", "solve_and_gait_opt", "line_search", "solve", "solve_and_gait_opt", "line_search"], modes
+
+
+def _run_tool(src, exe):
+    """Build (if needed) and run one of the stand-alone CUDA tools under tools/; returns its stdout."""
+    import os
+    import subprocess
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    exe_path = os.path.join(root, "tools", "bin", exe)
+    src_path = os.path.join(root, "tools", src)
+    if not os.path.exists(exe_path) or os.path.getmtime(exe_path) < os.path.getmtime(src_path):
+        os.makedirs(os.path.dirname(exe_path), exist_ok=True)
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-maxrregcount=128", "-I",
+                        os.path.join(root, "bilevel-gait-gen_b200", "csrc"), "-o", exe_path, src_path], check=True)
+    return subprocess.run([exe_path], check=True, capture_output=True, text=True).stdout
+
+
+def test_block_cholesky_unit():
+    """csrc/bgg_chol.cuh on its own: DMMA factorisation + two-step solves of a 120 x 120 SPD matrix whose entries span eleven
+    decades (the spread of the interior-point KKT matrix), against the host: relative residual of A x = b; and the
+    one-lane factor-and-invert of an 8 x 8 diagonal block: X A X' = I, explicit zeros above the diagonal."""
+    import re
+    out = _run_tool("microbench_chol.cu", "microbench_chol")
+    res = [float(x) for x in re.findall(r"\|Ax-b\|/\|b\| = ([0-9.e+-]+)", out)]
+    flags = [int(x) for x in re.findall(r"flag (\d+)", out)]
+    assert len(res) == 2 and all(r < 1e-5 for r in res), out
+    assert flags == [0, 0], out
+    out = _run_tool("microbench_diag.cu", "microbench_diag")
+    m = re.findall(r"variant 1: .* max \|X A X' - I\| = ([0-9.e+-]+) ; max \|upper\| = ([0-9.e+-]+)", out)
+    assert m and float(m[0][0]) < 1e-4 and float(m[0][1]) == 0.0, out
+    seed = re.findall(r"refined \(rsqrt_fast\): ([0-9.e+-]+)", out)
+    assert seed and float(seed[0]) < 1e-15, out
+
+
+def test_refinement_schedule_does_not_move_the_solution():
+    """bgg_config.ipm_refine_after: refining the corrector only in the late iterations (library default) ends at the same
+    optimum as refining from the first iteration, and as never refining on instances that solve either way."""
+    cfg_name = "a1_configuration"
+    cfg = wl.CONFIGS[cfg_name]
+    B = 16
+    states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=7)
+    sols, stats = {}, {}
+    for key, kw in (("late", {}), ("always", dict(ipm_refine_after=-1)), ("never", dict(ipm_refine=-1))):
+        gpu = common.make_gpu(cfg_name, B, states, **kw)
+        out = gpu.GetRealTimeUpdate(states, t0, ee)
+        sols[key] = np.stack([gpu.solution(b)["qp_sol"] for b in range(B)])
+        stats[key] = out["status"].copy()
+    both = (stats["late"] == 0) & (stats["always"] == 0)
+    assert both.sum() >= B // 2
+    for b in np.where(both)[0]:
+        assert _rel(sols["late"][b], sols["always"][b]) < 1e-5
+    three = both & (stats["never"] == 0)
+    for b in np.where(three)[0]:
+        assert _rel(sols["never"][b], sols["always"][b]) < 1e-4
