@@ -241,15 +241,34 @@ __device__ inline void kkt_mma_setup(KktWork* work, int* nwork_shared, int nb, K
                 w.rowB = static_cast<uint8_t>(p); w.jB0 = 0; w.lenB = static_cast<uint8_t>((p == nb - 1 - p) ? 0 : p + 1);
                 work[n++] = w;
             }
-        } else {                   // one row segment of at most kAccMax blocks per item
-            for (int r = nb - 1; r >= 0; --r)
-                for (int j0 = 0; j0 <= r; j0 += kAccMax) {
-                    KktWork w;
-                    w.rowA = static_cast<uint8_t>(r); w.jA0 = static_cast<uint8_t>(j0);
-                    w.lenA = static_cast<uint8_t>((r + 1 - j0 < kAccMax) ? r + 1 - j0 : kAccMax);
-                    w.rowB = 0; w.jB0 = 0; w.lenB = 0;
-                    work[n++] = w;
-                }
+        } else {                   // row segments of at most kAccMax blocks, packed two to an item: longest first, each with
+                                   // the longest remaining segment that still fits (nb = 19: 13 items instead of 22)
+            uint8_t srow[kMaxKktWork], sj0[kMaxKktWork], slen[kMaxKktWork];
+            bool used[kMaxKktWork];
+            int ns = 0;
+            for (int len = kAccMax; len >= 1; --len)       // descending by length
+                for (int r = nb - 1; r >= 0; --r)
+                    for (int j0 = 0; j0 <= r; j0 += kAccMax) {
+                        const int l = (r + 1 - j0 < kAccMax) ? r + 1 - j0 : kAccMax;
+                        if (l == len && ns < kMaxKktWork) {
+                            srow[ns] = static_cast<uint8_t>(r); sj0[ns] = static_cast<uint8_t>(j0); slen[ns] = static_cast<uint8_t>(l);
+                            used[ns++] = false;
+                        }
+                    }
+            for (int a = 0; a < ns; ++a) {
+                if (used[a]) continue;
+                used[a] = true;
+                KktWork w;
+                w.rowA = srow[a]; w.jA0 = sj0[a]; w.lenA = slen[a];
+                w.rowB = 0; w.jB0 = 0; w.lenB = 0;
+                for (int c = a + 1; c < ns; ++c)
+                    if (!used[c] && slen[a] + slen[c] <= kAccMax) {
+                        used[c] = true;
+                        w.rowB = srow[c]; w.jB0 = sj0[c]; w.lenB = slen[c];
+                        break;
+                    }
+                work[n++] = w;
+            }
         }
         *nwork_shared = n;
     }
