@@ -477,15 +477,21 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         qp_obj = pobj;
         add_Ct(S.lam, S.rd);
         add_Et(S.nueq, S.rd, 1.0);
-        apply_C(S.u, S.rp);
-        apply_E(S.u, S.re, true);
+        // The primal residuals rp = C u + s - d and re = E u - e are linear in the iterate and the Newton step satisfies
+        // C du + ds = -rp, E du = delta dnu - re by construction: after a step of length alpha they are (1 - alpha) rp and
+        // re + alpha (delta dnu - re) to rounding, so they are updated with the step and recomputed from scratch only at the
+        // first iteration and to confirm convergence (two structured products and their barriers less per iteration).
+        if (it == 0) {
+            apply_C(S.u, S.rp);
+            apply_E(S.u, S.re, true);
+        }
         double a = 0, c = 0, dsum = 0;
         #pragma unroll 1
         for (int i = tid; i < nu; i += nth) a = fmax(a, fabs(S.rd[i]));
         #pragma unroll 1
         for (int i = tid; i < m; i += nth) {
             if (S.lam[i] > 0.0) {   // active row (inactive rows keep lam == 0 exactly)
-                S.rp[i] = S.rp[i] + S.s[i] - rhs_of(i);
+                if (it == 0) S.rp[i] = S.rp[i] + S.s[i] - rhs_of(i);
                 c = fmax(c, fabs(S.rp[i]));
                 dsum += S.s[i] * S.lam[i];
             } else {
@@ -531,8 +537,31 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         last_mu = mu;
         if (n_rd <= P.ipm_tol_feas * nrm_q && n_rp <= P.ipm_tol_feas * nrm_d && n_re <= P.ipm_tol_feas * nrm_d &&
             dsum <= P.ipm_tol_gap * gap_scale) {
-            status = kSolved;
-            break;
+            bool confirmed = true;
+            if (it > 0) {   // confirm with primal residuals computed from scratch; they replace the updated ones either way
+                apply_C(S.u, S.rp);
+                apply_E(S.u, S.re, true);
+                double cf = 0;
+#pragma unroll 1
+                for (int i = tid; i < m; i += nth) {
+                    if (S.lam[i] > 0.0) {
+                        S.rp[i] = S.rp[i] + S.s[i] - rhs_of(i);
+                        cf = fmax(cf, fabs(S.rp[i]));
+                    } else {
+                        S.rp[i] = 0.0;
+                    }
+                }
+                n_rp = block_reduce<kMax>(cf, S.red);
+                n_re = 0;
+                for (int r = 0; r < neq; ++r) n_re = fmax(n_re, fabs(S.re[r]));
+                last_rp = n_rp;
+                last_re = n_re;
+                confirmed = n_rp <= P.ipm_tol_feas * nrm_d && n_re <= P.ipm_tol_feas * nrm_d;
+            }
+            if (confirmed) {
+                status = kSolved;
+                break;
+            }
         }
         if (it == P.ipm_max_iter) break;
 
@@ -646,8 +675,12 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             if (S.wv[i] != 0.0) {
                 S.s[i] += alpha * S.ds[i];
                 S.lam[i] += alpha * S.dl[i];
+                S.rp[i] *= 1.0 - alpha;
             }
-        if (tid < neq) S.nueq[tid] += alpha * S.dnu[tid];
+        if (tid < neq) {
+            S.nueq[tid] += alpha * S.dnu[tid];
+            S.re[tid] += alpha * (delta * S.dnu[tid] - S.re[tid]);
+        }
         __syncthreads();
     }
     // Exit classification when the iteration stopped without meeting the tolerances (iteration limit, or a
