@@ -523,8 +523,14 @@ def _run_tool(src, exe):
     exe_path = os.path.join(root, "tools", "bin", exe)
     src_path = os.path.join(root, "tools", src)
     if not os.path.exists(exe_path) or os.path.getmtime(exe_path) < os.path.getmtime(src_path):
+        import shutil
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        if not os.path.exists(nvcc):
+            if os.path.exists(exe_path):
+                return subprocess.run([exe_path], check=True, capture_output=True, text=True).stdout
+            pytest.skip("nvcc not found and the tool is not built (python -c 'import __graft_entry__ as g; g.build()')")
         os.makedirs(os.path.dirname(exe_path), exist_ok=True)
-        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-maxrregcount=128", "-I",
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-maxrregcount=128", "-I",
                         os.path.join(root, "bilevel-gait-gen_b200", "csrc"), "-o", exe_path, src_path], check=True)
     return subprocess.run([exe_path], check=True, capture_output=True, text=True).stdout
 
