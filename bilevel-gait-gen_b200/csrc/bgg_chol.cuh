@@ -9,10 +9,11 @@
 //     holds entries [g][2t], [g][2t+1].  With the contraction index permuted (first DMMA k = {0,2,4,6}, second
 //     k = {1,3,5,7}) this one layout is the A fragment of P, the B fragment of Q' in P Q', and the C fragment -- so a
 //     product that has just been accumulated feeds the next DMMA from registers, no shuffles and no shared-memory trip;
-//   * left-looking by block columns with look-ahead: while warp 0 factors and inverts the 8 x 8 diagonal block of
-//     column j (the only serial chain: one lane, eight pivots), warps 1.. apply columns < j to column j + 1; after the
-//     barrier every warp multiplies its rows of column j by the inverted block (a DMMA, not a substitution) and applies
-//     column j to column j + 1.  Two barriers per block column.
+//   * left-looking by block columns with look-ahead: warp 0 runs the chain of 8 x 8 diagonal blocks (the only serial
+//     part: one lane, eight pivots per block, factor and inverse in registers) with nothing but its own block row
+//     between two of them; warps 1.. multiply their rows of column j by the inverted block (a DMMA, not a
+//     substitution), apply column j to column j + 1 and, after a barrier among themselves, columns <= j to column
+//     j + 2.  One CTA-wide barrier per block column.
 //   * the inverses of the diagonal blocks are then merged in place into inverses of 64 x 64 diagonal super-blocks, so
 //     that a triangular solve is two (not 120, not 15) dependent steps of warp-per-block-row mat-vecs.
 // The first stage of the recursion K -> L is the textbook one; nothing here follows reference code (the reference
@@ -207,29 +208,60 @@ static __device__ __noinline__ void factor(double* K, int nb, int* flag) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
     if (tid == 0) *flag = 0;
     __syncthreads();
-    double2 keep = make_double2(0.0, 0.0);   // warp 0: L(j, j-1), stored one phase late (the others still read C(j, j-1))
+    // Column j, between two CTA-wide barriers:
+    //   warp 0      : L(j+1, j) = C(j+1, j) inv(L_jj)', C(j+1, j+1) -= L(j+1, j) L(j+1, j)', then the serial step -- factor and
+    //                 invert the diagonal block (j+1, j+1) -- without waiting for anybody;
+    //   warps 1 ..  : the rows below, L(i, j) = C(i, j) inv(L_jj)' and column j applied to column j+1 (each recomputes
+    //                 L(j+1, j) instead of waiting for warp 0), a barrier among themselves, then the look-ahead: columns
+    //                 <= j applied to column j+2.
+    // The chain of 8 x 8 diagonal factorisations is the critical path; nothing but one small block row sits between two of them.
+    double2 keep = make_double2(0.0, 0.0);   // warp 0: L(j+1, j), stored one column late (the others still read C(j+1, j))
     CPROF_DECL
-    for (int j = 0; j < nb; ++j) {
-        // ---- phase 1: diagonal block (warp 0)  ||  columns < j applied to column j + 1 (other warps)
+    if (wid == 0 && factor_invert_diag(K + blk(0, 0), lane)) *flag = 1;
+    __syncthreads();
+    const int nother = (nwarp - 1) * 32;
+    for (int j = 0; j + 1 < nb; ++j) {
+        const double2 X = ldfrag(K + blk(j, j), lane);
+        double2 Lj1 = make_double2(0.0, 0.0);
+        mma_pqT(Lj1, ldfrag(K + blk(j + 1, j), lane), X);
         if (wid == 0) {
             if (j > 0) stfrag(K + blk(j, j - 1), lane, keep);
+            keep = Lj1;
+            double2 upd = make_double2(0.0, 0.0);
+            mma_pqT(upd, Lj1, Lj1);
+            double2 c = ldfrag(K + blk(j + 1, j + 1), lane);
+            c.x -= upd.x;
+            c.y -= upd.y;
+            stfrag(K + blk(j + 1, j + 1), lane, c);
             __syncwarp();
-            if (factor_invert_diag(K + blk(j, j), lane)) *flag = 1;
+            if (factor_invert_diag(K + blk(j + 1, j + 1), lane)) *flag = 1;
             CPROF(0);
-        } else if (j >= 1 && j + 1 < nb) {
-            const int jc = j + 1;
-            for (int i = jc + wid - 1; i < nb; i += nwarp - 1) {
+        } else {
+            for (int i = j + 2 + (wid - 1); i < nb; i += nwarp - 1) {
+                double2 Lij = make_double2(0.0, 0.0);
+                mma_pqT(Lij, ldfrag(K + blk(i, j), lane), X);
+                stfrag(K + blk(i, j), lane, Lij);
+                double2 upd = make_double2(0.0, 0.0);
+                mma_pqT(upd, Lij, Lj1);
+                double2 c = ldfrag(K + blk(i, j + 1), lane);
+                c.x -= upd.x;
+                c.y -= upd.y;
+                stfrag(K + blk(i, j + 1), lane, c);
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(nother) : "memory");   // column j complete among warps 1 ..
+            const int jc = j + 2;
+            for (int i = jc + (wid - 1); i < nb; i += nwarp - 1) {   // look-ahead: columns 0 .. j applied to column j + 2
                 double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
                 const double* Li = K + blk(i, 0);
                 const double* Lj = K + blk(jc, 0);
                 int k = 0;
-                for (; k + 1 < j; k += 2) {
+                for (; k + 1 <= j; k += 2) {
                     const double2 p0 = ldfrag(Li + (k << 6), lane), q0 = ldfrag(Lj + (k << 6), lane);
                     const double2 p1 = ldfrag(Li + ((k + 1) << 6), lane), q1 = ldfrag(Lj + ((k + 1) << 6), lane);
                     mma_pqT(a0, p0, q0);
                     mma_pqT(a1, p1, q1);
                 }
-                if (k < j) mma_pqT(a0, ldfrag(Li + (k << 6), lane), ldfrag(Lj + (k << 6), lane));
+                if (k <= j) mma_pqT(a0, ldfrag(Li + (k << 6), lane), ldfrag(Lj + (k << 6), lane));
                 double2 c = ldfrag(Li + (jc << 6), lane);
                 c.x -= a0.x + a1.x;
                 c.y -= a0.y + a1.y;
@@ -238,32 +270,10 @@ static __device__ __noinline__ void factor(double* K, int nb, int* flag) {
         }
         __syncthreads();
         CPROF(1);
-        if (j + 1 >= nb) break;
-        // ---- phase 2: L(i, j) = C(i, j) inv(L_jj)' for the rows below, then column j applied to column j + 1
-        const double2 X = ldfrag(K + blk(j, j), lane);
-        double2 Lj1 = make_double2(0.0, 0.0);
-        mma_pqT(Lj1, ldfrag(K + blk(j + 1, j), lane), X);
-        for (int i = j + 1 + wid; i < nb; i += nwarp) {
-            double2 Lij;
-            if (i == j + 1) {
-                Lij = Lj1;
-                keep = Lj1;   // i == j + 1 belongs to warp 0
-            } else {
-                Lij = make_double2(0.0, 0.0);
-                mma_pqT(Lij, ldfrag(K + blk(i, j), lane), X);
-                stfrag(K + blk(i, j), lane, Lij);
-            }
-            double2 upd = make_double2(0.0, 0.0);
-            mma_pqT(upd, Lij, Lj1);
-            double2 c = ldfrag(K + blk(i, j + 1), lane);
-            c.x -= upd.x;
-            c.y -= upd.y;
-            stfrag(K + blk(i, j + 1), lane, c);
-        }
-        CPROF(2);
-        __syncthreads();
-        CPROF(3);
     }
+    if (wid == 0 && nb > 1) stfrag(K + blk(nb - 1, nb - 2), lane, keep);
+    __syncthreads();
+    CPROF(4);
     // ---- inverses of the 16 x 16, 32 x 32, 64 x 64 diagonal super-blocks, in place over L's blocks inside them.
     // Level h (half size in blocks): group q covers blocks [2hq, 2hq + 2h); with X11, X22 the inverses of its two halves
     //   X21 = -X22 (L21 X11)
