@@ -185,7 +185,7 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
 
     res.status = MaxIter;
     int it = 0;
-    double n_rd = 0, n_rp = 0, n_re = 0, mu = 0, gscale = 1, last_rp = 0, last_re = 0, last_rd = 0, last_mu = 0;
+    double n_rd = 0, n_rp = 0, n_re = 0, mu = 0, gscale = 1, last_rp = 0, last_re = 0, last_rd = 0, last_mu = 0, rp_ref = 0;
     for (it = 0; it <= st.max_iter; it++) {
         P.mul(z.data(), Pz.data());
         double pobj = 0;
@@ -221,6 +221,18 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
         if (n_rd <= st.tol_feas * nrm_q && n_rp <= st.tol_feas * nrm_b && n_re <= st.tol_feas * nrm_b && sdl <= st.tol_gap * gscale) {
             res.status = Solved;
             break;
+        }
+        // Early exit on a stalled primal residual (stands in for the infeasibility certificate of Clarabel's homogeneous
+        // embedding, which stops an infeasible QP long before the iteration limit): the primal residual shrinks by exactly
+        // (1 - alpha) per step, so less than 10 % over ten iterations while it is still far from feasible means the
+        // steps have collapsed.  Same rule as csrc/bgg_ipm.cu.
+        {
+            const double prim = std::max(n_rp, n_re);
+            if (it == 0) rp_ref = prim;
+            if (it > 0 && it % 10 == 0) {
+                if (prim > 1e3 * st.tol_feas * nrm_b && prim >= 0.9 * rp_ref) break;   // classified below (PrimalInfeasible)
+                rp_ref = prim;
+            }
         }
         if (it == st.max_iter) break;
         for (int r = 0; r < mi; r++) W[r] = lam[r] / s[r];
