@@ -572,3 +572,41 @@ def test_refinement_schedule_does_not_move_the_solution():
     three = both & (stats["never"] == 0)
     for b in np.where(three)[0]:
         assert _rel(sols["never"][b], sols["always"][b]) < 1e-4
+
+
+def test_full_size_disturbance_sweep_properties():
+    """BASELINE config #5 at a size the oracle cannot follow (2048 closed-loop scenarios, N = 50, 45 ticks = 0.9 s: the horizon
+    slides over a touch-down, knots are appended and dropped, nu grows from 120 to 148, i.e. beyond 15 block rows of the
+    KKT matrix): size-independent properties -- every tick nearly all scenarios solve, no instance reports a
+    structural error, times advance by one node per tick, states stay finite, and the disturbance is rejected: the
+    lateral momentum the scenarios start with decays."""
+    cfg_name = "a1_config_distr_rejection"
+    cfg = wl.CONFIGS[cfg_name]
+    B, T, dt = 2048, 45, cfg["integrator_dt"]
+    states, t0, ee = wl.disturbance_sweep_inputs(cfg, B, seed=9)
+    gpu = common.make_gpu(cfg_name, B, states)
+    gpu.upload(states, t0, ee)
+    gpu.solve_resident()
+    first = gpu.download()
+    nus = set()
+    mom0 = np.linalg.norm(states[:, 3:5], axis=1)
+    for tick in range(T):
+        gpu.advance_plant(dt)
+        gpu.solve_resident()
+        out = gpu.download()
+        ok = np.isin(out["status"], (0, 1))
+        assert ok.mean() > 0.95, (tick, np.bincount(out["status"], minlength=9).tolist())
+        assert np.all(np.isfinite(out["cost"][ok]))
+        if tick % 5 == 4:
+            for b in (0, B // 2, B - 1):
+                sz = gpu.sizes(b)
+                assert sz["error"] == 0
+                nus.add(sz["nu"])
+    assert len(nus) > 1 and max(nus) > 120, nus
+    mom = []
+    for b in range(0, B, 64):
+        assert abs(gpu.get_instance(b)["init_time"] - T * dt) < 1e-12
+        x = gpu.GetStates(b)
+        assert np.all(np.isfinite(x))
+        mom.append(np.linalg.norm(x[0, 3:5]))
+    assert np.median(mom) < 0.85 * np.median(mom0), (np.median(mom), np.median(mom0))
