@@ -29,23 +29,52 @@ RowView ToRows(const Csc& A) {
     return r;
 }
 
-// Envelope LDL' of a symmetric quasi-definite matrix stored densely (lower triangle), row i zero left of first[i].
+// dot product with four independent partial sums (fixed association order; lets the compiler keep the loop in SIMD
+// registers without -ffast-math); AVX2 clone selected at load time where the host has it
+__attribute__((target_clones("avx2", "default"))) double Dot4(const double* a, const double* b, int n) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int k = 0;
+    for (; k + 4 <= n; k += 4) {
+        s0 += a[k] * b[k];
+        s1 += a[k + 1] * b[k + 1];
+        s2 += a[k + 2] * b[k + 2];
+        s3 += a[k + 3] * b[k + 3];
+    }
+    for (; k < n; k++) s0 += a[k] * b[k];
+    return (s0 + s1) + (s2 + s3);
+}
+
+// Envelope LDL' of a symmetric quasi-definite matrix: row i holds columns first[i] .. i-1 (ragged storage, so that
+// re-assembly and factorisation touch the envelope only) and the diagonal separately.
 struct ProfileLdl {
     int n = 0;
-    Vec L, D;
     std::vector<int> first;
-    bool Factor() {
+    std::vector<size_t> off;
+    Vec L, D, diag;
+    void SetPattern(const std::vector<int>& f) {
+        n = static_cast<int>(f.size());
+        first = f;
+        off.assign(n + 1, 0);
+        for (int i = 0; i < n; i++) off[i + 1] = off[i] + static_cast<size_t>(i - first[i]);
+        L.assign(off[n], 0.0);
         D.assign(n, 0.0);
+        diag.assign(n, 0.0);
+    }
+    void Clear() {
+        std::fill(L.begin(), L.end(), 0.0);
+        std::fill(diag.begin(), diag.end(), 0.0);
+    }
+    double& At(int i, int j) { return (i == j) ? diag[i] : L[off[i] + (j - first[i])]; }   // i >= j >= first[i]
+    bool Factor() {
         Vec tmp(n);
         for (int i = 0; i < n; i++) {
-            double* Li = &L[static_cast<size_t>(i) * n];
+            double* Li = &L[off[i]] - first[i];
             for (int j = first[i]; j < i; j++) {
-                const double* Lj = &L[static_cast<size_t>(j) * n];
-                double s = Li[j];
-                for (int k = std::max(first[i], first[j]); k < j; k++) s -= tmp[k] * Lj[k];
-                tmp[j] = s;            // = L_ij * D_j
+                const double* Lj = &L[off[j]] - first[j];
+                const int k0 = std::max(first[i], first[j]);
+                tmp[j] = Li[j] - Dot4(&tmp[k0], Lj + k0, j - k0);            // = L_ij * D_j
             }
-            double d = Li[i];
+            double d = diag[i];
             for (int j = first[i]; j < i; j++) {
                 const double lij = tmp[j] / D[j];
                 d -= lij * tmp[j];
@@ -58,14 +87,12 @@ struct ProfileLdl {
     }
     void Solve(double* b) const {
         for (int i = 0; i < n; i++) {
-            const double* Li = &L[static_cast<size_t>(i) * n];
-            double s = b[i];
-            for (int k = first[i]; k < i; k++) s -= Li[k] * b[k];
-            b[i] = s;
+            const double* Li = &L[off[i]] - first[i];
+            b[i] -= Dot4(Li + first[i], b + first[i], i - first[i]);
         }
         for (int i = 0; i < n; i++) b[i] /= D[i];
         for (int i = n - 1; i >= 0; i--) {
-            const double* Li = &L[static_cast<size_t>(i) * n];
+            const double* Li = &L[off[i]] - first[i];
             const double xi = b[i];
             for (int k = first[i]; k < i; k++) b[k] -= Li[k] * xi;
         }
@@ -76,8 +103,23 @@ double NormInf(const Vec& v) {
     for (double x : v) m = std::max(m, std::abs(x));
     return m;
 }
+double Dot(const Vec& a, const Vec& b) {
+    double s = 0;
+    for (size_t i = 0; i < a.size(); i++) s += a[i] * b[i];
+    return s;
+}
 }  // namespace
 
+// Homogeneous self-dual embedding, as Clarabel (Goulart & Chen 2024, sections 2-3) restricted to Zero / Nonnegative cones:
+//   P x + A'y + q tau = 0 ,  A x + s - b tau = 0 ,  kappa + q'x + b'y + x'Px / tau = 0 ,  s o z = mu ,  tau kappa = mu
+// (y = all multipliers, z = its Nonnegative part).  Per iteration one factorisation of the reduced quasi-definite matrix
+//   [ P + eps I + A_I' W A_I , A_E' ; A_E , -delta I ] ,   W = 1 / (s/z + eps)
+// (eps, delta: Clarabel's static regularisation, here folded into the eliminated cone block), three solves with it -- the
+// constant right-hand side (-q ; b), the affine and the combined step -- each followed by `refine` steps of iterative
+// refinement against the UNREGULARISED system, sigma = (1 - alpha_aff)^3, step fraction 0.99.  Termination on the
+// de-homogenised point; a primal infeasibility certificate is b'y < 0 with A'y ~ 0 (Clarabel's is_primal_infeasible).
+// The QP here is strictly convex (mpc.cpp:1090-1095 adds 1e-3 I), so the dual-infeasible branch is not restated.
+// csrc/bgg_ipm.cu runs the same iteration on the condensed QP.
 IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const std::vector<char>& is_eq,
                    const std::vector<int>& order, const IpmSettings& st) {
     const int n = P.cols, m = A.rows;
@@ -101,22 +143,39 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
         for (int k = 0; k < D; k++) pos[order[k]] = k;
     }
     ProfileLdl F;
-    F.n = D;
-    F.L.assign(static_cast<size_t>(D) * D, 0.0);
-    F.first.assign(D, 0);
+    {   // symbolic pass: envelope of the permuted matrix
+        std::vector<int> first(D);
+        std::iota(first.begin(), first.end(), 0);
+        auto touch = [&](int a, int c) {
+            const int pa = pos[a], pc = pos[c];
+            const int i = std::max(pa, pc), j = std::min(pa, pc);
+            first[i] = std::min(first[i], j);
+        };
+        for (int j = 0; j < n; j++)
+            for (int k = P.colptr[j]; k < P.colptr[j + 1]; k++) touch(P.rowidx[k], j);
+        for (int r = 0; r < mi; r++) {
+            const int i = in_rows[r];
+            for (int a = R.ptr[i]; a < R.ptr[i + 1]; a++)
+                for (int c = R.ptr[i]; c <= a; c++) touch(R.col[a], R.col[c]);
+        }
+        for (int e = 0; e < me; e++) {
+            const int i = eq_rows[e];
+            for (int a = R.ptr[i]; a < R.ptr[i + 1]; a++) touch(n + e, R.col[a]);
+        }
+        F.SetPattern(first);
+    }
     auto at = [&](int a, int c) -> double& {
         const int pa = pos[a], pc = pos[c];
-        const int i = std::max(pa, pc), j = std::min(pa, pc);
-        F.first[i] = std::min(F.first[i], j);
-        return F.L[static_cast<size_t>(i) * D + j];
+        return F.At(std::max(pa, pc), std::min(pa, pc));
     };
-    Vec W(mi, 1.0);
+    Vec W(mi, 1.0), Dg(mi, 1.0);
     auto build_and_factor = [&]() -> bool {
-        std::fill(F.L.begin(), F.L.end(), 0.0);
-        for (int i = 0; i < D; i++) F.first[i] = i;
-        for (int j = 0; j < n; j++)
+        F.Clear();
+        for (int j = 0; j < n; j++) {
             for (int k = P.colptr[j]; k < P.colptr[j + 1]; k++)
                 if (P.rowidx[k] >= j) at(P.rowidx[k], j) += P.val[k];
+            at(j, j) += st.eps;
+        }
         for (int r = 0; r < mi; r++) {
             const int i = in_rows[r];
             for (int a = R.ptr[i]; a < R.ptr[i + 1]; a++)
@@ -129,15 +188,6 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
         }
         return F.Factor();
     };
-    // solve the quasi-definite system for right-hand side (r1 ; r2) in natural unknown order
-    Vec work(D);
-    auto kkt_solve = [&](const Vec& r1, const Vec& r2, Vec& dz, Vec& dnu) {
-        for (int j = 0; j < n; j++) work[pos[j]] = r1[j];
-        for (int e = 0; e < me; e++) work[pos[n + e]] = r2[e];
-        F.Solve(work.data());
-        for (int j = 0; j < n; j++) dz[j] = work[pos[j]];
-        for (int e = 0; e < me; e++) dnu[e] = work[pos[n + e]];
-    };
     auto rowdot = [&](int i, const Vec& v) {
         double s = 0;
         for (int k = R.ptr[i]; k < R.ptr[i + 1]; k++) s += R.val[k] * v[R.col[k]];
@@ -146,175 +196,188 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
     auto add_rowT = [&](int i, double coef, Vec& out) {
         for (int k = R.ptr[i]; k < R.ptr[i + 1]; k++) out[R.col[k]] += coef * R.val[k];
     };
+    // Solve   P dx + A_I'dz + A_E'dy = a1 ,  A_I dx - Dg dz = a2 ,  A_E dx = a3   (Dg = s / z): regularised factorisation,
+    // then refinement against the system as written.
+    Vec work(D), t1(n), cx(n), cz(mi), cy(me), e1(n), e2(mi), e3(me);
+    auto reg_solve = [&](const Vec& a1, const Vec& a2, const Vec& a3, Vec& dx, Vec& dz, Vec& dy) {
+        t1 = a1;
+        for (int r = 0; r < mi; r++) add_rowT(in_rows[r], W[r] * a2[r], t1);
+        for (int j = 0; j < n; j++) work[pos[j]] = t1[j];
+        for (int e = 0; e < me; e++) work[pos[n + e]] = a3[e];
+        F.Solve(work.data());
+        for (int j = 0; j < n; j++) dx[j] = work[pos[j]];
+        for (int e = 0; e < me; e++) dy[e] = work[pos[n + e]];
+        for (int r = 0; r < mi; r++) dz[r] = W[r] * (rowdot(in_rows[r], dx) - a2[r]);
+    };
+    auto kkt_solve = [&](const Vec& a1, const Vec& a2, const Vec& a3, Vec& dx, Vec& dz, Vec& dy) {
+        reg_solve(a1, a2, a3, dx, dz, dy);
+        for (int rf = 0; rf < st.refine; rf++) {
+            P.mul(dx.data(), e1.data());
+            for (int r = 0; r < mi; r++) add_rowT(in_rows[r], dz[r], e1);
+            for (int e = 0; e < me; e++) add_rowT(eq_rows[e], dy[e], e1);
+            for (int j = 0; j < n; j++) e1[j] = a1[j] - e1[j];
+            for (int r = 0; r < mi; r++) e2[r] = a2[r] - (rowdot(in_rows[r], dx) - Dg[r] * dz[r]);
+            for (int e = 0; e < me; e++) e3[e] = a3[e] - rowdot(eq_rows[e], dx);
+            reg_solve(e1, e2, e3, cx, cz, cy);
+            for (int j = 0; j < n; j++) dx[j] += cx[j];
+            for (int r = 0; r < mi; r++) dz[r] += cz[r];
+            for (int e = 0; e < me; e++) dy[e] += cy[e];
+        }
+    };
 
     IpmResult res;
-    Vec z(n, 0.0), s(mi), lam(mi), nu(me, 0.0), dz(n), dnu(me), ds(mi), dl(mi), rd(n), rp(mi), re(me), rc(mi), r1(n), r2(me), Pz(n);
-    // ---- starting point: W = I
+    Vec x(n, 0.0), s(mi), z(mi), y(me, 0.0), Px(n), rx(n), rz(mi), re(me);
+    Vec x1(n), z1(mi), y1(me), x2(n), z2(mi), y2(me), dx(n), dz(mi), dy(me), ds(mi), a1(n), a2(mi), a3(me);
+    Vec bi(mi), be(me), mq(n);
+    for (int r = 0; r < mi; r++) bi[r] = b[in_rows[r]];
+    for (int e = 0; e < me; e++) be[e] = b[eq_rows[e]];
+    for (int j = 0; j < n; j++) mq[j] = -q[j];
+    // ---- starting point (Clarabel's QP initialisation): unit scaling, s = -z, both shifted into the cone
     if (!build_and_factor()) {
         res.status = Other;
         return res;
     }
-    for (int j = 0; j < n; j++) r1[j] = -q[j];
-    for (int r = 0; r < mi; r++) add_rowT(in_rows[r], b[in_rows[r]], r1);
-    for (int e = 0; e < me; e++) r2[e] = b[eq_rows[e]];
-    kkt_solve(r1, r2, z, nu);
-    std::fill(nu.begin(), nu.end(), 0.0);
-    double mn = 1e300;
-    for (int r = 0; r < mi; r++) {
-        s[r] = b[in_rows[r]] - rowdot(in_rows[r], z);
-        mn = std::min(mn, s[r]);
-    }
-    const double shift = std::max(0.0, -1.5 * mn);
-    double xi = 0, sl = 0, ss = 0;
-    for (int r = 0; r < mi; r++) {
-        const double v = std::max(s[r] + shift, 1e-2);
-        s[r] = lam[r] = v;
-        xi += v * v;
-        sl += v;
-    }
-    for (int r = 0; r < mi; r++) {
-        s[r] += 0.5 * xi / sl;
-        ss += s[r];
-    }
-    for (int r = 0; r < mi; r++) lam[r] += 0.5 * xi / ss;
+    kkt_solve(mq, bi, be, x, z, y);
+    auto shift = [&](Vec& v) {
+        double mn = 1e300;
+        for (double e : v) mn = std::min(mn, e);
+        if (mn < 1e-8)
+            for (double& e : v) e += 1.0 - mn;
+    };
+    for (int r = 0; r < mi; r++) s[r] = -z[r];
+    shift(s);
+    shift(z);
+    double tau = 1.0, kap = 1.0;
 
     const double nrm_q = std::max(1.0, NormInf(q));
-    double nrm_b = 1.0;
-    for (int r = 0; r < mi; r++) nrm_b = std::max(nrm_b, std::abs(b[in_rows[r]]));
-    for (int e = 0; e < me; e++) nrm_b = std::max(nrm_b, std::abs(b[eq_rows[e]]));
-
+    const double nrm_b = std::max(1.0, NormInf(b));
     res.status = MaxIter;
     int it = 0;
-    double n_rd = 0, n_rp = 0, n_re = 0, mu = 0, gscale = 1, last_rp = 0, last_re = 0, last_rd = 0, last_mu = 0, rp_ref = 0;
+    double res_p = 0, res_d = 0, gap = 0, gscale = 1, bz = 0, aty = 0, ynorm = 1;
+    bool have_point = false;
+    Vec xg, zg, yg, sg;
+    double taug = 1.0;
     for (it = 0; it <= st.max_iter; it++) {
-        P.mul(z.data(), Pz.data());
-        double pobj = 0;
-        for (int j = 0; j < n; j++) {
-            pobj += z[j] * (0.5 * Pz[j] + q[j]);
-            rd[j] = Pz[j] + q[j];
-        }
-        for (int r = 0; r < mi; r++) add_rowT(in_rows[r], lam[r], rd);
-        for (int e = 0; e < me; e++) add_rowT(eq_rows[e], nu[e], rd);
-        double sdl = 0;
-        for (int r = 0; r < mi; r++) {
-            rp[r] = rowdot(in_rows[r], z) + s[r] - b[in_rows[r]];
-            sdl += s[r] * lam[r];
-        }
-        for (int e = 0; e < me; e++) re[e] = rowdot(eq_rows[e], z) - b[eq_rows[e]];
-        n_rd = NormInf(rd);
-        n_rp = NormInf(rp);
-        n_re = NormInf(re);
-        mu = mi ? sdl / mi : 0.0;
-        gscale = std::max(1.0, std::abs(pobj));
-        if (n_rd != n_rd || n_rp != n_rp || mu != mu) {
+        P.mul(x.data(), Px.data());
+        const double xPx = Dot(x, Px);
+        for (int j = 0; j < n; j++) rx[j] = Px[j] + q[j] * tau;
+        Vec aty_v(n, 0.0);
+        for (int r = 0; r < mi; r++) add_rowT(in_rows[r], z[r], aty_v);
+        for (int e = 0; e < me; e++) add_rowT(eq_rows[e], y[e], aty_v);
+        for (int j = 0; j < n; j++) rx[j] += aty_v[j];
+        for (int r = 0; r < mi; r++) rz[r] = rowdot(in_rows[r], x) + s[r] - bi[r] * tau;
+        for (int e = 0; e < me; e++) re[e] = rowdot(eq_rows[e], x) - be[e] * tau;
+        const double qx = Dot(q, x);
+        bz = Dot(bi, z) + Dot(be, y);
+        const double rt = kap + qx + bz + xPx / tau;
+        const double mu = (Dot(s, z) + tau * kap) / (mi + 1);
+        const double pc = (0.5 * xPx / tau + qx) / tau, dc = (-bz - 0.5 * xPx / tau) / tau;
+        res_p = std::max(NormInf(rz), NormInf(re)) / tau;
+        res_d = NormInf(rx) / tau;
+        gap = std::abs(pc - dc);
+        gscale = std::max(1.0, std::min(std::abs(pc), std::abs(dc)));
+        aty = NormInf(aty_v);
+        ynorm = std::max(1.0, std::max(NormInf(z), NormInf(y)));
+        if (!(res_p == res_p) || !(res_d == res_d) || !(mu == mu) || !(tau > 0)) {
             res.status = Other;
-            n_rp = last_rp;
-            n_re = last_re;
-            n_rd = last_rd;
-            mu = last_mu;
             break;
         }
-        last_rp = n_rp;
-        last_re = n_re;
-        last_rd = n_rd;
-        last_mu = mu;
-        if (n_rd <= st.tol_feas * nrm_q && n_rp <= st.tol_feas * nrm_b && n_re <= st.tol_feas * nrm_b && sdl <= st.tol_gap * gscale) {
+        have_point = true;   // last iterate with finite residuals: what is returned
+        xg = x; zg = z; yg = y; sg = s; taug = tau;
+        if (res_d <= st.tol_feas * nrm_q && res_p <= st.tol_feas * nrm_b && gap <= st.tol_gap * gscale) {
             res.status = Solved;
             break;
         }
-        // Early exit on a stalled primal residual (stands in for the infeasibility certificate of Clarabel's homogeneous
-        // embedding, which stops an infeasible QP long before the iteration limit): the primal residual shrinks by exactly
-        // (1 - alpha) per step, so less than 10 % over ten iterations while it is still far from feasible means the
-        // steps have collapsed.  Same rule as csrc/bgg_ipm.cu.
-        {
-            const double prim = std::max(n_rp, n_re);
-            if (it == 0) rp_ref = prim;
-            if (it > 0 && it % 10 == 0) {
-                if (prim > 1e3 * st.tol_feas * nrm_b && prim >= 0.9 * rp_ref) break;   // classified below (PrimalInfeasible)
-                rp_ref = prim;
-            }
+        if (bz < -st.tol_infeas && aty <= st.tol_infeas * ynorm * (-bz)) {
+            res.status = PrimalInfeasible;
+            break;
         }
         if (it == st.max_iter) break;
-        for (int r = 0; r < mi; r++) W[r] = lam[r] / s[r];
+        for (int r = 0; r < mi; r++) {
+            Dg[r] = s[r] / z[r];
+            W[r] = 1.0 / (Dg[r] + st.eps);
+        }
         if (!build_and_factor()) {
             res.status = Other;
             break;
         }
-        auto newton = [&](bool corrector, double sigmu) {
+        kkt_solve(mq, bi, be, x1, z1, y1);
+        const double den = kap / tau - Dot(q, x1) - Dot(bi, z1) - Dot(be, y1) + xPx / (tau * tau) - 2.0 * Dot(Px, x1) / tau;
+        double dtau = 0, dkap = 0;
+        // step for right-hand sides (d_x, d_z, d_e, d_tau, d_kappa, d_s): see the derivation in DESIGN.md section 3
+        auto step = [&](double scale, const Vec& d_s, double d_kap) {
+            for (int j = 0; j < n; j++) a1[j] = -scale * rx[j];
+            for (int r = 0; r < mi; r++) a2[r] = -scale * rz[r] + d_s[r] / z[r];
+            for (int e = 0; e < me; e++) a3[e] = -scale * re[e];
+            kkt_solve(a1, a2, a3, x2, z2, y2);
+            double num = scale * rt - d_kap / tau + Dot(q, x2) + Dot(bi, z2) + Dot(be, y2) + 2.0 * Dot(Px, x2) / tau;
+            dtau = num / den;
+            for (int j = 0; j < n; j++) dx[j] = x2[j] + dtau * x1[j];
             for (int r = 0; r < mi; r++) {
-                rc[r] = s[r] * lam[r];
-                if (corrector) rc[r] += ds[r] * dl[r] - sigmu;
+                dz[r] = z2[r] + dtau * z1[r];
+                ds[r] = (-d_s[r] - s[r] * dz[r]) / z[r];
             }
-            for (int j = 0; j < n; j++) r1[j] = -rd[j];
-            for (int r = 0; r < mi; r++) add_rowT(in_rows[r], -(-rc[r] + lam[r] * rp[r]) / s[r], r1);
-            for (int e = 0; e < me; e++) r2[e] = -re[e];
-            kkt_solve(r1, r2, dz, dnu);
-            for (int rf = 0; rf < st.refine; rf++) {   // refinement against the same regularised system
-                Vec t1(n), t2(me), ez(n), enu(me);
-                P.mul(dz.data(), t1.data());
-                for (int r = 0; r < mi; r++) add_rowT(in_rows[r], W[r] * rowdot(in_rows[r], dz), t1);
-                for (int e = 0; e < me; e++) {
-                    add_rowT(eq_rows[e], dnu[e], t1);
-                    t2[e] = rowdot(eq_rows[e], dz) - st.delta * dnu[e];
-                }
-                for (int j = 0; j < n; j++) t1[j] = r1[j] - t1[j];
-                for (int e = 0; e < me; e++) t2[e] = r2[e] - t2[e];
-                kkt_solve(t1, t2, ez, enu);
-                for (int j = 0; j < n; j++) dz[j] += ez[j];
-                for (int e = 0; e < me; e++) dnu[e] += enu[e];
-            }
-            for (int r = 0; r < mi; r++) {
-                ds[r] = -rp[r] - rowdot(in_rows[r], dz);
-                dl[r] = (-rc[r] - lam[r] * ds[r]) / s[r];
-            }
+            for (int e = 0; e < me; e++) dy[e] = y2[e] + dtau * y1[e];
+            dkap = (-d_kap - kap * dtau) / tau;
         };
         auto max_step = [&]() {
-            double a = 1e300;
+            double a = 1.0;
             for (int r = 0; r < mi; r++) {
                 if (ds[r] < 0) a = std::min(a, -s[r] / ds[r]);
-                if (dl[r] < 0) a = std::min(a, -lam[r] / dl[r]);
+                if (dz[r] < 0) a = std::min(a, -z[r] / dz[r]);
             }
+            if (dtau < 0) a = std::min(a, -tau / dtau);
+            if (dkap < 0) a = std::min(a, -kap / dkap);
             return a;
         };
-        newton(false, 0.0);
-        const double a_aff = std::min(1.0, max_step());
-        double mu_aff = 0;
-        for (int r = 0; r < mi; r++) mu_aff += (s[r] + a_aff * ds[r]) * (lam[r] + a_aff * dl[r]);
-        mu_aff = mi ? mu_aff / mi : 0.0;
-        const double sr = (mu > 0) ? mu_aff / mu : 0.0;
-        newton(true, sr * sr * sr * mu);
-        const double alpha = std::min(1.0, 0.99 * max_step());
-        for (int j = 0; j < n; j++) z[j] += alpha * dz[j];
+        Vec d_s(mi);
+        for (int r = 0; r < mi; r++) d_s[r] = s[r] * z[r];
+        step(1.0, d_s, kap * tau);
+        const double a_aff = max_step();
+        const double sigma = (1.0 - a_aff) * (1.0 - a_aff) * (1.0 - a_aff);
+        for (int r = 0; r < mi; r++) d_s[r] = s[r] * z[r] + ds[r] * dz[r] - sigma * mu;
+        step(1.0 - sigma, d_s, kap * tau + dkap * dtau - sigma * mu);
+        const double alpha = 0.99 * max_step();
+        for (int j = 0; j < n; j++) x[j] += alpha * dx[j];
         for (int r = 0; r < mi; r++) {
             s[r] += alpha * ds[r];
-            lam[r] += alpha * dl[r];
+            z[r] += alpha * dz[r];
         }
-        for (int e = 0; e < me; e++) nu[e] += alpha * dnu[e];
+        for (int e = 0; e < me; e++) y[e] += alpha * dy[e];
+        tau += alpha * dtau;
+        kap += alpha * dkap;
     }
-    // Exit classification without Clarabel's homogeneous embedding: residuals within 1e3 x tolerance -> SolvedInacc
-    // ("AlmostSolved"); primal residual still far from feasible after the multipliers diverged -> PrimalInfeasible.
-    if (res.status == MaxIter || res.status == Other) {
-        const double loose = 1e3;
-        if (n_rd <= loose * st.tol_feas * nrm_q && n_rp <= loose * st.tol_feas * nrm_b && n_re <= loose * st.tol_feas * nrm_b &&
-            mu * mi <= loose * st.tol_gap * gscale)
+    // Exit without meeting the tolerances (iteration limit or a numerical breakdown): Clarabel's reduced tolerances decide
+    // between AlmostSolved, AlmostPrimalInfeasible and the plain failure status (reduced_tol_feas 1e-4, reduced_tol_gap 5e-5,
+    // reduced_tol_infeas 5e-5).  A breakdown before the first complete residual evaluation stays `Other` with no iterate.
+    if ((res.status == MaxIter || res.status == Other) && have_point) {
+        if (res_d <= 1e-4 * nrm_q && res_p <= 1e-4 * nrm_b && gap <= 5e-5 * gscale)
             res.status = SolvedInacc;
-        else if (n_rp > loose * st.tol_feas * nrm_b || n_re > loose * st.tol_feas * nrm_b)
-            res.status = PrimalInfeasible;
+        else if (bz < -5e-5 && aty <= 5e-5 * ynorm * (-bz))
+            res.status = PrimalInfeasibleInacc;
     }
+    if (it > st.max_iter) it = st.max_iter;
     res.iters = it;
-    res.prim_res = std::max(n_rp, n_re);
-    res.dual_res = n_rd;
-    res.gap = mu * mi;
-    res.x = z;
+    res.prim_res = res_p;
+    res.dual_res = res_d;
+    res.gap = gap;
+    if (!have_point) {
+        res.x.assign(n, 0.0);
+        res.y.assign(m, 0.0);
+        res.s.assign(m, 0.0);
+        return res;
+    }
+    res.x.assign(n, 0.0);
+    for (int j = 0; j < n; j++) res.x[j] = xg[j] / taug;
     res.y.assign(m, 0.0);
     res.s.assign(m, 0.0);
     for (int i = 0; i < m; i++)
-        if (!is_eq[i]) res.s[i] = b[i] - rowdot(i, z);
+        if (!is_eq[i]) res.s[i] = b[i] - rowdot(i, res.x);
     for (int r = 0; r < mi; r++) {
-        res.y[in_rows[r]] = lam[r];
-        res.s[in_rows[r]] = s[r];
+        res.y[in_rows[r]] = zg[r] / taug;
+        res.s[in_rows[r]] = sg[r] / taug;
     }
-    for (int e = 0; e < me; e++) res.y[eq_rows[e]] = nu[e];
+    for (int e = 0; e < me; e++) res.y[eq_rows[e]] = yg[e] / taug;
     return res;
 }
 

@@ -18,9 +18,11 @@ namespace oracle {
 
 struct IpmSettings {
     double tol_feas = 1e-8, tol_gap = 1e-8;   // Clarabel defaults; the reference tightens feas to 1e-10 (:18-27)
-    double delta = 1e-8;                      // static regularisation of the equality block
-    int max_iter = 50;
-    int refine = 1;
+    double tol_infeas = 1e-8;                 // Clarabel's tol_infeas_abs / tol_infeas_rel
+    double eps = 1e-10;                       // static regularisation of the (1,1) block and of the eliminated cone block
+    double delta = 1e-10;                     // static regularisation of the equality block
+    int max_iter = 50;                        // (Clarabel's default is 200; a QP of this family that needs more than 50 is reported MaxIter)
+    int refine = 1;                           // iterative-refinement steps per solve, against the unregularised system
 };
 
 struct IpmResult {
