@@ -115,8 +115,7 @@ double Dot(const Vec& a, const Vec& b) {
 // (y = all multipliers, z = its Nonnegative part).  Per iteration one factorisation of the reduced quasi-definite matrix
 //   [ P + eps I + A_I' W A_I , A_E' ; A_E , -delta I ] ,   W = 1 / (s/z + eps)
 // (eps, delta: Clarabel's static regularisation, here folded into the eliminated cone block), three solves with it -- the
-// constant right-hand side (-q ; b), the affine and the combined step -- each followed by `refine` steps of iterative
-// refinement against the UNREGULARISED system, sigma = (1 - alpha_aff)^3, step fraction 0.99.  Termination on the
+// constant right-hand side (-q ; b), the affine and the combined step -- sigma = (1 - alpha_aff)^3, step fraction 0.99.  Termination on the
 // de-homogenised point; a primal infeasibility certificate is b'y < 0 with A'y ~ 0 (Clarabel's is_primal_infeasible).
 // The QP here is strictly convex (mpc.cpp:1090-1095 adds 1e-3 I), so the dual-infeasible branch is not restated.
 // csrc/bgg_ipm.cu runs the same iteration on the condensed QP.
@@ -196,33 +195,38 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
     auto add_rowT = [&](int i, double coef, Vec& out) {
         for (int k = R.ptr[i]; k < R.ptr[i + 1]; k++) out[R.col[k]] += coef * R.val[k];
     };
-    // Solve   P dx + A_I'dz + A_E'dy = a1 ,  A_I dx - Dg dz = a2 ,  A_E dx = a3   (Dg = s / z): regularised factorisation,
-    // then refinement against the system as written.
-    Vec work(D), t1(n), cx(n), cz(mi), cy(me), e1(n), e2(mi), e3(me);
-    auto reg_solve = [&](const Vec& a1, const Vec& a2, const Vec& a3, Vec& dx, Vec& dz, Vec& dy) {
-        t1 = a1;
-        for (int r = 0; r < mi; r++) add_rowT(in_rows[r], W[r] * a2[r], t1);
-        for (int j = 0; j < n; j++) work[pos[j]] = t1[j];
-        for (int e = 0; e < me; e++) work[pos[n + e]] = a3[e];
+    // Solve the REGULARISED system   (P + eps I) dx + A_I'dz + A_E'dy = a1 ,  A_I dx - (Dg + eps) dz = a2 ,  A_E dx - delta dy = a3
+    // (Dg = s / z).  The static regularisation is not refined away: with the step taken from this system the method is the
+    // primal-dual proximal (exactly regularised) interior-point iteration, whose fixed point is the solution of the
+    // unregularised QP; refining a nearly degenerate vertex against the unregularised system with a contraction factor
+    // close to 1 stalls instead (tools/ipm_proto.py, instance 2344 of the config #2 batch).  `refine` steps of iterative
+    // refinement against the same regularised matrix, applied matrix-free, remove the rounding of the factorisation.
+    Vec work(D), t1(n), cx(n), cy(me), e1(n), e3(me), tz(mi);
+    auto ldl_solve = [&](const Vec& r1, const Vec& r3, Vec& dx, Vec& dy) {
+        for (int j = 0; j < n; j++) work[pos[j]] = r1[j];
+        for (int e = 0; e < me; e++) work[pos[n + e]] = r3[e];
         F.Solve(work.data());
         for (int j = 0; j < n; j++) dx[j] = work[pos[j]];
         for (int e = 0; e < me; e++) dy[e] = work[pos[n + e]];
-        for (int r = 0; r < mi; r++) dz[r] = W[r] * (rowdot(in_rows[r], dx) - a2[r]);
     };
     auto kkt_solve = [&](const Vec& a1, const Vec& a2, const Vec& a3, Vec& dx, Vec& dz, Vec& dy) {
-        reg_solve(a1, a2, a3, dx, dz, dy);
+        t1 = a1;
+        for (int r = 0; r < mi; r++) add_rowT(in_rows[r], W[r] * a2[r], t1);
+        ldl_solve(t1, a3, dx, dy);
         for (int rf = 0; rf < st.refine; rf++) {
             P.mul(dx.data(), e1.data());
-            for (int r = 0; r < mi; r++) add_rowT(in_rows[r], dz[r], e1);
-            for (int e = 0; e < me; e++) add_rowT(eq_rows[e], dy[e], e1);
-            for (int j = 0; j < n; j++) e1[j] = a1[j] - e1[j];
-            for (int r = 0; r < mi; r++) e2[r] = a2[r] - (rowdot(in_rows[r], dx) - Dg[r] * dz[r]);
-            for (int e = 0; e < me; e++) e3[e] = a3[e] - rowdot(eq_rows[e], dx);
-            reg_solve(e1, e2, e3, cx, cz, cy);
+            for (int j = 0; j < n; j++) e1[j] += st.eps * dx[j];
+            for (int r = 0; r < mi; r++) add_rowT(in_rows[r], W[r] * rowdot(in_rows[r], dx), e1);
+            for (int e = 0; e < me; e++) {
+                add_rowT(eq_rows[e], dy[e], e1);
+                e3[e] = a3[e] - (rowdot(eq_rows[e], dx) - st.delta * dy[e]);
+            }
+            for (int j = 0; j < n; j++) e1[j] = t1[j] - e1[j];
+            ldl_solve(e1, e3, cx, cy);
             for (int j = 0; j < n; j++) dx[j] += cx[j];
-            for (int r = 0; r < mi; r++) dz[r] += cz[r];
             for (int e = 0; e < me; e++) dy[e] += cy[e];
         }
+        for (int r = 0; r < mi; r++) dz[r] = W[r] * (rowdot(in_rows[r], dx) - a2[r]);
     };
 
     IpmResult res;

@@ -22,7 +22,7 @@ struct IpmSettings {
     double eps = 1e-10;                       // static regularisation of the (1,1) block and of the eliminated cone block
     double delta = 1e-10;                     // static regularisation of the equality block
     int max_iter = 50;                        // (Clarabel's default is 200; a QP of this family that needs more than 50 is reported MaxIter)
-    int refine = 1;                           // iterative-refinement steps per solve, against the unregularised system
+    int refine = 1;                           // iterative-refinement steps per solve, against the same regularised matrix
 };
 
 struct IpmResult {

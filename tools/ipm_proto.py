@@ -228,6 +228,10 @@ def hsde_condensed(Q, eps=1e-8, delta=1e-8, max_iter=60, tol_feas=1e-8, tol_gap=
         du, dz, dy, dsv, dtau, dkap = step((1 - sig) * rx, (1 - sig) * rz, (1 - sig) * re, (1 - sig) * rt,
                                            kap * tau + dkap * dtau - sig * mu, s * z + dsv * dz - sig * mu)
         alpha = 0.99 * max_step(dsv, dz, dtau, dkap)
+        if verbose:
+            lin2 = C @ du + dsv - d * dtau + (1 - sig) * rz
+            lin3 = E @ du - e * dtau + (1 - sig) * re
+            print("    alpha", alpha, "sig", sig, "eq2 err", np.abs(lin2).max(), "eq3 err", np.abs(lin3).max() if me else 0)
         u = u + alpha * du; z = z + alpha * dz; y = y + alpha * dy; s = s + alpha * dsv; tau += alpha * dtau; kap += alpha * dkap
     return dict(status=status, iters=it, u=u / tau)
 
@@ -240,3 +244,89 @@ def equilibrate(Q):
     Ct = C * Du[None, :]; Et = E * Du[None, :]
     rc = 1.0 / np.abs(Ct).max(1); re_ = 1.0 / np.abs(Et).max(1) if E.shape[0] else np.zeros(0)
     return dict(H=Ht, g=Du * g, C=rc[:, None] * Ct, d=rc * d, E=re_[:, None] * Et, e=re_ * e, c0=Q["c0"]), Du, rc, re_
+
+
+def hsde_kernel_form(Q, eps=1e-10, delta=1e-10, max_iter=50, tol_feas=1e-8, tol_gap=1e-8, refine=0, verbose=False, tol_inf=1e-8):
+    """The iteration exactly as csrc/bgg_ipm.cu and oracle/qp_ipm.cpp run it: unrefined regularised solves for the constant
+    and the step right-hand sides, d tau from those, the TOTAL direction refined against the unregularised system with the
+    analytic residuals (-eps dz, -delta dy) when refine > 0 (default 0: see oracle/qp_ipm.cpp), ds from the complementarity equation."""
+    H, g, C, d, E, e = Q["H"], Q["g"], Q["C"], Q["d"], Q["E"], Q["e"]
+    nu, m, me = H.shape[0], C.shape[0], E.shape[0]
+    EtE = E.T @ E / delta
+    def factor(w):
+        return np.linalg.cholesky(H + eps * np.eye(nu) + C.T @ (w[:, None] * C) + EtE)
+    def csolve(L, r):
+        return np.linalg.solve(L.T, np.linalg.solve(L, r))
+    def reg(L, w, b1, b2, b3):
+        du = csolve(L, b1 + C.T @ (w * b2) + E.T @ b3 / delta)
+        return du, w * (C @ du - b2), (E @ du - b3) / delta
+    w = np.full(m, 1.0 / (1.0 + eps))
+    L = factor(w)
+    u, z, y = reg(L, w, -g, d, e)
+    s = -z
+    def shift(v):
+        a = v.min()
+        return v + (1.0 - a) if a < 1e-8 else v
+    s = shift(s); z = shift(z)
+    tau = 1.0; kap = 1.0
+    nb = max(1.0, np.abs(d).max(), np.abs(e).max() if me else 0.0); nq = max(1.0, Q.get("nrm_q", np.abs(g).max()))
+    status = "MaxIter"
+    for it in range(max_iter + 1):
+        Hu = H @ u; uHu = u @ Hu
+        aty_v = C.T @ z + E.T @ y
+        rx = Hu + aty_v + g * tau
+        rz = C @ u + s - d * tau
+        re = E @ u - e * tau
+        bz = d @ z + e @ y
+        rt = kap + g @ u + bz + uHu / tau
+        mu = (s @ z + tau * kap) / (m + 1)
+        pc = (0.5 * uHu / tau + g @ u) / tau; dc = (-bz - 0.5 * uHu / tau) / tau
+        res_p = max(np.abs(rz).max(), np.abs(re).max() if me else 0) / tau; res_d = np.abs(rx).max() / tau
+        gap = abs(pc - dc); gs = max(1.0, min(abs(pc + Q["c0"]), abs(dc + Q["c0"])))
+        aty = np.abs(aty_v).max(); zn = max(1.0, np.abs(z).max())
+        if verbose:
+            print(it, f"resp {res_p:.2e} (rz {np.abs(rz).max():.2e} @{np.abs(rz).argmax()} re {np.abs(re).max() if me else 0:.2e}) resd {res_d:.2e} gap {gap:.2e} tau {tau:.2e} kap {kap:.2e} mu {mu:.2e} zmax {z.max():.2e} ymax {np.abs(y).max():.2e} smin {s.min():.1e}")
+        if res_p <= tol_feas * nb and res_d <= tol_feas * nq and gap <= tol_gap * gs:
+            status = "Solved"; break
+        if bz < -tol_inf and aty <= tol_inf * zn * (-bz):
+            status = "PrimalInfeasible"; break
+        if it == max_iter:
+            break
+        D = s / z; w = 1.0 / (D + eps)
+        L = factor(w)
+        x1, z1, y1 = reg(L, w, -g, d, e)
+        den = kap / tau - g @ x1 - d @ z1 - e @ y1 + uHu / tau ** 2 - 2 * (Hu @ x1) / tau
+        def step(scale, d_s, d_kap, do_refine):
+            a1 = -scale * rx; a2 = -scale * rz + d_s / z; a3 = -scale * re
+            x2, z2, y2 = reg(L, w, a1, a2, a3)
+            dtau = (scale * rt - d_kap / tau + g @ x2 + d @ z2 + e @ y2 + 2 * (Hu @ x2) / tau) / den
+            du = x2 + dtau * x1; dz = z2 + dtau * z1; dy = y2 + dtau * y1
+            if verbose and do_refine:
+                print("      pre-refine eq2", np.abs(C @ du - D * dz - (a2 + dtau * d)).max(), "x2-only", np.abs(C @ x2 - D * z2 - a2).max(), "x1-only", np.abs(C @ x1 - D * z1 - d).max(), "eq1", np.abs((a1 - dtau * g) - (H @ du + C.T @ dz + E.T @ dy)).max(), "|du|", np.abs(du).max(), "|dz|", np.abs(dz).max())
+            for _ in range(refine if do_refine else 0):
+                e1 = (a1 - dtau * g) - (H @ du + C.T @ dz + E.T @ dy)
+                cu, cz, cy = reg(L, w, e1, -eps * dz, -delta * dy)
+                du += cu; dz += cz; dy += cy
+                if verbose: print("      post-refine eq2", np.abs(C @ du - D * dz - (a2 + dtau * d)).max(), "|cz|", np.abs(cz).max(), "|cu|", np.abs(cu).max(), "eq1", np.abs((a1 - dtau * g) - (H @ du + C.T @ dz + E.T @ dy)).max())
+            dsv = (-d_s - s * dz) / z      # from the complementarity equation: keeps the relative accuracy of tiny slacks
+            dkap = (-d_kap - kap * dtau) / tau
+            return du, dz, dy, dsv, dtau, dkap
+        def max_step(dsv, dz, dtau, dkap):
+            a = 1.0
+            for v, dv in ((s, dsv), (z, dz)):
+                neg = dv < 0
+                if neg.any(): a = min(a, (-v[neg] / dv[neg]).min())
+            if dtau < 0: a = min(a, -tau / dtau)
+            if dkap < 0: a = min(a, -kap / dkap)
+            return a
+        du, dz, dy, dsv, dtau, dkap = step(1.0, s * z, kap * tau, False)
+        a_aff = max_step(dsv, dz, dtau, dkap)
+        sig = (1 - a_aff) ** 3
+        du, dz, dy, dsv, dtau, dkap = step(1 - sig, s * z + dsv * dz - sig * mu, kap * tau + dkap * dtau - sig * mu, True)
+        alpha = 0.99 * max_step(dsv, dz, dtau, dkap)
+        if verbose:
+            lin2 = C @ du + dsv - d * dtau + (1 - sig) * rz
+            lin3 = E @ du - e * dtau + (1 - sig) * re
+            print("    alpha", alpha, "sig", sig, "eq2 err", np.abs(lin2).max(), "eq3 err", np.abs(lin3).max() if me else 0)
+        u = u + alpha * du; z = z + alpha * dz; y = y + alpha * dy; s = s + alpha * dsv; tau += alpha * dtau; kap += alpha * dkap
+    return dict(status=status, iters=it, u=u / tau)
