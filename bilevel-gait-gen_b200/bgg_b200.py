@@ -30,7 +30,7 @@ class Config(C.Structure):
                 ("ipm_refine", C.c_int32), ("ipm_refine_after", C.c_int32), ("integrator_dt", C.c_double), ("friction_coef", C.c_double),
                 ("force_bound", C.c_double), ("swing_height", C.c_double), ("foot_offset", C.c_double),
                 ("ee_box_size", C.c_double * 2), ("force_cost", C.c_double), ("ipm_tol_feas", C.c_double),
-                ("ipm_tol_gap", C.c_double), ("ipm_eq_delta", C.c_double)]
+                ("ipm_tol_gap", C.c_double), ("ipm_eq_delta", C.c_double), ("ipm_reg_eps", C.c_double), ("ipm_tol_infeas", C.c_double)]
 
 
 class Robot(C.Structure):

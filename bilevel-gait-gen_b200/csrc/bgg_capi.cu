@@ -209,7 +209,9 @@ int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) 
     P.td_fraction = 0.75;     // mpc.cpp:73
     P.ipm_tol_feas = cfg->ipm_tol_feas > 0 ? cfg->ipm_tol_feas : 1e-8;
     P.ipm_tol_gap = cfg->ipm_tol_gap > 0 ? cfg->ipm_tol_gap : 1e-8;
-    P.ipm_eq_delta = cfg->ipm_eq_delta > 0 ? cfg->ipm_eq_delta : 1e-8;
+    P.ipm_eq_delta = cfg->ipm_eq_delta > 0 ? cfg->ipm_eq_delta : 1e-10;
+    P.ipm_reg_eps = cfg->ipm_reg_eps > 0 ? cfg->ipm_reg_eps : 1e-10;
+    P.ipm_tol_infeas = cfg->ipm_tol_infeas > 0 ? cfg->ipm_tol_infeas : 1e-8;
     P.ipm_max_iter = cfg->ipm_max_iter > 0 ? cfg->ipm_max_iter : 50;
     P.ipm_refine = cfg->ipm_refine < 0 ? 0 : (cfg->ipm_refine == 0 ? 1 : cfg->ipm_refine);
     P.ipm_refine_mu_frac = cfg->ipm_refine_after < 0 ? 1e300 : pow(10.0, -static_cast<double>(cfg->ipm_refine_after == 0 ? 4 : cfg->ipm_refine_after));

@@ -234,12 +234,9 @@ void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, int nu
     int cap = (nu_max + 7) / 8 * 8;
     if (cap > L.max_nu) cap = L.max_nu;
     const size_t smem = condense_smem_for(cap);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(k_condense<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        cudaFuncSetAttribute(k_condense<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        configured = smem;
-    }
+    // per device and context, so set on every launch (see launch_ipm)
+    cudaFuncSetAttribute(k_condense<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(k_condense<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     // eight warps own one pair of block rows each up to 16 block rows (nu <= 128), two pairs beyond
     if (cap / 8 <= 16) k_condense<1><<<B, 256, smem, stream>>>(P, L, ws, cap);
     else k_condense<2><<<B, 256, smem, stream>>>(P, L, ws, cap);

@@ -115,7 +115,9 @@ __global__ void __launch_bounds__(128) k_finish(Params P, Instance* __restrict__
         }
     }
     __syncthreads();
-    if (status == kPrimalInfeasible)   // "Primal infeasible." is thrown and the previous solution reused (:115-129)
+    // "Primal infeasible." is thrown and the previous solution reused (:115-129); the same when the solver broke down
+    // before it had an iterate at all (NaN input, refused instance): there is nothing to step towards
+    if (status == kPrimalInfeasible || Hd->no_iterate)
         for (int i = tid; i < n; i += nth) zq[i] = zp[i];
     __syncthreads();
     double sn = 0;
@@ -285,11 +287,8 @@ __global__ void __launch_bounds__(128) k_finish(Params P, Instance* __restrict__
 
 void launch_finish(const Params& P, Instance* inst, const WsLayout& L, char* ws, int B, cudaStream_t stream) {
     const size_t smem = finish_smem_bytes(L);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        configured = smem;
-    }
+    // per device and context, so set on every launch (see launch_ipm)
+    cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     k_finish<<<B, 128, smem, stream>>>(P, inst, L, ws);
 }
 

@@ -835,11 +835,8 @@ int launch_gradient(const Params& P, const Instance* inst, const WsLayout& L, ch
     c.rows = 6 * (ns_max < 1 ? 1 : ns_max) + 2 * (L.N - 3) * 8;
     const size_t smem = grad_smem_for(L.N, c);
     if (smem > static_cast<size_t>(max_smem)) return -1;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(k_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        configured = smem;
-    }
+    // per device and context, so set on every launch (see launch_ipm)
+    cudaFuncSetAttribute(k_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     k_gradient<<<B, 256, smem, stream>>>(P, inst, L, ws, c.nu, c.rows);
     return 0;
 }

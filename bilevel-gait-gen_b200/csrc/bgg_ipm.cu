@@ -1,18 +1,27 @@
-// bilevel-gait-gen_b200 -- kernel 4: the QP solve, one CTA per MPC instance, a primal-dual interior-point method
-// (Mehrotra predictor-corrector) on the condensed QP
+// bilevel-gait-gen_b200 -- kernel 4: the QP solve, one CTA per MPC instance, a primal-dual interior-point method on the
+// condensed QP
 //      min 1/2 u'Hu + g'u   s.t.  C u <= d  (force box, friction pyramid, foot box),   E u = e  (touch-down, foot start)
 // The reference's live solver is Clarabel, an interior-point method run to 1e-8 (mpc.h:264, clarabel_interface.cpp:
 // 18-27,72-155); an ADMM at OSQP tolerances leaves this ill-conditioned QP 1e-2 away from the optimum,
-// so the kernel follows the live path.  Per iteration: K = H + C'WC + E'E/delta is assembled from the *structured*
-// rows (never a sparse matrix), factorised by an in-shared-memory packed Cholesky, and used for the predictor and the
-// corrector solve.  Equality rows are handled by the proximal (static-regularisation) term E'E/delta with their
-// multipliers accumulated, as Clarabel does with its static KKT regularisation.
+// so the kernel follows the live path, and follows Clarabel's algorithm: the homogeneous self-dual embedding
+//      H u + C'z + E'y + g tau = 0 ,  C u + s - d tau = 0 ,  E u - e tau = 0 ,  kappa + g'u + d'z + e'y + u'Hu / tau = 0 ,
+//      s o z = mu ,  tau kappa = mu
+// with predictor-corrector steps (sigma = (1 - alpha_aff)^3, step fraction 0.99), static regularisation and the
+// infeasibility certificate  d'z + e'y < 0, C'z + E'y ~ 0.  Per iteration K = H + eps I + C'WC + E'E/delta with
+// W = 1 / (s/z + eps) is assembled from the *structured* rows (never a sparse matrix), factorised once by an
+// in-shared-memory block Cholesky and used for three solves: the constant right-hand side (-g ; d ; e), the affine and
+// the combined step.  The step is the one of the regularised system (primal-dual proximal form, fixed point = the
+// solution of the unregularised QP); oracle/qp_ipm.cpp runs the same iteration on the reference's sparse QP and
+// tools/ipm_proto.py holds the numpy prototype both were derived from.
 //
 // Inequality rows, internal order (m = 6 ns + 2 ne):
 //   6 j + 0 :  f_z(tau_j) <= force_bound          6 j + 1 : -f_z(tau_j) <= 0               (mpc.cpp:352-414)
 //   6 j + 2..5 : (+-e_x - mu e_z).f <= 0, (+-e_y - mu e_z).f <= 0                          (mpc.cpp:153-209)
 //   6 ns + 2 e + 0 : -p_c(k) + w.u_pos <=  hip_c + box_c/2     e = ((k-4)*4 + foot)*2 + c   (mpc_single_rigid_body.cpp:381-443)
 //   6 ns + 2 e + 1 :  p_c(k) - w.u_pos <= -(hip_c - box_c/2)
+#include <cstdio>
+#include <cstdlib>
+
 #include "bgg_kernels.cuh"
 #include "bgg_chol.cuh"
 #include "bgg_kkt.cuh"
@@ -38,10 +47,10 @@ namespace {
 
 struct Smem {
     double* K;       // lower triangle in 8 x 8 blocks (csrc/bgg_chol.cuh)
-    double *u, *du, *rd, *rhs, *g, *tmpn;            // nu
-    double *s, *lam, *ds, *dl, *rp, *wv, *d;         // m
+    double *u, *du, *rd, *rhs, *Hu, *x1;             // nu (rd: dual residual rx)
+    double *s, *lam, *ds, *dl, *rp, *wv, *d;         // m  (wv: row weights while K is built, then C x1; rp: primal residual rz)
     double *tkc, *ckc;                               // 2(N-3)
-    double *nueq, *re, *dnu;                         // kMaxEq
+    double *nueq, *re, *dnu, *y1, *a3;               // kMaxEq
     double* red;                                     // 72
     double* pw;                                      // [(N-3)*4][2] foot-box position weights
     int *pcnt, *poff;                                // [(N-3)*4]
@@ -66,8 +75,9 @@ struct IpmCtx {
     double mu_f;
 };
 
-// out[0..m) = C v   (v: nu-vector in shared memory)
-static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double* v, double* out) {
+// out[0..m) = C v   (v: nu-vector in shared memory); with eout != nullptr also eout[0..neq) = E v - rhs_scale e, computed by the
+// last warp while the others take the samples (no extra barrier)
+static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double* v, double* out, double* eout, double rhs_scale) {
     const Smem S = c.S;
     const int *fbase = c.fbase, *pbase = c.pbase, *nfv = c.nfv, *npv = c.npv;
     __builtin_assume(__isShared(v)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(S.tkc));
@@ -96,6 +106,12 @@ static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double
         o[4] = fv[1] - mu_f * fv[2];
         o[5] = -fv[1] - mu_f * fv[2];
     }
+    if (eout != nullptr && tid >= nth - 32 && tid - (nth - 32) < c.neq) {
+        const EqRow& q = c.eq[tid - (nth - 32)];
+        double s = -rhs_scale * q.rhs;
+        for (int i = 0; i < q.cnt; ++i) s += q.w[i] * v[q.col[i]];
+        eout[tid - (nth - 32)] = s;
+    }
     __syncthreads();
     #pragma unroll 1
     for (int e = tid; e < ne; e += nth) {
@@ -109,8 +125,9 @@ static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double
     __syncthreads();
 }
 
-// out[0..nu) += C' y   (y: m-vector; inactive rows carry y == 0).  Every output entry is owned by one thread.
-static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double* y, double* out) {
+// out[0..nu) += C' y   (y: m-vector; inactive rows carry y == 0); with ey != nullptr also += escale E' ey (the equality rows
+// touch position columns only: the thread that owns the column adds them).  Every output entry is owned by one thread.
+static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double* y, double* out, const double* ey, double escale) {
     const Smem S = c.S;
     __builtin_assume(__isShared(y)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(S.ckc));
     __builtin_assume(__isShared(S.smp)); __builtin_assume(__isShared(S.pw)); __builtin_assume(__isShared(S.col));
@@ -163,6 +180,16 @@ static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double*
                     const int kf = kk * 4 + ci.foot, e = kf * 2 + ci.coord;
                     s += (y[6 * ns + 2 * e] - y[6 * ns + 2 * e + 1]) * S.pw[2 * kf + (ci.var - S.poff[kf])];
                 }
+                if (ey != nullptr && part == 0) {
+                    double se = 0;
+                    #pragma unroll 1
+                    for (int r = 0; r < c.neq; ++r) {
+                        const EqRow& q = c.eq[r];
+                        for (int i = 0; i < q.cnt; ++i)
+                            if (q.col[i] == col) se += ey[r] * q.w[i];
+                    }
+                    s += escale * se;
+                }
             }
             if (half == 2) s += __shfl_xor_sync(0xffffffffu, s, 1);   // partner thread: adjacent lane
             if (act && part == 0) out[col] += s;
@@ -172,36 +199,8 @@ static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double*
 }
 
 // out[0..nu) = H v, H full symmetric in HBM/L2, read column-wise (coalesced across threads)
-static __device__ __forceinline__ void ipm_apply_H(const IpmCtx& c, const double* v, double* out) {
-    l2_apply_H(c.Hg, c.nu, smem_addr(v), smem_addr(out));   // csrc/bgg_l2ops.cuh
-}
-
-// out = E v - e (or E v when with_rhs == false).  The two equality-row operators take scalars only and are out of line:
-// nine call sites per Newton iteration, one copy in the binary.
-static __device__ __noinline__ void ipm_apply_E(const EqRow* eq, int neq, const double* v, double* out, bool with_rhs) {
-    const int tid = threadIdx.x;
-    __builtin_assume(__isShared(v)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(eq));
-    if (tid < neq) {
-        const EqRow& q = eq[tid];
-        double s = with_rhs ? -q.rhs : 0.0;
-        for (int i = 0; i < q.cnt; ++i) s += q.w[i] * v[q.col[i]];
-        out[tid] = s;
-    }
-    __syncthreads();
-}
-
-// out += scale E' y
-static __device__ __noinline__ void ipm_add_Et(const EqRow* eq, int neq, const double* y, double* out, double scale) {
-    const int tid = threadIdx.x;
-    __builtin_assume(__isShared(y)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(eq));
-    if (tid < kNumEE * 2)   // one thread per (foot, coord): rows of different groups touch different columns
-#pragma unroll 1
-        for (int r = 0; r < neq; ++r) {
-            const EqRow& q = eq[r];
-            if (q.pad != tid) continue;
-            for (int i = 0; i < q.cnt; ++i) out[q.col[i]] += scale * y[r] * q.w[i];
-        }
-    __syncthreads();
+static __device__ __forceinline__ void ipm_apply_H(const IpmCtx& c, const double* v, double* out, bool subtract) {
+    l2_apply_H(c.Hg, c.nu, smem_addr(v), smem_addr(out), subtract);   // csrc/bgg_l2ops.cuh
 }
 
 struct IpmCaps {          // per-launch shared-memory sizing, from the actual maxima over the batch
@@ -209,7 +208,7 @@ struct IpmCaps {          // per-launch shared-memory sizing, from the actual ma
 };
 static size_t ipm_smem_core(int N, int nu, int rows, int ns) {
     const size_t kc = 2 * (N - 3), eb = 4 * (N - 3);
-    return 8 * (chol::doubles(nu / 8) + 6 * nu + 6 * static_cast<size_t>(rows) + 2 * eb * 2 + 2 * kc + 3 * kMaxEq + 72 + 2 * eb) +
+    return 8 * (chol::doubles(nu / 8) + 6 * nu + 6 * static_cast<size_t>(rows) + 2 * eb * 2 + 2 * kc + 5 * kMaxEq + 72 + 2 * eb) +
            8 * eb + sizeof(Sample) * static_cast<size_t>(ns) + sizeof(ColInfo) * static_cast<size_t>(nu) + 64;
 }
 static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max) {
@@ -239,11 +238,14 @@ size_t ipm_smem_bytes(const WsLayout& L) {   // worst case for the configured ca
 
 __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi, int cap_nu, int cap_rows) {
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
-    const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
     WsHeader* Hd = reinterpret_cast<WsHeader*>(ws + L.hdr);
-    if (Hd->error) {
-        if (tid == 0) Hd->status = kOther;
+    if (Hd->error) {   // k_prepare refused the instance: no QP, no iterate (k_finish keeps the previous solution)
+        if (tid == 0) {
+            Hd->status = kOther;
+            Hd->no_iterate = 1;
+            Hd->iters = 0;
+        }
         return;
     }
     const NodeLin* nodes = reinterpret_cast<const NodeLin*>(ws + L.nodes);
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     const int N = P.N, nu = Hd->nu, nf = Hd->nf, ns = Hd->n_samples, ne = Hd->n_eebox, neq = Hd->n_eq;
     const int m = 6 * ns + 2 * ne, nkc = 2 * (N - 3), npk = nu * (nu + 1) / 2;
     const double cost_const = Hd->cost_const;
-    const double mu_f = P.friction_coef, delta = P.ipm_eq_delta, inv_delta = 1.0 / P.ipm_eq_delta;
+    const double mu_f = P.friction_coef, delta = P.ipm_eq_delta, inv_delta = 1.0 / P.ipm_eq_delta, eps = P.ipm_reg_eps;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PROF_DECL
@@ -266,12 +268,12 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         double* p = reinterpret_cast<double*>(smem_raw);
         S.K = p; p += chol::doubles(cap_nu >> 3);
         S.u = p; p += cap_nu; S.du = p; p += cap_nu; S.rd = p; p += cap_nu;
-        S.rhs = p; p += cap_nu; S.g = p; p += cap_nu; S.tmpn = p; p += cap_nu;
+        S.rhs = p; p += cap_nu; S.Hu = p; p += cap_nu; S.x1 = p; p += cap_nu;
         S.s = p; p += cap_rows; S.lam = p; p += cap_rows; S.ds = p; p += cap_rows; S.dl = p; p += cap_rows;
         S.rp = p; p += cap_rows; S.wv = p; p += cap_rows;
         S.d = p; p += 2 * 8 * (N - 3);   // right-hand sides of the foot-box rows only (force rows: see rhs_of)
         S.tkc = p; p += nkc; S.ckc = p; p += nkc;
-        S.nueq = p; p += kMaxEq; S.re = p; p += kMaxEq; S.dnu = p; p += kMaxEq;
+        S.nueq = p; p += kMaxEq; S.re = p; p += kMaxEq; S.dnu = p; p += kMaxEq; S.y1 = p; p += kMaxEq; S.a3 = p; p += kMaxEq;
         S.red = p; p += 72;   // block_reduce scratch (33) / chol::solve scratch (64)
         S.pw = p; p += 2 * 4 * (N - 3);
         S.pcnt = reinterpret_cast<int*>(p);
@@ -314,10 +316,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         s_npv[tid] = Hd->npv[tid];
     }
     #pragma unroll 1
-    for (int i = tid; i < nu; i += nth) S.g[i] = gg[i];
-    #pragma unroll 1
-    for (int i = tid; i < 6 * cap_nu; i += nth)   // u du rd rhs g tmpn: the padding up to 8 nb stays zero (chol::solve)
-        if (i % cap_nu >= nu) S.u[i] = 0.0;
+    for (int i = tid; i < 6 * cap_nu; i += nth) S.u[i] = 0.0;   // u du rd rhs Hu x1: the padding up to 8 nb stays zero (chol::solve)
     if (tid == 0) {
         int e = 0;
         s_sb[0] = 0;
@@ -326,15 +325,22 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         while (e < kNumEE) s_sb[++e] = ns;
     }
 
-    // ---- right-hand sides d and the active mask (wv = 1 / 0 while setting up).  Force rows have the fixed pattern
-    // (force_bound, 0, 0, 0, 0, 0) per sample; only the foot-box right-hand sides are stored.
+    // ---- right-hand sides d and the active mask.  Force rows have the fixed pattern (force_bound, 0, 0, 0, 0, 0) per
+    // sample; only the foot-box right-hand sides are stored.  A row whose coefficients are all exactly zero (the
+    // touch-down sample of a stance) stays out of the iteration: it keeps z == 0, s == 1 and weight 0 throughout, and
+    // z > 0 is the active mask everywhere below.
     const double box0 = Hd->ee_box[0] / 2, box1 = Hd->ee_box[1] / 2;
     const double fbound = P.force_bound;
     const int m_force = 6 * ns;
+    int m_act = 0;
     #pragma unroll 1
     for (int j = tid; j < ns; j += nth) {
         const bool act = samples[j].active != 0;
-        for (int r = 0; r < 6; ++r) S.wv[6 * j + r] = act ? 1.0 : 0.0;
+        for (int r = 0; r < 6; ++r) {
+            S.lam[6 * j + r] = act ? 1.0 : 0.0;
+            S.s[6 * j + r] = 1.0;
+        }
+        m_act += act ? 6 : 0;
     }
     #pragma unroll 1
     for (int e = tid; e < ne; e += nth) {
@@ -343,18 +349,25 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         const double off = xoff[(kk + kEENodeStart) * kNx + c];
         S.d[2 * e + 0] = (bx + P.hip_xy[foot][c]) + off;
         S.d[2 * e + 1] = -(-bx + P.hip_xy[foot][c]) - off;
-        S.wv[m_force + 2 * e + 0] = 1.0;
-        S.wv[m_force + 2 * e + 1] = 1.0;
+        S.lam[m_force + 2 * e + 0] = 1.0;
+        S.lam[m_force + 2 * e + 1] = 1.0;
+        S.s[m_force + 2 * e + 0] = 1.0;
+        S.s[m_force + 2 * e + 1] = 1.0;
+        m_act += 2;
     }
     auto rhs_of = [&](int i) -> double { return (i < m_force) ? ((i % 6 == 0) ? fbound : 0.0) : S.d[i - m_force]; };
-    __syncthreads();
+    m_act = static_cast<int>(block_reduce<kSum>(static_cast<double>(m_act), S.red) + 0.5);
     kkt_build_colinfo(S.col, nu, nf, N, s_fbase, s_pbase, s_nfv, s_npv, s_sb, S.smp, S.pcnt, S.poff);
     __syncthreads();
     KktItem* kitems = reinterpret_cast<KktItem*>(ws + L.ktab);
     KktPos* kpos = reinterpret_cast<KktPos*>(ws + L.ktab + sizeof(KktItem) * kMaxKktItems);
     kkt_mma_setup(s_work, &s_nwork, (nu + 7) >> 3, kitems, &s_nitems, s_fbase, s_nfv, S.col, S.smp, kpos, &s_npos, nu, nf, s_eq, neq);
     if (s_nitems > kMaxKktItems || s_npos > kMaxKktPos) {   // cannot happen within max_spline_vars = 160; refuse rather than drop terms
-        if (tid == 0) Hd->status = kOther;
+        if (tid == 0) {
+            Hd->status = kOther;
+            Hd->no_iterate = 1;
+            Hd->iters = 0;
+        }
         return;
     }
     __syncthreads();
@@ -364,91 +377,66 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     IpmCtx ctx;
     ctx.S = S; ctx.Hg = Hg; ctx.eq = s_eq; ctx.fbase = s_fbase; ctx.pbase = s_pbase; ctx.nfv = s_nfv; ctx.npv = s_npv;
     ctx.N = N; ctx.nu = nu; ctx.nf = nf; ctx.ns = ns; ctx.ne = ne; ctx.neq = neq; ctx.nkc = nkc; ctx.mu_f = mu_f;
-    auto apply_C = [&](const double* v, double* out) { PROF(10); ipm_apply_C(ctx, v, out); PROF(6); };
-    auto add_Ct = [&](const double* y, double* out) { PROF(10); ipm_add_Ct(ctx, y, out); PROF(7); };
-    auto apply_H = [&](const double* v, double* out) { PROF(10); ipm_apply_H(ctx, v, out); PROF(8); };
-    auto apply_E = [&](const double* v, double* out, bool with_rhs) { PROF(10); ipm_apply_E(s_eq, neq, v, out, with_rhs); PROF(9); };
-    auto add_Et = [&](const double* y, double* out, double scale) { PROF(10); ipm_add_Et(s_eq, neq, y, out, scale); PROF(9); };
+    auto apply_C = [&](const double* v, double* out, double* eout, double rhs_scale) { PROF(10); ipm_apply_C(ctx, v, out, eout, rhs_scale); PROF(6); };
+    auto add_Ct = [&](const double* y, double* out, const double* ey, double escale) { PROF(10); ipm_add_Ct(ctx, y, out, ey, escale); PROF(7); };
+    auto apply_H = [&](const double* v, double* out, bool subtract) { PROF(10); ipm_apply_H(ctx, v, out, subtract); PROF(8); };
 
-    // K = H + C' diag(wv) C + E'E/delta in 8 x 8 blocks in shared memory (csrc/bgg_kkt_mma.cuh), then chol::factor in place.
+    // K = H + eps I + C' diag(wv) C + E'E/delta in 8 x 8 blocks in shared memory (csrc/bgg_kkt_mma.cuh), then chol::factor in place.
     const int nb = (nu + 7) >> 3;   // 8 x 8 blocks per side; rows nu .. 8 nb - 1 are padded with the identity
     KktMma km;
     km.K = S.K; km.Hg = Hg; km.phig = phipos; km.phi_ld = L.max_nu; km.nu = nu; km.nf = nf; km.nb = nb; km.ns = ns; km.ne = ne;
     km.neq = neq; km.nkc = nkc; km.wv = S.wv; km.pw = S.pw; km.pcnt = S.pcnt; km.poff = S.poff; km.smp = S.smp; km.eq = s_eq;
     km.col = S.col; km.ckc = S.ckc; km.scratch = S.ds; km.work = s_work; km.nwork = s_nwork; km.items = kitems; km.nitems = s_nitems; km.pos = kpos; km.npos = s_npos;
-    km.mu_f = mu_f; km.inv_delta = inv_delta;
+    km.mu_f = mu_f; km.inv_delta = inv_delta; km.eps = eps;
+    // row weight 1 / (s/z + eps), computed where it is used: the slot that holds the weights while K is assembled is
+    // overwritten by C x1 right after the factorisation (shared memory: six row vectors, as before the embedding)
+    auto wrow = [&](int i) -> double {
+        const double zi = S.lam[i];
+        return (zi > 0.0) ? zi / (S.s[i] + eps * zi) : 0.0;
+    };
     auto build_and_factor = [&]() -> bool {
         PROF(10);
+        #pragma unroll 1
+        for (int i = tid; i < m; i += nth) S.wv[i] = wrow(i);
+        __syncthreads();
         kkt_assemble_mma(km);   // csrc/bgg_kkt_mma.cuh (also writes the identity padding)
         PROF(1);
         chol::factor(S.K, nb, &s_flag);   // csrc/bgg_chol.cuh: DMMA block Cholesky, diagonal super-blocks inverted
         PROF(3);
         return s_flag == 0;
     };
-    // Solve K x = v in place (v padded with zeros to 8 nb entries)
-    auto chol_solve = [&](double* v) {
+    // Solve K x = rhs in place (x padded with zeros to 8 nb entries); with `refine`, one step of iterative refinement
+    // against K = H + eps I + C'WC + E'E/delta applied matrix-free.  It removes the rounding of the factorisation once W
+    // has spread over many decades (block inverses, not substitutions, carry the solves: csrc/bgg_chol.cuh); without it
+    // one nearly degenerate instance of the 4096 of config #2 stalls short of the tolerance where the oracle converges
+    // (instance 2344; refining only the total direction is not enough: d tau is formed from x1).  The residual
+    // rhs - K x accumulates in the copy of rhs.  Scratch: rhs, the ds row vector, dnu.
+    auto solve_K = [&](double* x, bool refine) {
         PROF(10);
-        chol::solve(S.K, nb, v, S.red);
+        if (refine) {
+            #pragma unroll 1
+            for (int i = tid; i < nu; i += nth) S.rhs[i] = x[i];
+        }
+        chol::solve(S.K, nb, x, S.red);
         PROF(5);
+        if (refine) {
+            #pragma unroll 1
+            for (int i = tid; i < nu; i += nth) S.rhs[i] -= eps * x[i];
+            __syncthreads();
+            apply_H(x, S.rhs, true);
+            apply_C(x, S.ds, S.dnu, 0.0);
+            #pragma unroll 1
+            for (int i = tid; i < m; i += nth) S.ds[i] *= -wrow(i);
+            __syncthreads();
+            add_Ct(S.ds, S.rhs, S.dnu, -inv_delta);
+            PROF(10);
+            chol::solve(S.K, nb, S.rhs, S.red);
+            PROF(5);
+            #pragma unroll 1
+            for (int i = tid; i < nu; i += nth) x[i] += S.rhs[i];
+            __syncthreads();
+        }
     };
-
-    // ------------------------------------------------------------------------------------------------ start point
-    // u0 = argmin of the equality/inequality-penalised quadratic: (H + C'C + E'E/delta) u = -g + C'd + E'e/delta
-    bool ok = build_and_factor();
-    #pragma unroll 1
-    for (int i = tid; i < nu; i += nth) S.rhs[i] = -S.g[i];
-    #pragma unroll 1
-    for (int i = tid; i < m; i += nth) S.rp[i] = (S.wv[i] != 0.0) ? rhs_of(i) : 0.0;
-    if (tid < neq) S.re[tid] = s_eq[tid].rhs;
-    __syncthreads();
-    add_Ct(S.rp, S.rhs);
-    add_Et(S.re, S.rhs, inv_delta);
-    #pragma unroll 1
-    for (int i = tid; i < nu; i += nth) S.u[i] = S.rhs[i];
-    chol_solve(S.u);
-    apply_C(S.u, S.ds);
-    double mn = 1e300;
-    #pragma unroll 1
-    for (int i = tid; i < m; i += nth)
-        if (S.wv[i] != 0.0) {
-            S.s[i] = rhs_of(i) - S.ds[i];
-            mn = fmin(mn, S.s[i]);
-        }
-    mn = block_reduce<kMin>(mn, S.red);
-    const double shift = fmax(0.0, -1.5 * mn);
-    double sl = 0, ss = 0, xi = 0;
-    #pragma unroll 1
-    for (int i = tid; i < m; i += nth) {
-        if (S.wv[i] != 0.0) {
-            const double v = fmax(S.s[i] + shift, 1e-2);
-            S.s[i] = v;
-            S.lam[i] = v;
-            xi += v * v;
-            sl += v;
-        } else {
-            S.s[i] = 1.0;
-            S.lam[i] = 0.0;
-        }
-    }
-    xi = block_reduce<kSum>(xi, S.red);
-    sl = block_reduce<kSum>(sl, S.red);
-    #pragma unroll 1
-    for (int i = tid; i < m; i += nth)
-        if (S.wv[i] != 0.0) {
-            S.s[i] += 0.5 * xi / sl;
-            ss += S.s[i];
-        }
-    ss = block_reduce<kSum>(ss, S.red);
-    int m_act = 0;
-    #pragma unroll 1
-    for (int i = tid; i < m; i += nth)
-        if (S.wv[i] != 0.0) {
-            S.lam[i] += 0.5 * xi / ss;
-            m_act++;
-        }
-    m_act = static_cast<int>(block_reduce<kSum>(static_cast<double>(m_act), S.red) + 0.5);
-    if (tid < kMaxEq) S.nueq[tid] = 0.0;
-    __syncthreads();
 
     double nrm_q = 1.0, nrm_d = 1.0;
     for (int r = 0; r < kNx; ++r) nrm_q = fmax(nrm_q, fmax(fabs(P.w[r]), fabs(P.Phi_w[r])));
@@ -456,294 +444,314 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         double v = 0;
         #pragma unroll 1
         for (int i = tid; i < m; i += nth)
-            if (S.wv[i] != 0.0) v = fmax(v, fabs(rhs_of(i)));
+            if (S.lam[i] > 0.0) v = fmax(v, fabs(rhs_of(i)));
+        for (int r = 0; r < neq; ++r) v = fmax(v, fabs(s_eq[r].rhs));
         nrm_d = fmax(1.0, block_reduce<kMax>(v, S.red));
     }
+    if (tid < kMaxEq) S.nueq[tid] = 0.0;
+    __syncthreads();
 
     // ------------------------------------------------------------------------------------------------ main loop
+    // it == -1 is the starting point (Clarabel's QP initialisation: unit scaling, (u, z, y) from the constant solve, s = -z,
+    // s and z shifted into the cone, tau = kappa = 1); it shares the factorisation and constant-solve code with the iterations.
     int it = 0, status = kMaxIter;
-    double mu_first = 0.0, rp_ref = 0.0;
-    double n_rd = 0, n_rp = 0, n_re = 0, mu = 0, gap_scale = 1, qp_obj = 0, last_rp = 0, last_re = 0, last_rd = 0, last_mu = 0;
-    for (it = 0; it <= P.ipm_max_iter; ++it) {
-        // residuals: rd = H u + g + C'lam + E'nu ; rp = C u + s - d ; re = E u - e
-        apply_H(S.u, S.rd);
-        double pobj = 0;
-        #pragma unroll 1
-        for (int i = tid; i < nu; i += nth) {
-            pobj += S.u[i] * (0.5 * S.rd[i] + S.g[i]);
-            S.rd[i] += S.g[i];
-        }
-        pobj = block_reduce<kSum>(pobj, S.red);
-        qp_obj = pobj;
-        add_Ct(S.lam, S.rd);
-        add_Et(S.nueq, S.rd, 1.0);
-        // The primal residuals rp = C u + s - d and re = E u - e are linear in the iterate and the Newton step satisfies
-        // C du + ds = -rp, E du = delta dnu - re by construction: after a step of length alpha they are (1 - alpha) rp and
-        // re + alpha (delta dnu - re) to rounding, so they are updated with the step and recomputed from scratch only at the
-        // first iteration and to confirm convergence (two structured products and their barriers less per iteration).
-        if (it == 0) {
-            apply_C(S.u, S.rp);
-            apply_E(S.u, S.re, true);
-        }
-        double a = 0, c = 0, dsum = 0;
-        #pragma unroll 1
-        for (int i = tid; i < nu; i += nth) a = fmax(a, fabs(S.rd[i]));
-        #pragma unroll 1
-        for (int i = tid; i < m; i += nth) {
-            if (S.lam[i] > 0.0) {   // active row (inactive rows keep lam == 0 exactly)
-                if (it == 0) S.rp[i] = S.rp[i] + S.s[i] - rhs_of(i);
-                c = fmax(c, fabs(S.rp[i]));
-                dsum += S.s[i] * S.lam[i];
-            } else {
-                S.rp[i] = 0.0;
-            }
-        }
-        {   // one pass for the three reductions: two maxima and a sum
-            a = warp_max(a);
-            c = warp_max(c);
-            dsum = warp_sum(dsum);
+    double tau = 1.0, kap = 1.0, mu_first = 0.0;
+    double res_p = 0, res_d = 0, gap = 0, gscale = 1, bz = 0, aty_n = 0, zn = 1, pc = 0;
+    bool have_point = false;
+    for (it = -1; it <= P.ipm_max_iter; ++it) {
+        double uHu = 0, rt = 0, mu = 0;
+        bool refine_now = false;
+        if (it >= 0) {
+            // residuals  rx = H u + C'z + E'y + g tau ,  rz = C u + s - d tau ,  re = E u - e tau
+            apply_H(S.u, S.Hu, false);
+            #pragma unroll 1
+            for (int i = tid; i < nu; i += nth) S.rd[i] = 0.0;
             __syncthreads();
-            if (lane == 0) {
-                S.red[wid] = a;
-                S.red[8 + wid] = c;
-                S.red[16 + wid] = dsum;
+            add_Ct(S.lam, S.rd, S.nueq, 1.0);
+            apply_C(S.u, S.rp, S.re, tau);
+            double r8[8] = {0, 0, 0, 0, 0, 0, 0, 1.0};   // sums: u'Hu, g'u, d'z, s'z ; maxima: |C'z + E'y|, |rx|, |rz|, z
+            #pragma unroll 1
+            for (int i = tid; i < nu; i += nth) {
+                const double gi = gg[i], hu = S.Hu[i], ui = S.u[i], at = S.rd[i];
+                r8[0] += ui * hu;
+                r8[1] += gi * ui;
+                r8[4] = fmax(r8[4], fabs(at));
+                const double rx = hu + at + gi * tau;
+                S.rd[i] = rx;
+                r8[5] = fmax(r8[5], fabs(rx));
             }
-            __syncthreads();
-            a = c = dsum = 0;
-            for (int w = 0; w < nwarp; ++w) {
-                a = fmax(a, S.red[w]);
-                c = fmax(c, S.red[8 + w]);
-                dsum += S.red[16 + w];
-            }
-            n_rd = a;
-            n_rp = c;
-        }
-        mu = dsum / m_act;
-        n_re = 0;
-        for (int r = 0; r < neq; ++r) n_re = fmax(n_re, fabs(S.re[r]));
-        gap_scale = fmax(1.0, fabs(pobj + cost_const));   // full objective, as Clarabel's relative gap
-        const bool nan_seen = !(n_rd == n_rd) || !(n_rp == n_rp) || !(mu == mu);
-        if (nan_seen || !ok) {
-            status = kOther;
-            n_rp = last_rp;
-            n_re = last_re;
-            n_rd = last_rd;
-            mu = last_mu;
-            break;
-        }
-        last_rp = n_rp;
-        last_re = n_re;
-        last_rd = n_rd;
-        last_mu = mu;
-        if (n_rd <= P.ipm_tol_feas * nrm_q && n_rp <= P.ipm_tol_feas * nrm_d && n_re <= P.ipm_tol_feas * nrm_d &&
-            dsum <= P.ipm_tol_gap * gap_scale) {
-            bool confirmed = true;
-            if (it > 0) {   // confirm with primal residuals computed from scratch; they replace the updated ones either way
-                apply_C(S.u, S.rp);
-                apply_E(S.u, S.re, true);
-                double cf = 0;
-#pragma unroll 1
-                for (int i = tid; i < m; i += nth) {
-                    if (S.lam[i] > 0.0) {
-                        S.rp[i] = S.rp[i] + S.s[i] - rhs_of(i);
-                        cf = fmax(cf, fabs(S.rp[i]));
-                    } else {
-                        S.rp[i] = 0.0;
-                    }
+            #pragma unroll 1
+            for (int i = tid; i < m; i += nth) {
+                const double zi = S.lam[i];
+                if (zi > 0.0) {
+                    const double di = rhs_of(i), rz = S.rp[i] + S.s[i] - di * tau;
+                    S.rp[i] = rz;
+                    r8[2] += di * zi;
+                    r8[3] += S.s[i] * zi;
+                    r8[6] = fmax(r8[6], fabs(rz));
+                    r8[7] = fmax(r8[7], zi);
+                } else {
+                    S.rp[i] = 0.0;
                 }
-                n_rp = block_reduce<kMax>(cf, S.red);
-                n_re = 0;
-                for (int r = 0; r < neq; ++r) n_re = fmax(n_re, fabs(S.re[r]));
-                last_rp = n_rp;
-                last_re = n_re;
-                confirmed = n_rp <= P.ipm_tol_feas * nrm_d && n_re <= P.ipm_tol_feas * nrm_d;
             }
-            if (confirmed) {
+            PROF(10);
+            block_reduce_multi<4, 4>(r8, S.red);
+            PROF(13);
+            uHu = r8[0];
+            const double gu = r8[1];
+            double ey = 0, n_re = 0;
+            for (int r = 0; r < neq; ++r) {
+                ey += s_eq[r].rhs * S.nueq[r];
+                n_re = fmax(n_re, fabs(S.re[r]));
+            }
+            bz = r8[2] + ey;
+            aty_n = r8[4];
+            zn = r8[7];
+            rt = kap + gu + bz + uHu / tau;
+            mu = (r8[3] + tau * kap) / (m_act + 1);
+            pc = (0.5 * uHu / tau + gu) / tau;
+            const double dc = (-bz - 0.5 * uHu / tau) / tau;
+            const double n_rp = fmax(r8[6], n_re) / tau, n_rd = r8[5] / tau, n_gap = fabs(pc - dc);
+            if (!(n_rp == n_rp) || !(n_rd == n_rd) || !(mu == mu) || !(n_gap == n_gap) || !(tau > 0.0)) {
+                status = kOther;   // cannot happen while the step below refuses non-finite directions; the outputs then
+                break;             // carry the header of the last finite evaluation
+            }
+            res_p = n_rp;
+            res_d = n_rd;
+            gap = n_gap;
+            gscale = fmax(1.0, fmin(fabs(pc + cost_const), fabs(dc + cost_const)));   // full objective, as Clarabel's relative gap
+            have_point = true;
+            if (res_d <= P.ipm_tol_feas * nrm_q && res_p <= P.ipm_tol_feas * nrm_d && gap <= P.ipm_tol_gap * gscale) {
                 status = kSolved;
                 break;
             }
-        }
-        // Early exit on a stalled primal residual (what the infeasibility certificate of Clarabel's homogeneous embedding does
-        // for the reference: an infeasible QP -- a quarter of the first solves of a random batch, a fifth of the line-search
-        // candidates -- otherwise runs to the iteration limit and holds its SM for twice the time of a solved one).  The
-        // primal residual shrinks by exactly (1 - alpha) per step: less than 10 % over ten iterations while still far from
-        // feasible means the steps have collapsed.  The oracle applies the same rule (oracle/qp_ipm.cpp).
-        {
-            const double prim = fmax(n_rp, n_re);
-            if (it == 0) rp_ref = prim;
-            if (it > 0 && it % 10 == 0) {
-                if (prim > 1e3 * P.ipm_tol_feas * nrm_d && prim >= 0.9 * rp_ref) break;   // classified at exit (PrimalInfeasible)
-                rp_ref = prim;
+            // primal infeasibility certificate (Clarabel's is_primal_infeasible): d'z + e'y < 0 with C'z + E'y ~ 0
+            if (bz < -P.ipm_tol_infeas && aty_n <= P.ipm_tol_infeas * zn * (-bz)) {
+                status = kPrimalInfeasible;
+                break;
             }
+            if (it == P.ipm_max_iter) break;
+            // refinement of the solves pays for itself only once W = z / s has spread over many decades: it starts when mu
+            // has fallen to ipm_refine_mu_frac of its first value
+            if (it == 0) mu_first = mu;
+            refine_now = mu <= P.ipm_refine_mu_frac * mu_first;
         }
-        if (it == P.ipm_max_iter) break;
-
-        // Iterative refinement of the corrector pays for itself only once W = lam / s has spread over many decades: it starts
-        // when mu has fallen to ipm_refine_mu_frac of its first value (measured on 4096 instances: always 32.0 ms, never
-        // 27.7 ms with 0.8 % more unsolved instances)
-        if (it == 0) mu_first = mu;
-        const bool refine_now = mu <= P.ipm_refine_mu_frac * mu_first;
-        // scaling W = lam / s (inactive rows keep 0), factorisation
-        #pragma unroll 1
-        for (int i = tid; i < m; i += nth) S.wv[i] = (S.lam[i] > 0.0) ? S.lam[i] / S.s[i] : 0.0;
-        __syncthreads();
-        ok = build_and_factor();
-        if (!ok) {   // residuals of this iteration are valid; classify at exit
+        if (!build_and_factor()) {
             status = kOther;
             break;
         }
 
-        // one Newton solve for complementarity target rc (dl holds -rc on entry, see callers):
-        //   K du = -rd - C'((-rc + lam rp)/s) - E' re / delta ; ds = -rp - C du ; dl = (-rc - lam ds)/s
-        auto newton = [&](bool corrector, double sig_mu) {
+        // Three solves with the one factorisation, one copy of the code: pass 0 the constant right-hand side (-g ; d ; e)
+        // -> (x1, C x1, y1); pass 1 the affine step; pass 2 the combined step.  Row vectors while a pass runs: dl holds a2
+        // (then dz), ds holds W a2 (then C x2, then ds).
+        double den = 1.0, dtau = 0.0, dkap = 0.0, sigma = 0.0, alpha = 0.0, dkdt_aff = 0.0;
+        bool bad = false;
+#pragma unroll 1
+        for (int pass = 0; pass < (it < 0 ? 1 : 3); ++pass) {
+            const double scale = (pass == 0) ? 0.0 : (pass == 1 ? 1.0 : 1.0 - sigma);
+            double* x = (pass == 0) ? S.x1 : S.du;
+            double* tslot = (pass == 0) ? S.wv : S.ds;
             #pragma unroll 1
             for (int i = tid; i < m; i += nth) {
-                if (S.wv[i] == 0.0) {
-                    S.dl[i] = 0.0;
-                    continue;
-                }
-                double rc = S.s[i] * S.lam[i];
-                if (corrector) rc += S.ds[i] * S.dl[i] - sig_mu;
-                S.dl[i] = rc;                                           // keep rc
-            }
-            __syncthreads();
-            #pragma unroll 1
-            for (int i = tid; i < m; i += nth)
-                S.ds[i] = (S.wv[i] != 0.0) ? -(-S.dl[i] + S.lam[i] * S.rp[i]) / S.s[i] : 0.0;
-            #pragma unroll 1
-            for (int i = tid; i < nu; i += nth) S.rhs[i] = -S.rd[i];
-            __syncthreads();
-            add_Ct(S.ds, S.rhs);
-            add_Et(S.re, S.rhs, -inv_delta);
-            #pragma unroll 1
-            for (int i = tid; i < nu; i += nth) S.du[i] = S.rhs[i];
-            chol_solve(S.du);
-            // The predictor only steers the centring parameter sigma: it is solved without refinement.
-            for (int rf = 0; rf < ((corrector && refine_now) ? P.ipm_refine : 0); ++rf) {
-                // iterative refinement against K = H + C'WC + E'E/delta applied matrix-free
-                apply_H(S.du, S.tmpn);
-                apply_C(S.du, S.ds);
-                #pragma unroll 1
-                for (int i = tid; i < m; i += nth) S.ds[i] *= S.wv[i];
-                __syncthreads();
-                add_Ct(S.ds, S.tmpn);
-                apply_E(S.du, S.dnu, false);
-                add_Et(S.dnu, S.tmpn, inv_delta);
-                #pragma unroll 1
-                for (int i = tid; i < nu; i += nth) S.tmpn[i] = S.rhs[i] - S.tmpn[i];
-                chol_solve(S.tmpn);
-                #pragma unroll 1
-                for (int i = tid; i < nu; i += nth) S.du[i] += S.tmpn[i];
-                __syncthreads();
-            }
-            apply_C(S.du, S.ds);
-            #pragma unroll 1
-            for (int i = tid; i < m; i += nth) {
-                if (S.wv[i] == 0.0) {
+                const double zi = S.lam[i];
+                if (!(zi > 0.0)) {
                     S.ds[i] = 0.0;
-                    S.dl[i] = 0.0;
+                    if (pass > 0) S.dl[i] = 0.0;
                     continue;
                 }
-                const double dsi = -S.rp[i] - S.ds[i];
-                S.dl[i] = (-S.dl[i] - S.lam[i] * dsi) / S.s[i];
-                S.ds[i] = dsi;
+                const double w = wrow(i);
+                if (pass == 0) {
+                    S.ds[i] = w * rhs_of(i);
+                } else {
+                    double d_s = S.s[i] * zi;
+                    if (pass == 2) d_s += S.ds[i] * S.dl[i] - sigma * mu;
+                    const double a2 = -scale * S.rp[i] + d_s / zi;
+                    S.dl[i] = a2;
+                    S.ds[i] = w * a2;
+                }
             }
-            apply_E(S.du, S.dnu, false);
-            if (tid < neq) S.dnu[tid] = (S.dnu[tid] + S.re[tid]) * inv_delta;
+            #pragma unroll 1
+            for (int i = tid; i < nu; i += nth) x[i] = (pass == 0) ? -gg[i] : -scale * S.rd[i];
+            if (tid < neq) S.a3[tid] = (pass == 0) ? s_eq[tid].rhs : -scale * S.re[tid];
             __syncthreads();
-        };
-        auto max_step = [&]() -> double {
-            double al = 1e300;
+            PROF(14);
+            add_Ct(S.ds, x, S.a3, inv_delta);
+            solve_K(x, refine_now && P.ipm_refine > 0 && pass != 1);   // the affine step only steers sigma: not refined
+            double* yx = (pass == 0) ? S.y1 : S.dnu;
+            apply_C(x, tslot, yx, 0.0);
+            if (tid < neq) yx[tid] = (yx[tid] - S.a3[tid]) * inv_delta;
+            __syncthreads();
+            if (it < 0) break;
+            // g'x, (H u)'x, d'z_x with z_x = W (C x - a2), e'y_x
+            double r3[3] = {0, 0, 0};
+            #pragma unroll 1
+            for (int i = tid; i < nu; i += nth) {
+                r3[0] += gg[i] * x[i];
+                r3[1] += S.Hu[i] * x[i];
+            }
             #pragma unroll 1
             for (int i = tid; i < m; i += nth)
-                if (S.wv[i] != 0.0) {
-                    if (S.ds[i] < 0.0) al = fmin(al, -S.s[i] / S.ds[i]);
-                    if (S.dl[i] < 0.0) al = fmin(al, -S.lam[i] / S.dl[i]);
+                if (S.lam[i] > 0.0) {
+                    const double di = rhs_of(i);
+                    r3[2] += di * wrow(i) * (tslot[i] - ((pass == 0) ? di : S.dl[i]));
                 }
-            return block_reduce<kMin>(al, S.red);
-        };
-        // predictor, then corrector: one copy of the Newton step in the binary (instruction-cache footprint)
-        double sig_mu = 0.0, alpha = 1.0;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            newton(pass == 1, sig_mu);
-            const double amax = max_step();
+            PROF(10);
+            block_reduce_multi<3, 0>(r3, S.red);
+            PROF(13);
+            double eyx = 0;
+            for (int r = 0; r < neq; ++r) eyx += s_eq[r].rhs * yx[r];
             if (pass == 0) {
-                const double a_aff = fmin(1.0, amax);
-                double mu_aff = 0;
-#pragma unroll 1
-                for (int i = tid; i < m; i += nth)
-                    if (S.wv[i] != 0.0) mu_aff += (S.s[i] + a_aff * S.ds[i]) * (S.lam[i] + a_aff * S.dl[i]);
-                mu_aff = block_reduce<kSum>(mu_aff, S.red) / m_act;
-                const double sr = mu_aff / mu;
-                sig_mu = sr * sr * sr * mu;
-            } else {
-                alpha = fmin(1.0, 0.99 * amax);
+                den = kap / tau - r3[0] - r3[2] - eyx + uHu / (tau * tau) - 2.0 * r3[1] / tau;
+                continue;
             }
+            const double d_kap = (pass == 1) ? kap * tau : kap * tau + dkdt_aff - sigma * mu;
+            dtau = (scale * rt - d_kap / tau + r3[0] + r3[2] + eyx + 2.0 * r3[1] / tau) / den;
+            dkap = (-d_kap - kap * dtau) / tau;
+            // total direction: (du, dz, dy) = (x2, z2, y2) + dtau (x1, z1, y1); ds from the complementarity equation (keeps the
+            // relative accuracy of tiny slacks); largest step that keeps s, z, tau, kappa non-negative
+            bool nf_local = !(dtau == dtau) || !(dkap == dkap) || fabs(dtau) > 1e300 || fabs(dkap) > 1e300;
+            #pragma unroll 1
+            for (int i = tid; i < nu; i += nth) {
+                const double v = S.du[i] + dtau * S.x1[i];
+                S.du[i] = v;
+                nf_local |= !(fabs(v) <= 1e300);
+            }
+            #pragma unroll 1
+            for (int i = tid; i < m; i += nth) {
+                const double zi = S.lam[i];
+                if (!(zi > 0.0)) continue;
+                const double a2 = S.dl[i];
+                const double t = S.ds[i] + dtau * S.wv[i];
+                const double dzv = wrow(i) * (t - a2 - dtau * rhs_of(i));
+                S.dl[i] = dzv;
+                S.ds[i] = -(a2 + scale * S.rp[i]) - (S.s[i] / zi) * dzv;
+            }
+            if (tid < neq) S.dnu[tid] += dtau * S.y1[tid];
+            __syncthreads();
+            double amax = 1.0;
+            #pragma unroll 1
+            for (int i = tid; i < m; i += nth) {
+                const double zi = S.lam[i];
+                if (!(zi > 0.0)) continue;
+                const double dsv = S.ds[i], dzv = S.dl[i];
+                nf_local |= !(fabs(dzv) <= 1e300) || !(fabs(dsv) <= 1e300);
+                if (dsv < 0.0) amax = fmin(amax, -S.s[i] / dsv);
+                if (dzv < 0.0) amax = fmin(amax, -zi / dzv);
+            }
+            PROF(15);
+            amax = block_reduce<kMin>(amax, S.red);
+            if (__syncthreads_or(nf_local ? 1 : 0)) {
+                bad = true;
+                break;
+            }
+            PROF(13);
+            if (dtau < 0.0) amax = fmin(amax, -tau / dtau);
+            if (dkap < 0.0) amax = fmin(amax, -kap / dkap);
+            if (pass == 1) {
+                sigma = (1.0 - amax) * (1.0 - amax) * (1.0 - amax);
+                dkdt_aff = dkap * dtau;
+            } else {
+                alpha = 0.99 * amax;
+            }
+        }
+        if (it < 0) {
+            // starting point from the constant solve: u = x1, z = W (C x1 - d) with W = 1 / (1 + eps), s = -z, y = y1
+            double mn[2] = {-1e300, -1e300};   // maxima of -s and -z = minus the minima
+            #pragma unroll 1
+            for (int i = tid; i < m; i += nth)
+                if (S.lam[i] > 0.0) {
+                    const double zv = (S.wv[i] - rhs_of(i)) / (1.0 + eps);
+                    S.dl[i] = zv;
+                    mn[0] = fmax(mn[0], zv);    // -s = z
+                    mn[1] = fmax(mn[1], -zv);
+                }
+            block_reduce_multi<0, 2>(mn, S.red);
+            const double smin = -mn[0], zmin = -mn[1];
+            const double sshift = (smin < 1e-8) ? 1.0 - smin : 0.0, zshift = (zmin < 1e-8) ? 1.0 - zmin : 0.0;
+            #pragma unroll 1
+            for (int i = tid; i < m; i += nth)
+                if (S.lam[i] > 0.0) {
+                    const double zv = S.dl[i];
+                    S.s[i] = -zv + sshift;
+                    S.lam[i] = zv + zshift;   // > 0: stays the active mask
+                }
+            #pragma unroll 1
+            for (int i = tid; i < nu; i += nth) S.u[i] = S.x1[i];
+            if (tid < neq) S.nueq[tid] = S.y1[tid];
+            __syncthreads();
+            continue;
+        }
+        if (bad) {   // a non-finite direction (breakdown of the factorisation that the pivot test did not catch): keep the last iterate
+            status = kOther;
+            break;
         }
         #pragma unroll 1
         for (int i = tid; i < nu; i += nth) S.u[i] += alpha * S.du[i];
         #pragma unroll 1
         for (int i = tid; i < m; i += nth)
-            if (S.wv[i] != 0.0) {
+            if (S.lam[i] > 0.0) {
                 S.s[i] += alpha * S.ds[i];
                 S.lam[i] += alpha * S.dl[i];
-                S.rp[i] *= 1.0 - alpha;
             }
-        if (tid < neq) {
-            S.nueq[tid] += alpha * S.dnu[tid];
-            S.re[tid] += alpha * (delta * S.dnu[tid] - S.re[tid]);
-        }
+        if (tid < neq) S.nueq[tid] += alpha * S.dnu[tid];
+        tau += alpha * dtau;
+        kap += alpha * dkap;
         __syncthreads();
     }
-    // Exit classification when the iteration stopped without meeting the tolerances (iteration limit, or a
-    // factorisation / NaN breakdown once the scaling W = lam/s has blown up):
-    //  * residuals within 1e3 x the tolerances         -> SolvedInacc (Clarabel's "AlmostSolved")
-    //  * primal residual still far from feasible        -> PrimalInfeasible (multipliers diverge on an infeasible QP;
-    //                                                      Clarabel certifies this through its homogeneous embedding)
-    if (status == kMaxIter || status == kOther) {
-        const double loose = 1e3;
-        if (n_rd <= loose * P.ipm_tol_feas * nrm_q && n_rp <= loose * P.ipm_tol_feas * nrm_d &&
-            n_re <= loose * P.ipm_tol_feas * nrm_d && mu * m_act <= loose * P.ipm_tol_gap * gap_scale)
-            status = kSolvedInacc;
-        else if (n_rp > loose * P.ipm_tol_feas * nrm_d || n_re > loose * P.ipm_tol_feas * nrm_d)
-            status = kPrimalInfeasible;
+    // Exit without meeting the tolerances (iteration limit or a numerical breakdown): Clarabel's reduced tolerances decide
+    // between AlmostSolved (SolvedInacc), AlmostPrimalInfeasible and the plain failure status (reduced_tol_feas 1e-4,
+    // reduced_tol_gap 5e-5, reduced_tol_infeas 5e-5).  A breakdown before the first complete residual evaluation stays
+    // `Other`, and k_finish then reuses the previous solution.  Same rule as oracle/qp_ipm.cpp.
+    if ((status == kMaxIter || status == kOther) && have_point) {
+        if (res_d <= 1e-4 * nrm_q && res_p <= 1e-4 * nrm_d && gap <= 5e-5 * gscale) status = kSolvedInacc;
+        else if (bz < -5e-5 && aty_n <= 5e-5 * zn * (-bz)) status = kPrimalInfeasibleInacc;
     }
+    if (it > P.ipm_max_iter) it = P.ipm_max_iter;
+    if (it < 0) it = 0;
 
     // ------------------------------------------------------------------------------------------------ outputs
+    // the de-homogenised point (u, z, s, y) / tau; without a finite evaluation (have_point == false) u = 0 is written
+    // and the status (Other) makes k_finish keep the previous solution
     double* uo = reinterpret_cast<double*>(ws + L.u);
     double* lo = reinterpret_cast<double*>(ws + L.lam);
     double* so = reinterpret_cast<double*>(ws + L.slack);
     double* no = reinterpret_cast<double*>(ws + L.nueq);
+    const double itau = have_point ? 1.0 / tau : 0.0;
     #pragma unroll 1
-    for (int i = tid; i < nu; i += nth) uo[i] = S.u[i];
+    for (int i = tid; i < nu; i += nth) uo[i] = have_point ? S.u[i] * itau : 0.0;
     #pragma unroll 1
     for (int i = tid; i < m; i += nth) {
-        lo[i] = S.lam[i];
-        so[i] = (S.lam[i] > 0.0 || S.s[i] != 1.0) ? S.s[i] : rhs_of(i);   // inactive rows: slack = d (row is 0 <= d)
+        const bool act = S.lam[i] > 0.0;
+        lo[i] = act ? S.lam[i] * itau : 0.0;
+        so[i] = act ? S.s[i] * itau : rhs_of(i);   // inactive rows: slack = d (row is 0 <= d)
     }
-    if (tid < neq) no[tid] = S.nueq[tid];
+    if (tid < neq) no[tid] = S.nueq[tid] * itau;
     PROF(10);
     PROF_DUMP;
     if (tid == 0) {
         Hd->status = status;
+        Hd->no_iterate = have_point ? 0 : 1;
         Hd->iters = it;
-        Hd->prim_res = fmax(n_rp, n_re);
-        Hd->dual_res = n_rd;
-        Hd->gap = mu * m_act;
-        Hd->qp_cost = qp_obj + cost_const;
+        Hd->prim_res = res_p;
+        Hd->dual_res = res_d;
+        Hd->gap = gap;
+        Hd->qp_cost = pc + cost_const;
     }
     (void)delta;
     (void)npk;
+    (void)gscale;
 }
 
 void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, cudaStream_t stream) {
     const IpmCaps c = ipm_caps(L, nu_max, ns_max);
     const size_t smem = ipm_smem_for(L, c);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(k_ipm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        configured = smem;
+    // the opt-in is per device and context: set on every launch (a second handle on another GPU, or another host thread,
+    // must not depend on what an earlier launch configured)
+    cudaFuncSetAttribute(k_ipm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (getenv("BGG_DEBUG_OCC")) {
+        int nblk = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, k_ipm, 256, smem);
+        fprintf(stderr, "k_ipm: dynamic smem %zu B, caps nu %d rows %d, stage_phi %d, resident CTAs per SM %d\n", smem, c.nu, c.rows, c.stage_phi, nblk);
     }
     k_ipm<<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows);
 }

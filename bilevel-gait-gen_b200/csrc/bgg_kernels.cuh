@@ -42,6 +42,27 @@ __device__ __noinline__ double block_reduce(double v, double* scratch) {
     return scratch[32];
 }
 
+// NS sums followed by NM maxima in one pass (one pair of barriers for all of them); scratch >= 8 (NS + NM) doubles,
+// blockDim.x <= 256.  Result broadcast to every thread in v.
+template <int NS, int NM>
+__device__ __forceinline__ void block_reduce_multi(double (&v)[NS + NM], double* scratch) {   // inlined: v stays in registers
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NS + NM; ++k) v[k] = (k < NS) ? warp_sum(v[k]) : warp_max(v[k]);
+    __syncthreads();   // protect scratch from the previous use
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NS + NM; ++k) scratch[wid * (NS + NM) + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NS + NM; ++k) {
+        double a = scratch[k];
+        for (int w = 1; w < nw; ++w) a = (k < NS) ? a + scratch[w * (NS + NM) + k] : fmax(a, scratch[w * (NS + NM) + k]);
+        v[k] = a;
+    }
+}
+
 // kernel launchers (each is asynchronous on `stream`)
 void launch_prepare(const Params& P, Instance* inst, const double* state, const double* t0, const double* ee_start,
                     const WsLayout& L, char* ws, int B, cudaStream_t stream);

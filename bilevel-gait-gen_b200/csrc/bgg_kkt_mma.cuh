@@ -81,6 +81,7 @@ __device__ __forceinline__ unsigned smem_addr(const void* p) { return static_cas
 struct KktDenseArgs {      // 32-bit shared-window addresses and scalars; passed by value in registers / param space
     unsigned K, wv, pw, poff, col, ckc, buf, work;
     int nwork, nu, nf, nb, nkc, m_force, phi_ld;
+    double eps;               // static regularisation added to the diagonal of H
 };
 
 // Dense part of the assembly (see the file header), its own function so that its sixteen block accumulators do not
@@ -142,6 +143,10 @@ static __device__ __noinline__ void kkt_dense_mma(const KktDenseArgs a, const do
             if (i >= nu) acc[u] = make_double2(i == j ? 1.0 : 0.0, i == j + 1 ? 1.0 : 0.0);
             else if (j >= nu) acc[u] = make_double2(0.0, 0.0);
             if (u >= nslot) acc[u] = make_double2(0.0, 0.0);
+            else if (ib == jb && i < nu) {   // + eps I
+                if (g == 2 * t) acc[u].x += a.eps;
+                else if (g == 2 * t + 1) acc[u].y += a.eps;
+            }
         }
         const int iA = 8 * rowA + g, iB = 8 * rowB + g;
         // position variable i: foot, coordinate, node range and local index (ColInfo, 8 bytes)
@@ -224,7 +229,7 @@ struct KktMma {
     int nitems;
     const KktPos* pos;         // HBM / L2
     int npos;
-    double mu_f, inv_delta;
+    double mu_f, inv_delta, eps;
 };
 
 // Once per solve: the block map and the item table.  Every thread of the CTA; ends with a barrier.
@@ -380,7 +385,7 @@ __device__ inline void kkt_assemble_mma(const KktMma& v) {
         KktDenseArgs a;
         a.K = smem_addr(v.K); a.wv = smem_addr(v.wv); a.pw = smem_addr(v.pw); a.poff = smem_addr(v.poff); a.col = smem_addr(v.col);
         a.ckc = smem_addr(v.ckc); a.buf = smem_addr(buf); a.work = smem_addr(v.work);
-        a.nwork = v.nwork; a.nu = nu; a.nf = nf; a.nb = nb; a.nkc = nkc; a.m_force = m_force; a.phi_ld = v.phi_ld;
+        a.eps = v.eps; a.nwork = v.nwork; a.nu = nu; a.nf = nf; a.nb = nb; a.nkc = nkc; a.m_force = m_force; a.phi_ld = v.phi_ld;
         kkt_dense_mma(a, v.Hg, v.phig);   // ends with a barrier
     }
     KPROF(1);

@@ -22,9 +22,10 @@ __device__ __forceinline__ double ldany64(const double* p) {   // phi is staged 
     return v;
 }
 
-// out[i] = sum_j H[j][i] v[j]   (H symmetric, row stride nu: coalesced across i).  Two threads per column when the CTA
-// has them.  Every thread of the CTA; ends with a barrier.
-static __device__ __noinline__ void l2_apply_H(const double* __restrict__ Hg, int nu, unsigned v_s, unsigned out_s) {
+// out[i] = sum_j H[j][i] v[j]   (H symmetric, row stride nu: coalesced across i); with `subtract` out[i] -= that sum instead
+// (the residual of the iterative refinement accumulates in place).  Two threads per column when the CTA has them.
+// Every thread of the CTA; ends with a barrier.
+static __device__ __noinline__ void l2_apply_H(const double* __restrict__ Hg, int nu, unsigned v_s, unsigned out_s, bool subtract) {
     const int tid = threadIdx.x, nth = blockDim.x;
     const int half = (2 * nu <= nth) ? 2 : 1;
     for (int base = 0; base < half * nu; base += nth) {
@@ -46,13 +47,13 @@ static __device__ __noinline__ void l2_apply_H(const double* __restrict__ Hg, in
                 }
             }
         }
-        const double s = s0 + s1;
+        const double s = subtract ? -(s0 + s1) : s0 + s1;
         if (half == 2) {   // the two halves of a column sit nu threads apart: combine through shared memory
-            if (act && part == 1) sts64(out_s + 8u * i, s);
+            if (act && part == 1) sts64(out_s + 8u * i, subtract ? lds64(out_s + 8u * i) + s : s);
             __syncthreads();
             if (act && part == 0) sts64(out_s + 8u * i, lds64(out_s + 8u * i) + s);
         } else if (act) {
-            sts64(out_s + 8u * i, s);
+            sts64(out_s + 8u * i, subtract ? lds64(out_s + 8u * i) + s : s);
         }
     }
     __syncthreads();

@@ -74,6 +74,8 @@ struct Params {
     double td_fraction;        // 0.75, mpc.cpp:73
     // interior-point settings (the live reference solver is Clarabel, clarabel_interface.cpp:18-27)
     double ipm_tol_feas, ipm_tol_gap, ipm_eq_delta;
+    double ipm_reg_eps;          // static regularisation of the eliminated cone block: W = 1 / (s/z + eps)
+    double ipm_tol_infeas;       // infeasibility certificate tolerance (Clarabel tol_infeas_abs / _rel)
     int32_t ipm_max_iter, ipm_refine;
     double ipm_refine_mu_frac;   // iterative refinement starts once mu <= this fraction of the first iteration's mu
 };

@@ -43,8 +43,8 @@ typedef struct bgg_config {
     int32_t max_spline_vars;  /* cap on force+position spline variables per instance (0 = default 160) */
     int32_t device;           /* CUDA device ordinal */
     int32_t ipm_max_iter;     /* 0 = default 50 */
-    int32_t ipm_refine;       /* iterative-refinement steps per Newton solve (default 1; negative = 0) */
-    int32_t ipm_refine_after; /* refine only once the complementarity gap mu has fallen below 10^-k of its first value, k = this field
+    int32_t ipm_refine;       /* iterative refinement of the late solves against the regularised matrix: 0 / positive = one step (default), negative = none */
+    int32_t ipm_refine_after; /* refine the solves only once the complementarity gap mu has fallen below 10^-k of its first value, k = this field
                                  (0: library default 4; negative: refine from the first iteration) */
     double integrator_dt;
     double friction_coef;
@@ -55,7 +55,9 @@ typedef struct bgg_config {
     double force_cost;
     double ipm_tol_feas;      /* 0 = default 1e-8 */
     double ipm_tol_gap;       /* 0 = default 1e-8 */
-    double ipm_eq_delta;      /* 0 = default 1e-8 (static regularisation of the equality rows) */
+    double ipm_eq_delta;      /* 0 = default 1e-10 (static regularisation of the equality rows) */
+    double ipm_reg_eps;       /* 0 = default 1e-10 (static regularisation of the eliminated cone block and of H) */
+    double ipm_tol_infeas;    /* 0 = default 1e-8 (primal infeasibility certificate, Clarabel tol_infeas_abs / _rel) */
 } bgg_config;
 
 /* What the reference reads out of pinocchio at construction: mpc/models/model.cpp:27 (mass),

@@ -239,6 +239,10 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
     // ---- starting point (Clarabel's QP initialisation): unit scaling, s = -z, both shifted into the cone
     if (!build_and_factor()) {
         res.status = Other;
+        res.no_iterate = true;
+        res.x.assign(n, 0.0);
+        res.y.assign(m, 0.0);
+        res.s.assign(m, 0.0);
         return res;
     }
     kkt_solve(mq, bi, be, x, z, y);
@@ -342,6 +346,15 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
         for (int r = 0; r < mi; r++) d_s[r] = s[r] * z[r] + ds[r] * dz[r] - sigma * mu;
         step(1.0 - sigma, d_s, kap * tau + dkap * dtau - sigma * mu);
         const double alpha = 0.99 * max_step();
+        {   // a non-finite direction is not applied (same guard as the kernel): the last iterate is kept
+            bool fin = std::isfinite(dtau) && std::isfinite(dkap) && std::isfinite(alpha);
+            for (int j = 0; j < n && fin; j++) fin = std::isfinite(dx[j]);
+            for (int r = 0; r < mi && fin; r++) fin = std::isfinite(dz[r]) && std::isfinite(ds[r]);
+            if (!fin) {
+                res.status = Other;
+                break;
+            }
+        }
         for (int j = 0; j < n; j++) x[j] += alpha * dx[j];
         for (int r = 0; r < mi; r++) {
             s[r] += alpha * ds[r];
@@ -366,6 +379,7 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
     res.dual_res = res_d;
     res.gap = gap;
     if (!have_point) {
+        res.no_iterate = true;
         res.x.assign(n, 0.0);
         res.y.assign(m, 0.0);
         res.s.assign(m, 0.0);
@@ -408,6 +422,7 @@ QpSolution IpmQpSolver::Solve(const QpData& data, const Vec& /*warm_start*/, boo
     out.iters = r.iters;
     out.prim_res = r.prim_res;
     out.dual_res = r.dual_res;
+    out.no_iterate = r.no_iterate;
     return out;
 }
 

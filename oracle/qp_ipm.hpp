@@ -30,6 +30,7 @@ struct IpmResult {
     SolveQuality status = Unsolved;
     int iters = 0;
     double prim_res = 0, dual_res = 0, gap = 0;
+    bool no_iterate = false;
 };
 
 // `order` (optional): elimination order over [z (n) ; equality multipliers (in row order)], a permutation of

@@ -879,7 +879,7 @@ const Traj& SrbMpc::Solve(const Vec& state, double init_time, const std::vector<
     Prepare(state, init_time, ee_start);
     last_qp_ = solver_->Solve(data_, prev_qp_sol_, in_real_time_);   // :110-129
     Vec sol = last_qp_.x;
-    if (last_qp_.status == PrimalInfeasible) sol = prev_qp_sol_;      // the "Primal infeasible." throw/catch
+    if (last_qp_.status == PrimalInfeasible || last_qp_.no_iterate) sol = prev_qp_sol_;      // the "Primal infeasible." throw/catch
     if (last_qp_.status != SolvedInacc && last_qp_.status != Solved && last_qp_.status != MaxIter) {   // :136-144
         info_.ee_box_size[0] += 0.05;
         info_.ee_box_size[1] += 0.05;

@@ -178,6 +178,7 @@ struct QpSolution {
     SolveQuality status = Unsolved;
     int iters = 0;
     double prim_res = 0, dual_res = 0;
+    bool no_iterate = false;   // the solver broke down before its first finite residual evaluation: x holds nothing
 };
 
 // The solver seam (mpc/include/qp/qp_interface.h:30-65).  The oracle's implementation is the ADMM restatement in

@@ -1,5 +1,6 @@
-"""Developer diagnostic: the instances of BASELINE config #2 whose RTI solve does not end `Solved` on the CUDA path,
-replayed on the CPU oracle (same inputs, same number of RTI steps) -- do both sides agree on the outcome?"""
+"""Developer diagnostic: BASELINE config #2 (4096 random instances, 5 RTI steps) on the CUDA path, and a sample of the
+instances -- every one that is not `Solved` at any step plus the first NSAMPLE -- replayed on the CPU oracle
+(same inputs, same number of RTI steps): status and iteration count per step on both sides."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,25 +11,40 @@ cfg_name = os.environ.get("CFG", "a1_configuration")
 cfg = wl.CONFIGS[cfg_name]
 B = int(os.environ.get("B", 4096))
 STEPS = int(os.environ.get("STEPS", 5))
-states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=0)
-gpu = common.make_gpu(cfg_name, B, states)
-hist = []
+NS = int(os.environ.get("NSAMPLE", 64))
+states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=int(os.environ.get("SEED", 0)))
+kw = {}
+if os.environ.get("REFINE"): kw["ipm_refine"] = int(os.environ["REFINE"])
+gpu = common.make_gpu(cfg_name, B, states, **kw)
+hist, ith = [], []
 for it in range(STEPS):
     out = gpu.GetRealTimeUpdate(states, t0, ee)
-    hist.append(out["status"].copy())
-    print(it, "status hist", np.bincount(out["status"], minlength=9).tolist(), "iters mean", round(float(out["iters"].mean()), 2))
-bad = np.where(~np.isin(hist[-1], (0,)))[0]
-print("not Solved at the last step:", len(bad), "of", B)
-agree = 0
-rows = []
-for b in bad[: int(os.environ.get("NBAD", 24))]:
+    hist.append(out["status"].copy()); ith.append(out["iters"].copy())
+    print(it, "status hist", np.bincount(out["status"], minlength=9).tolist(), "iters mean", round(float(out["iters"].mean()), 2),
+          "max", int(out["iters"].max()), flush=True)
+hist = np.array(hist); ith = np.array(ith)
+bad = np.where((hist != 0).any(0))[0]
+sample = sorted(set(bad.tolist()) | set(range(NS)))
+print("not Solved at some step:", len(bad), "of", B, "; oracle sample", len(sample))
+
+
+def replay(b):
     o = common.make_oracle(cfg_name, states[b])
-    seq = []
+    st, its = [], []
     for it in range(STEPS):
-        seq.append(int(o.solve(states[b], 0.0, ee[b], real_time=True)))
-    g = [int(h[b]) for h in hist]
-    rows.append((int(b), g, seq))
-    agree += int(g[-1] == seq[-1])
-for r in rows:
-    print("instance", r[0], "cuda", r[1], "oracle", r[2])
-print("same final status on", agree, "of", len(rows))
+        st.append(int(o.solve(states[b], 0.0, ee[b], real_time=True)))
+        its.append(int(o.qp_solution()["iters"]))
+    return b, st, its
+
+
+import multiprocessing as mp
+with mp.Pool(min(16, os.cpu_count())) as pool:
+    rows = pool.map(replay, sample)
+same = 0; dit = []
+for b, st, its in rows:
+    g = hist[:, b].tolist()
+    same += int(g == st)
+    dit += (ith[:, b] - np.array(its)).tolist()
+    if g != st or b in bad:
+        print("instance", b, "cuda", g, ith[:, b].tolist(), "oracle", st, its)
+print("same status sequence on", same, "of", len(rows), "; iteration-count difference histogram", dict(zip(*np.unique(dit, return_counts=True))))
