@@ -312,10 +312,11 @@ __global__ void __launch_bounds__(256) k_ls_select(Instance* __restrict__ parent
         for (int k = 0; k < K; ++k) {
             const WsHeader* h = reinterpret_cast<const WsHeader*>(child_ws + static_cast<size_t>(b * K + k) * L.stride + L.hdr);
             const int st = h->error ? static_cast<int>(kOther) : h->status;
-            const double c = h->cost / h->n;   // GetCost() / GetNumDecisionVars(), :716
+            const double c = h->error ? 1e300 : h->cost / h->n;   // GetCost() / GetNumDecisionVars(), :716
             costs[b * K + k] = c;
             quality[b * K + k] = st;
-            if (c < cmin && st != kPrimalInfeasible) {
+            // a child that k_prepare refused was never solved (the reference's copy would have thrown): it cannot win
+            if (!h->error && c == c && c < cmin && st != kPrimalInfeasible) {
                 cmin = c;
                 best = k;
             }
@@ -324,9 +325,17 @@ __global__ void __launch_bounds__(256) k_ls_select(Instance* __restrict__ parent
         s_best = best < 0 ? 0 : best;
     }
     __syncthreads();
-    const double* src = reinterpret_cast<const double*>(child + b * K + s_best);
-    double* dst = reinterpret_cast<double*>(parent + b);
-    for (int i = tid; i < static_cast<int>(sizeof(Instance) / 8); i += blockDim.x) dst[i] = src[i];
+    // MPC::SetWarmStartTrajectory (mpc.cpp:110-119) assigns prev_traj_ and init_time_ only: the parent's adaptive foot box
+    // and run count are its own (the child's solve changed the child's copies through Increase / DecreaseEEBox)
+    const Instance* src = child + b * K + s_best;
+    Instance* dst = parent + b;
+    const double* ssrc = reinterpret_cast<const double*>(src->states);
+    double* sdst = reinterpret_cast<double*>(dst->states);
+    for (int i = tid; i < static_cast<int>(sizeof(src->states) / 8); i += blockDim.x) sdst[i] = ssrc[i];
+    const double* fsrc = reinterpret_cast<const double*>(src->foot);
+    double* fdst = reinterpret_cast<double*>(dst->foot);
+    for (int i = tid; i < static_cast<int>(sizeof(src->foot) / 8); i += blockDim.x) fdst[i] = fsrc[i];
+    if (tid == 0) dst->init_time = src->init_time;
 }
 
 void launch_gait_lp(const Instance* inst, const WsLayout& L, const char* ws, int B, const double* grad, const double* time, double trust,

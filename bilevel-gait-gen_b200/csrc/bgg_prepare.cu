@@ -100,10 +100,12 @@ __global__ void __launch_bounds__(128) k_prepare(Params P, Instance* __restrict_
         int ns = 0, prev = -1;
         for (int i = 0; i < s.n; ++i) {
             if (s.ttype[i] == kInter) continue;
-            if (prev >= 0 && s.ttype[prev] == kTouchDown && ns < kMaxStances) {
-                st_lo[tid][ns] = s.t[prev];
-                st_hi[tid][ns] = s.t[i];
-                ns++;
+            if (prev >= 0 && s.ttype[prev] == kTouchDown) {
+                if (ns < kMaxStances) {
+                    st_lo[tid][ns] = s.t[prev];
+                    st_hi[tid][ns] = s.t[i];
+                }
+                ns++;   // counted beyond the cap: the instance is refused (error bit 2) rather than solved without those rows
             }
             prev = i;
         }
@@ -121,6 +123,10 @@ __global__ void __launch_bounds__(128) k_prepare(Params P, Instance* __restrict_
             sh.pbase[e] = pb;
             fb += 3 * sh.nfv[e];
             pb += 2 * sh.npv[e];
+            if (st_n[e] > kMaxStances) {
+                err |= 4;
+                st_n[e] = kMaxStances;
+            }
             st_base[e + 1] = st_base[e] + st_n[e] * kSamplesPerStance;
             if (sf[e].n + kNumForcePolys > kMaxKnots) err |= 1;
             // a touch-down row pair when the next touch-down is closer than td_fraction of the current swing
@@ -143,6 +149,10 @@ __global__ void __launch_bounds__(128) k_prepare(Params P, Instance* __restrict_
         sh.status = kUnsolved;
         sh.iters = 0;
         sh.ls_iters = 0;
+        sh.no_iterate = 0;
+        sh.cost = 0.0;      // k_finish writes these; a refused instance (error != 0) must not carry stale or uninitialised values
+        sh.qp_cost = 0.0;
+        sh.alpha = 0.0;
         sh.ee_box[0] = I.ee_box[0];
         sh.ee_box[1] = I.ee_box[1];
     }

@@ -255,7 +255,15 @@ Trajectory MPC::GetTrajectory() const {
     return Trajectory(inst, info_.num_nodes, info_.integrator_dt);
 }
 void MPC::SetWarmStartTrajectory(const Trajectory& trajectory) {
-    Check(bgg_set_instance(h_, 0, &trajectory.Raw()));   // prev_traj_ = trajectory; init_time_ = trajectory.GetTime(0)
+    // prev_traj_ = trajectory; init_time_ = trajectory.GetTime(0) (mpc.cpp:110-119) -- and nothing else: the adaptive foot
+    // box and the run count belong to this MPC, not to the trajectory that is handed in
+    bgg::Instance inst;
+    Check(bgg_get_instance(h_, 0, &inst));
+    const bgg::Instance& src = trajectory.Raw();
+    std::memcpy(inst.states, src.states, sizeof(inst.states));
+    std::memcpy(inst.foot, src.foot, sizeof(inst.foot));
+    inst.init_time = src.init_time;
+    Check(bgg_set_instance(h_, 0, &inst));
 }
 void MPC::UpdateContactTimes(std::vector<time_v>& contact_times) {
     Trajectory t = GetTrajectory();

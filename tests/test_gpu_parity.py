@@ -3,8 +3,12 @@ the CPU oracle on identical inputs.
 
 Tolerances (BASELINE.json north_star): discretised dynamics within 1e-10 with bit-identical sparsity; QP primal
 solution, cost and the post-line-search trajectory within 1e-4 relative; constraint violation no worse than the
-oracle's tolerance.  The oracle's QP solver here is its interior-point restatement of the reference's live Clarabel
-path (oracle/qp_ipm.cpp); both sides run to 1e-8.
+oracle's tolerance.  The oracle's QP solver here is its restatement of the reference's live Clarabel path
+(oracle/qp_ipm.cpp: homogeneous self-dual embedding); the CUDA kernel runs the same iteration on the condensed QP.
+Solver STATUS is an integer output and is compared for equality -- no instance is skipped.  Both sides default to
+Clarabel's 1e-8 tolerances; where a test compares the MINIMISER to 1e-4 both sides are run at 1e-9 (`TIGHT`): the QP is
+flat in most spline directions (71 of 120 condensed eigenvalues below 1e-2 against 6e8), so two iterates that both meet
+1e-8 can still differ by 1e-3 in u (measured: tools/_tolcheck.py), while the cost already agrees to 1e-4.
 """
 import numpy as np
 import pytest
@@ -13,6 +17,18 @@ import common
 from common import wl
 
 pytestmark = pytest.mark.gpu
+
+TIGHT = 1e-9   # "same eps on both sides" for minimiser comparisons, see the module docstring
+
+
+def _tight_gpu(cfg_name, B, states, **kw):
+    return common.make_gpu(cfg_name, B, states, ipm_tol=TIGHT, ipm_tol_gap=TIGHT, **kw)
+
+
+def _tight_oracle(cfg_name, state=None):
+    o = common.make_oracle(cfg_name, state)
+    o.set_ipm(tol_feas=TIGHT, tol_gap=TIGHT)
+    return o
 
 
 def _rel(a, b):
@@ -30,14 +46,15 @@ def _kkt_check(qp, z, tol_eq=1e-6, tol_in=1e-6):
 def test_first_solve_matches_oracle(cfg_name):
     cfg = wl.CONFIGS[cfg_name]
     N = cfg["num_nodes"]
-    B = 6
+    B = 12
     states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=3)
     states[0] = cfg["srb_init"]
     ee[0] = wl.EE_NOMINAL
-    gpu = common.make_gpu(cfg_name, B, states)
+    gpu = _tight_gpu(cfg_name, B, states)
     out = gpu.GetRealTimeUpdate(states, t0, ee)
+    seen = set()
     for b in range(B):
-        o = common.make_oracle(cfg_name, states[b])
+        o = _tight_oracle(cfg_name, states[b])
         o.assemble(states[b], 0.0, ee[b])
         osz, gsz = o.sizes(), gpu.sizes(b)
         assert (gsz["n"], gsz["nf"], gsz["np"]) == (osz["n"], osz["nf"], osz["np"])
@@ -50,29 +67,80 @@ def test_first_solve_matches_oracle(cfg_name):
         assert np.abs(cd[0] - ocd).max() <= 1e-10
         assert np.array_equal(Ad[0] != 0, oAd != 0)
         assert np.array_equal(Bd[0] != 0, oBd != 0)
-        # kernel 4: QP optimum
+        # kernel 4: status (integer: exact) and QP optimum
         qp = o.qp()
-        o.solve(states[b], 0.0, ee[b], real_time=True)
+        st = o.solve(states[b], 0.0, ee[b], real_time=True)
         oq = o.qp_solution()
         sol = gpu.solution(b)
-        if oq["status"] != 0:
-            continue   # the oracle itself did not converge on this sample; covered by the KKT check below
-        assert out["status"][b] == 0
+        assert out["status"][b] == st, f"instance {b}: status {out['status'][b]} vs the oracle's {st}"
+        seen.add(int(st))
+        ost = o.stats()
+        # foot-box adaptation driven by the status (mpc_single_rigid_body.cpp:131-144)
+        assert np.array_equal(gpu.get_instance(b)["ee_box"], [ost["ee_box_x"], ost["ee_box_y"]])
+        if st == 3:   # PrimalInfeasible on both sides: "Primal infeasible." is thrown, the previous solution is kept
+            assert _rel(sol["z"], o.prev_qp_sol()) < 1e-12
+            continue
+        assert st == 0, f"instance {b}: neither Solved nor PrimalInfeasible ({st}); pick inputs the solver classifies"
+        # same iteration, so the same count -- up to a step when a residual crosses its threshold within rounding, and
+        # except on the nearly degenerate instance of this batch (44 against 50 iterations; both converge)
+        assert abs(int(out["iters"][b]) - oq["iters"]) <= 2 or min(int(out["iters"][b]), oq["iters"]) >= 30
         _kkt_check(qp, sol["qp_sol"])
         obj = lambda z: 0.5 * z @ (qp["P"] @ z) + qp["q"] @ z
-        # cost within 1e-4 relative (north_star); the oracle's 1e-8 relative equality residual times its large dynamics
-        # multipliers already moves its objective by ~1e-5 relative, the CUDA path satisfies the dynamics rows exactly
         assert abs(obj(sol["qp_sol"]) - obj(oq["x"])) <= 1e-4 * max(1.0, abs(obj(oq["x"])))
         assert abs(gsz["qp_cost"] - obj(sol["qp_sol"])) <= 1e-8 * max(1.0, abs(obj(oq["x"])))
         assert _rel(sol["qp_sol"], oq["x"]) < 1e-4
         # kernel 5: line search and trajectory update
-        ost = o.stats()
         assert out["alpha"][b] == ost["alpha"]
         assert _rel(sol["z"], o.prev_qp_sol()) < 1e-4
         assert abs(out["cost"][b] - ost["cost"]) <= 1e-4 * max(1.0, abs(ost["cost"]))
         assert np.abs(gpu.GetStates(b) - o.states()).max() < 1e-4 * max(1.0, np.abs(o.states()).max())
         # an l1 sum over 12 N defects of trajectories that agree to 1e-4
         assert abs(gsz["eq_violation"] - ost["eq_violation"]) <= 5e-3 * max(1.0, ost["eq_violation"])
+    assert 0 in seen
+    if cfg_name == "a1_gait_opt_config":
+        assert 3 in seen, "this batch is meant to contain infeasible QPs (certificate path on both sides)"
+
+
+def _replay_on_oracle(args):
+    """Worker of test_status_parity_on_the_full_batch: `steps` RTI solves of one instance on the CPU oracle."""
+    cfg_name, state, ee, steps = args
+    o = common.make_oracle(cfg_name, state)
+    st, its = [], []
+    for _ in range(steps):
+        st.append(int(o.solve(state, 0.0, ee, real_time=True)))
+        its.append(int(o.qp_solution()["iters"]))
+    return st, its
+
+
+def test_status_parity_on_the_full_batch():
+    """BASELINE config #2 at full size, 5 RTI steps at the default tolerances: the status vector of the CUDA path equals the
+    oracle's on a sample of 256 instances PLUS every instance that is not `Solved` at any step; fewer than 1 % of the first
+    solves end anything but `Solved` (round 1: 27 %, from uncapped weights and a coarse equality regularisation); no
+    instance ends `Other`.  Iteration counts are reported by both sides and agree to within 2 on 99 % of the sample."""
+    import multiprocessing as mp
+    cfg_name = "a1_configuration"
+    cfg = wl.CONFIGS[cfg_name]
+    B, STEPS = 4096, 5
+    states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=0)
+    gpu = common.make_gpu(cfg_name, B, states)
+    hist, iters = [], []
+    for _ in range(STEPS):
+        out = gpu.GetRealTimeUpdate(states, t0, ee)
+        hist.append(out["status"].copy())
+        iters.append(out["iters"].copy())
+    hist, iters = np.array(hist), np.array(iters)
+    assert np.mean(hist[0] != 0) < 0.01, np.bincount(hist[0], minlength=9).tolist()
+    assert not np.any(hist == 8), "a numerical breakdown (Other) on the random batch"
+    bad = np.flatnonzero((hist != 0).any(0))
+    sample = sorted(set(bad.tolist()) | set(range(0, B, 16)))
+    assert len(sample) >= 256
+    with mp.get_context("fork").Pool(min(16, mp.cpu_count())) as pool:
+        rows = pool.map(_replay_on_oracle, [(cfg_name, states[b], ee[b], STEPS) for b in sample])
+    diffs = []
+    for b, (st, its) in zip(sample, rows):
+        assert hist[:, b].tolist() == st, f"instance {b}: CUDA statuses {hist[:, b].tolist()} vs the oracle's {st}"
+        diffs += np.abs(iters[:, b] - np.array(its)).tolist()
+    assert np.mean(np.array(diffs) <= 2) >= 0.99, np.bincount(diffs).tolist()
 
 
 def _assert_same_qp(gq, oq):
@@ -111,8 +179,8 @@ def test_receding_horizon_with_mirrored_trajectory():
     cfg_name = "a1_configuration"
     cfg = wl.CONFIGS[cfg_name]
     init = np.asarray(cfg["srb_init"], float)
-    o = common.make_oracle(cfg_name)
-    gpu = common.make_gpu(cfg_name, 1)
+    o = _tight_oracle(cfg_name)
+    gpu = _tight_gpu(cfg_name, 1, None)
     ee = wl.EE_NOMINAL.copy()
     o.initial_run(init, ee)
     seen_sizes = set()
@@ -177,13 +245,11 @@ def test_full_size_batch_properties():
         out = gpu.GetRealTimeUpdate(states, t0, ee)
         ok = np.isin(out["status"], (0, 1))
         hist = np.bincount(out["status"], minlength=9).tolist()
-        # The first solve starts from feet pinned up to 2 cm off nominal with a 15 cm foot box: roughly a quarter of the
-        # random instances are genuinely infeasible, get reported as such and have their box widened (reference
-        # behaviour, mpc_single_rigid_body.cpp:136-144); afterwards nearly everything solves.
-        # status Other = numerical breakdown on barely-feasible instances (huge multipliers); the oracle's interior
-        # point method shows the same on such inputs
-        assert hist[8] <= (0.08 if it == 0 else 0.03) * B, f"too many unclassified failures: {hist}"
-        assert ok.mean() > (0.70 if it == 0 else 0.97), f"only {ok.mean():.4f} of the batch solved at iteration {it}: {hist}"
+        # every QP of this batch is feasible (feet pinned up to 2 cm off nominal against a 15 cm foot box); a handful of
+        # nearly degenerate first solves may stop at the iteration limit within the reduced tolerances (SolvedInacc)
+        assert hist[8] == 0, f"numerical breakdowns: {hist}"
+        assert (out["status"] == 0).mean() >= (0.995 if it == 0 else 0.999), f"solved fraction at iteration {it}: {hist}"
+        assert ok.all(), hist
         assert np.all(out["alpha"][ok] > 0) and np.all(out["alpha"][ok] <= 1)
         assert np.all(np.isfinite(out["cost"][ok]))
         costs.append(out["cost"])
@@ -197,13 +263,12 @@ def _gradient_case(cfg_name, states, ee, rt_steps=1, tol_gap=0.0):
     """Oracle and CUDA path solve the same RTI step from a mirrored trajectory; returns both sides' derivative data."""
     import gait_oracle as go
     B = len(states)
-    kw = dict(ipm_tol=1e-8, ipm_tol_gap=tol_gap) if tol_gap > 0 else {}
-    gpu = common.make_gpu(cfg_name, B, states, **kw)
+    tol = tol_gap if tol_gap > 0 else TIGHT
+    gpu = common.make_gpu(cfg_name, B, states, ipm_tol=tol, ipm_tol_gap=tol)
     oracles = []
     for b in range(B):
         o = common.make_oracle(cfg_name, states[b])
-        if tol_gap > 0:
-            o.set_ipm(tol_gap=tol_gap)
+        o.set_ipm(tol_feas=tol, tol_gap=tol)
         o.initial_run(states[b], ee[b])
         common.mirror_oracle_to_gpu(o, gpu, b)
         oracles.append(o)
@@ -233,9 +298,7 @@ def test_gait_gradient_matches_oracle(cfg_name):
     for b in range(B):
         o = oracles[b]
         terms = go.derivative_terms(o)
-        if terms is None or out["status"][b] != 0:
-            assert res["status"][b] == 1 or terms is None
-            continue
+        assert out["status"][b] == 0 and terms is not None, "both sides solve every instance of this batch"
         assert res["status"][b] == 0
         ct = go.contact_times(o)
         assert [len(t) for t, _ in ct] == res["n_contacts"][b].tolist()
@@ -250,7 +313,14 @@ def test_gait_gradient_matches_oracle(cfg_name):
         # solver's final (lam, s); it is checked on identical inputs in test_gait_gradient_kernel_on_injected_solution
         # dual solution of the QP (north_star: primal / dual within 1e-4 relative): inequality multipliers in the reference's
         # row order, multipliers of the dynamics rows (recovered by the adjoint recursion) and of the touch-down / foot-start rows
-        assert _rel(sol["lam"][order], terms["lam"]) < 1e-4
+        # The multipliers themselves are unique only under strict complementarity: what the optimality conditions pin
+        # down is A_I' lam (= -(P z + q + A_E' nu)), compared at 1e-4; lam at 1e-4 where min(lam + s) shows a clean
+        # active set, 1e-2 on a weakly active one (measured 1.9e-3 on instance 1 of the N = 50 batch, whose gradient
+        # still agrees to 2e-7: tools/_graddiag.py)
+        qp = o.qp()
+        Ain = qp["A"][np.flatnonzero(~qp["is_eq"])]
+        assert _rel(Ain.T @ sol["lam"][order], Ain.T @ terms["lam"]) < 1e-4
+        assert _rel(sol["lam"][order], terms["lam"]) < (1e-4 if np.min(terms["lam"] + terms["slack"]) > 1e-3 else 1e-2)
         assert _rel(adj["nu_dyn"], terms["nu"][:nd]) < 1e-6
         n_eq_extra = len(terms["nu"]) - nd
         assert np.abs(sol["nu_eq"][:n_eq_extra] - terms["nu"][nd:]).max() <= 1e-4 * max(1.0, np.abs(terms["nu"]).max())
@@ -263,14 +333,14 @@ def test_gait_gradient_matches_oracle(cfg_name):
         assert g.shape == g_o.shape
         assert np.abs(g - g_o).max() <= 1e-4 * max(1.0, np.abs(g_o).max()), (g, g_o)
         checked += 1
-    assert checked >= 2
+    assert checked == B
 
 
 @pytest.mark.parametrize("cfg_name", ["a1_configuration", "a1_gait_opt_config"])
 def test_gait_gradient_kernel_on_injected_solution(cfg_name):
     """Kernel 6 in isolation: the oracle's primal / dual point and trajectory are written into the CUDA path's workspace,
     so both sides differentiate the same point.  The condensed LU + Schur complement + refinement then has to reproduce
-    the sparse LU of the full (n+m)^2 differential system: dz within 1e-5, dH/dtheta within 1e-8 relative."""
+    the sparse LU of the full (n+m)^2 differential system: dz within 1e-5 (of itself, or 1e-8 of the adjoint vector), dH/dtheta within 1e-7 relative."""
     cfg = wl.CONFIGS[cfg_name]
     N = cfg["num_nodes"]
     B = 3
@@ -284,8 +354,7 @@ def test_gait_gradient_kernel_on_injected_solution(cfg_name):
         o = oracles[b]
         terms = go.derivative_terms(o)
         all_terms.append(terms)
-        if terms is None:
-            continue
+        assert terms is not None, "the oracle solves every instance of this batch"
         sol = gpu.solution(b)
         order = common.gpu_rows_to_reference_order(sol, N)
         lam_k, s_k = np.zeros_like(sol["lam"]), np.zeros_like(sol["slack"])
@@ -296,18 +365,20 @@ def test_gait_gradient_kernel_on_injected_solution(cfg_name):
     checked = 0
     for b in range(B):
         terms = all_terms[b]
-        if terms is None:
-            continue
         assert res["status"][b] == 0
         adj = gpu.adjoint(b)
-        assert _rel(adj["dz"], terms["dz"]) < 1e-5
+        # dz against the scale of the adjoint vector it is a part of: on a nearly degenerate vertex (instance 2 of the N = 20
+        # batch: |dz| = 8e-7 next to |dnu| = 9e3) the constraints leave dz no room and its digits are cancellation noise in
+        # either factorisation, while the quantities that enter dH/dtheta agree to 1e-8
+        scale = max(np.abs(terms["dz"]).max(), np.abs(terms["dlam"]).max(), np.abs(terms["dnu"]).max())
+        assert np.abs(adj["dz"] - terms["dz"]).max() <= max(1e-5 * np.abs(terms["dz"]).max(), 1e-8 * scale)
         assert _rel(adj["nu_dyn"], terms["nu"][:nd]) < 1e-10
-        assert _rel(adj["dnu_dyn"], terms["dnu"][:nd]) < 1e-8
-        assert _rel(adj["dnu_eq"], terms["dnu"][nd:]) < 1e-8
+        assert _rel(adj["dnu_dyn"], terms["dnu"][:nd]) < 1e-7
+        assert _rel(adj["dnu_eq"], terms["dnu"][nd:]) < 1e-7
         g_o = go.cost_gradient(oracles[b], terms)
-        assert np.abs(res["dHdtheta"][b] - g_o).max() <= 1e-8 * max(1.0, np.abs(g_o).max())
+        assert np.abs(res["dHdtheta"][b] - g_o).max() <= 1e-7 * max(1.0, np.abs(g_o).max())
         checked += 1
-    assert checked >= 2
+    assert checked == B
 
 
 def test_gait_gradient_refuses_unsolved_instances():
@@ -316,11 +387,12 @@ def test_gait_gradient_refuses_unsolved_instances():
     cfg = wl.CONFIGS[cfg_name]
     B = 64
     states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=0)
+    ee[:, :, :2] += np.random.default_rng(5).uniform(-0.08, 0.08, (B, 4, 2))   # feet up to 10 cm off nominal: some QPs are infeasible
     gpu = common.make_gpu(cfg_name, B, states)
     out = gpu.GetRealTimeUpdate(states, t0, ee)
     res = gpu.ComputeCostFcnDerivWrtContactTimes()
     assert np.array_equal(res["status"] == 0, out["status"] == 0)
-    assert np.any(out["status"] != 0), "the first solve from pinned random feet leaves some instances infeasible"
+    assert np.any(out["status"] == 3) and np.any(out["status"] == 0), np.bincount(out["status"], minlength=9).tolist()
     for b in np.flatnonzero(out["status"] != 0):
         assert res["status"][b] == 1 and np.all(res["raw"][b] == 0)
     for b in np.flatnonzero(out["status"] == 0)[:8]:
@@ -345,6 +417,7 @@ def test_contact_time_lp_and_line_search_match_oracle(cfg_name):
     for b in range(B):
         o = oracles[b]
         ok = res["status"][b] == 0 and o.qp_solution()["status"] == 0
+        assert ok, "both sides solve every instance of this batch"
         g_os.append(go.cost_gradient(o) if ok else None)
         if ok:
             k = 0
@@ -400,7 +473,7 @@ def test_contact_time_lp_and_line_search_match_oracle(cfg_name):
         if ls["best"][b] != best_o:
             assert abs(costs_o[ls["best"][b]] - costs_o[best_o]) <= 1e-4 * max(1.0, abs(costs_o[best_o]))
         checked += 1
-    assert checked >= 2
+    assert checked == B
     # SetWarmStartTrajectory(best): the parent now carries the winning copy's contact times
     t_after, _, n_after = gpu.GetContactTimes()
     for b in range(B):
