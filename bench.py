@@ -86,13 +86,20 @@ def ipm_algorithmic_bytes(N, nu, n_samples, n_eebox, n_eq):
     return reads + writes
 
 
-def ipm_algorithmic_flops(N, nu, nf, iters, refine=1):
-    """FP64 flops of one k_ipm instance (2 per multiply-add), DESIGN.md "kernel 4": per interior-point iteration one K
-    assembly (rank-2(N-3) update of the nf x nf triangle), one nu^3/3 Cholesky, 2 (1 + refine) blocked substitution
-    pairs, 1 + 2 refine products with H and ~10 products with the structured C / C'; plus the start point."""
+def ipm_algorithmic_flops(N, nu, nf, n_samples, iters, refined_iters):
+    """FP64 flops of one k_ipm instance (2 per multiply-add), DESIGN.md "kernel 4".  Per factorisation (iters + 1: the
+    starting point has one): K assembly = rank-2(N-3) update of the nf x nf triangle, Cholesky nu^3/6.  Per iteration:
+    3 solves (constant, affine, combined right-hand side: nu^2 each, forward + backward), 1 product with H (nu^2),
+    4 products with the structured C and 4 with C' (dense position rows 2(N-3) nf + ~36 per force sample each).  An
+    iteration that runs with refinement (the kernel counts them: bgg_sizes.refined_iters) adds, for the constant and the
+    combined solve, one more solve, one product with H and one with C and C' each."""
     nkc = 2 * (N - 3)
-    per_it = 2 * (nkc * nf * (nf + 1) / 2 + nu ** 3 / 6 + 2 * (1 + refine) * nu * nu + (1 + 2 * refine) * nu * nu + 10 * nkc * nf)
-    return (iters + 1) * per_it
+    cprod = nkc * nf + 36 * n_samples
+    fact = nkc * nf * (nf + 1) / 2 + nu ** 3 / 6
+    per_it = 3 * nu * nu + nu * nu + 8 * cprod
+    per_ref = 2 * (nu * nu + nu * nu + 2 * cprod)
+    start = nu * nu + 2 * cprod
+    return 2 * ((iters + 1) * fact + iters * per_it + refined_iters * per_ref + start)
 
 
 def oracle_latency(cfg_name, solves):
@@ -161,6 +168,7 @@ def main():
                     help="BASELINE config #5: --scenarios closed-loop scenarios cut across the ranks (strong scaling); a step is one "
                          "closed-loop tick (plant step + RTI solve) of every scenario")
     ap.add_argument("--scenarios", type=int, default=65536)
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the short legs of BASELINE configs #3 and #5 after the headline")
     ap.add_argument("--gait-opt", type=int, default=0, metavar="K",
                     help="BASELINE config #3: per step every instance does solve -> dH/dtheta -> contact-time LP -> line search over "
                          "K candidates (K + 1 RTI solves per instance and step); use with --config a1_gait_opt_config --batch 64")
@@ -189,8 +197,8 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "note": "CPU oracle (restated reference algorithm, interior-point QP); "
-                           "the reference binary needs Eigen/pinocchio/Clarabel which are absent from this image"},
+                "config": {"workload": workload, "note": "CPU oracle (restated reference algorithm: same assembly, Clarabel's interior-point algorithm "
+                           "with an envelope LDL'); the reference binary needs Eigen/pinocchio/Clarabel which are absent from this image"},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": f"{sample} instances x {args.steps} RTI solves on {cores} threads"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -213,165 +221,215 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    B, N = args.batch, cfg["num_nodes"]
-    if args.closed_loop:
-        lo, hi = sharding.shard_range(args.scenarios, rank, world)
-        B = hi - lo
-        states, t0, ee = wl.disturbance_sweep_inputs(cfg, args.scenarios, seed=7)
-        states, t0, ee = states[lo:hi].copy(), t0[lo:hi].copy(), ee[lo:hi].copy()
-    else:
-        states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=1000 + rank)
-    mpc = bg.BatchedMPC(N, cfg["integrator_dt"], wl.robot(), device=local_rank, ipm_refine=args.ipm_refine, ipm_refine_after=args.ipm_refine_after,
-                        max_spline_vars=args.max_spline_vars, **wl.mpc_kwargs(cfg))
-    mpc.AddQuadraticTrackingCost(wl.target_tangent(cfg), np.asarray(cfg["Q"], float))
-    mpc.Reset(B)
-    mpc.SetStateTrajectoryWarmStart(states)
+    def make_mpc(cfg_name, batch, states):
+        c = wl.CONFIGS[cfg_name]
+        m = bg.BatchedMPC(c["num_nodes"], c["integrator_dt"], wl.robot(), device=local_rank, ipm_refine=args.ipm_refine,
+                          ipm_refine_after=args.ipm_refine_after, max_spline_vars=args.max_spline_vars, **wl.mpc_kwargs(c))
+        m.AddQuadraticTrackingCost(wl.target_tangent(c), np.asarray(c["Q"], float))
+        m.Reset(batch)
+        m.SetStateTrajectoryWarmStart(states)
+        return m
 
-    # ---- device-resident throughput: inputs already in HBM, K solves timed with CUDA events on the launching stream
-    dt_plant = cfg["integrator_dt"]
-    gait_stats = {"grad_ok": 0, "best_hist": np.zeros(max(args.gait_opt, 1), np.int64)}
+    def run_leg(cfg_name, mode, batch, steps, warmup, gait_k=0, scenarios=0, detail=False):
+        """One timed leg.  mode: 'solve' (config #2: `batch` instances per GPU, weak scaling), 'gait' (config #3: per step solve
+        + dH/dtheta + contact-time LP + line search over gait_k candidates) or 'closed_loop' (config #5: `scenarios`
+        closed-loop scenarios cut across the ranks, strong scaling).  Device time with CUDA events on the launching stream,
+        barrier + synchronise on both sides, max over ranks; end-to-end time through the host-buffer API with the decision
+        vectors copied back every step."""
+        c = wl.CONFIGS[cfg_name]
+        N = c["num_nodes"]
+        if mode == "closed_loop":
+            lo, hi = sharding.shard_range(scenarios, rank, world)
+            B = hi - lo
+            st, t0, ee = wl.disturbance_sweep_inputs(c, scenarios, seed=7)
+            st, t0, ee = st[lo:hi].copy(), t0[lo:hi].copy(), ee[lo:hi].copy()
+        else:
+            B = batch
+            st, t0, ee = wl.batched_trot_inputs(c, B, seed=1000 + rank)
+        mpc = make_mpc(cfg_name, B, st)
+        dt_plant = c["integrator_dt"]
+        gait_stats = {"grad_ok": 0, "best_hist": np.zeros(max(gait_k, 1), np.int64)}
+        n_max = 12 * (N + 1) + (args.max_spline_vars or 160)
+        z_host = np.zeros((B, n_max))
 
-    def step():
-        if args.closed_loop:
-            mpc.advance_plant(dt_plant)
-        mpc.solve_resident()
-        if args.gait_opt:   # MPCController::GaitOpt + GaitOptimizer::LineSearch for every instance of the batch
+        def gait_tail():   # MPCController::GaitOpt + GaitOptimizer::LineSearch for every instance of the batch
             g = mpc.ComputeCostFcnDerivWrtContactTimes()
             lp = mpc.OptimizeContactTimes(t0)
-            ls = mpc.LineSearch(states, t0, ee, lp["xk"], lp["step"], K=args.gait_opt)
+            ls = mpc.LineSearch(st, t0, ee, lp["xk"], lp["step"], K=gait_k)
             gait_stats["grad_ok"] = int((g["status"] == 0).sum())
-            gait_stats["best_hist"] += np.bincount(np.maximum(ls["best"], 0), minlength=args.gait_opt)
+            gait_stats["best_hist"] += np.bincount(np.maximum(ls["best"], 0), minlength=gait_k)
 
-    mpc.upload(states, t0, ee)
-    mpc.solve_resident()
-    for _ in range(args.warmup):
-        step()
-    mpc.synchronize()
+        def step():
+            if mode == "closed_loop":
+                mpc.advance_plant(dt_plant)
+            mpc.solve_resident()
+            if mode == "gait":
+                gait_tail()
+
+        mpc.upload(st, t0, ee)
+        mpc.solve_resident()
+        for _ in range(warmup):
+            step()
+        mpc.synchronize()
+        barrier()
+        l0 = mpc.launch_count()
+        mpc.event_record(0)
+        for _ in range(steps):
+            step()
+        mpc.event_record(1)
+        ms_dev = mpc.event_elapsed_ms(0, 1)
+        barrier()
+        launches = mpc.launch_count() - l0
+        res = mpc.download()
+        out = {"B": B, "N": N, "mpc": mpc, "res": res, "launches": launches, "sizes": mpc.sizes(0), "gait_stats": gait_stats}
+
+        kms = None
+        if detail:   # per-kernel device time (CUDA events around each launch) over another `steps` steps, for the roofline entry
+            mpc.set_profiling(True)
+            kms = {"prepare": 0.0, "condense": 0.0, "ipm": 0.0, "finish": 0.0}
+            for _ in range(steps):
+                step()
+                for k, v in mpc.last_kernel_ms().items():
+                    kms[k] += v / steps
+            mpc.set_profiling(False)
+            refined = [mpc.sizes(b)["refined_iters"] for b in range(0, B, max(1, B // 64))]
+            out["mean_refined_iters"] = float(np.mean(refined))
+        out["kernel_ms"] = kms
+
+        # end to end through the public call with HOST buffers: H2D of the step's inputs and D2H of its results (status, iteration
+        # count, step length, cost AND the decision vector a controller consumes) inside the timed region
+        barrier()
+        t_start = time.perf_counter()
+        for _ in range(steps):
+            if mode == "closed_loop":   # the plant lives on the device: no inputs travel, the per-scenario results do
+                mpc.advance_plant(dt_plant)
+                mpc.solve_resident()
+                res2 = mpc.download(z_out=z_host)
+            else:
+                res2 = mpc.GetRealTimeUpdate(st, t0, ee, z_out=z_host)
+                if mode == "gait":
+                    gait_tail()
+        mpc.synchronize()
+        e2e_s = time.perf_counter() - t_start
+        barrier()
+        assert np.all(np.isfinite(z_host[res2["status"] == 0]))
+        total = scenarios if mode == "closed_loop" else B * world
+        status = res["status"].astype(np.int32)
+        if world > 1:
+            ms_dev, e2e_s = sharding.max_over_ranks([ms_dev, e2e_s], dist, "cuda")
+            # the only data-path collective: gather of the per-instance results (status) at the end of the batch
+            status = sharding.gather_to_root(status, total, dist, "cuda")
+        spi = 1 + (gait_k if mode == "gait" else 0)
+        out.update({"ms_dev": ms_dev, "e2e_s": e2e_s, "total": total, "solves_per_instance": spi,
+                    "value": total * spi * steps / (ms_dev * 1e-3), "e2e_value": total * spi * steps / e2e_s,
+                    "solved_fraction": (float(np.isin(status, (0, 1)).mean()) if rank == 0 else None),
+                    "h2d": 0 if mode == "closed_loop" else B * (13 + 1 + 12) * 8,
+                    "d2h": B * (2 * 4 + 2 * 8 + 8 * n_max) + (B * (4 * 12 * 8 + 16 + 4 + gait_k * 12) if mode == "gait" else 0)})
+        return out
+
+    main_mode = "closed_loop" if args.closed_loop else ("gait" if args.gait_opt else "solve")
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
-    l0 = mpc.launch_count()
-    mpc.event_record(0)
-    for _ in range(args.steps):
-        step()
-    mpc.event_record(1)
-    ms_dev = mpc.event_elapsed_ms(0, 1)
-    barrier()
-    launches = mpc.launch_count() - l0
-    res = mpc.download()
-    solved = int(np.isin(res["status"], (0, 1)).sum())
-
-    # ---- per-kernel device time (CUDA events around each launch) over another K steps, for the roofline entry
-    mpc.set_profiling(True)
-    kms = {"prepare": 0.0, "condense": 0.0, "ipm": 0.0, "finish": 0.0}
-    for _ in range(args.steps):
-        step()
-        for k, v in mpc.last_kernel_ms().items():
-            kms[k] += v / args.steps
-    mpc.set_profiling(False)
-
-    # ---- end to end through the public call with HOST buffers: H2D of the step's inputs and D2H of its results inside
-    barrier()
-    t_start = time.perf_counter()
-    for _ in range(args.steps):
-        if args.closed_loop:   # the plant lives on the device: no inputs travel, the per-instance results do
-            mpc.advance_plant(dt_plant)
-            mpc.solve_resident()
-            res = mpc.download()
-        else:
-            res = mpc.GetRealTimeUpdate(states, t0, ee)
-    mpc.synchronize()
-    e2e_s = time.perf_counter() - t_start
-    barrier()
+    leg = run_leg(args.config, main_mode, args.batch, args.steps, args.warmup, gait_k=args.gait_opt, scenarios=args.scenarios, detail=True)
     clocks = sampler.stop()
+    mpc, res, sz, kms, B, N = leg["mpc"], leg["res"], leg["sizes"], leg["kernel_ms"], leg["B"], leg["N"]
 
     # ---- single-instance latency (BASELINE metric's second half): one MPC, host buffers in, results out, per call
     lat = None
     if rank == 0:
-        one = bg.BatchedMPC(N, cfg["integrator_dt"], wl.robot(), device=local_rank, ipm_refine=args.ipm_refine, ipm_refine_after=args.ipm_refine_after, **wl.mpc_kwargs(cfg))
-        one.AddQuadraticTrackingCost(wl.target_tangent(cfg), np.asarray(cfg["Q"], float))
-        one.Reset(1)
         init = np.asarray(cfg["srb_init"], float)[None]
-        one.SetStateTrajectoryWarmStart(init)
+        one = make_mpc(args.config, 1, init)
         ee1 = wl.EE_NOMINAL[None].copy()
         one.CreateInitialRun(init, ee1)
+        z1 = np.zeros((1, 12 * (N + 1) + 160))
         ts = []
         for _ in range(args.latency_solves):
             t = time.perf_counter()
-            r1 = one.GetRealTimeUpdate(init, np.zeros(1), ee1)
+            r1 = one.GetRealTimeUpdate(init, np.zeros(1), ee1, z_out=z1)
             ts.append(1e3 * (time.perf_counter() - t))
         lat = {"p50_ms": float(np.percentile(ts, 50)), "p95_ms": float(np.percentile(ts, 95)), "solves": len(ts),
                "status": int(r1["status"][0]), "ipm_iters": int(r1["iters"][0]),
-               "what": "bgg_solve_batch with batch = 1 (host buffers in, results out), wall clock per call"}
+               "what": "bgg_solve_batch with batch = 1 (host buffers in; status, cost and the decision vector out), wall clock per call"}
         one.close()
+    mpc.close()
 
-    total = args.scenarios if args.closed_loop else B * world
-    if world > 1:
-        ms_dev, e2e_s = sharding.max_over_ranks([ms_dev, e2e_s], dist, "cuda")
-        # the only data-path collective: gather of the per-instance results (status) at the end of the batch
-        if args.closed_loop:
-            g = sharding.gather_to_root(res["status"].astype(np.int32), total, dist, "cuda")
-        else:   # weak scaling: every rank holds `B` instances
-            g = sharding.gather_to_root(res["status"].astype(np.int32), B * world, dist, "cuda")
-        if rank == 0:
-            solved = int(np.isin(g, (0, 1)).sum())
+    # ---- the other GPU configurations of BASELINE.json under the same timing rules (short legs): #3 gait optimisation with 64
+    #      candidates, #5 the 65 536-scenario closed-loop sweep cut across the ranks (strong scaling)
+    extra = {}
+    if main_mode == "solve" and not args.no_extra_configs:
+        g3 = run_leg("a1_gait_opt_config", "gait", 64, 3, 1, gait_k=64)
+        g3["mpc"].close()
+        extra["#3"] = {"workload": "a1_gait_opt_config: N=50, 64 instances per GPU, per step solve + dH/dtheta + contact-time LP + line search over 64 candidates (65 RTI solves per instance)",
+                       "value": g3["value"], "unit": UNIT, "scaling": "weak", "steps": 3, "warmup": 1, "ms_per_step": g3["ms_dev"] / 3,
+                       "gait_steps_per_s": g3["total"] * 3 / (g3["ms_dev"] * 1e-3), "e2e": g3["e2e_value"],
+                       "instances_with_gradient": g3["gait_stats"]["grad_ok"], "solved_fraction_parents": g3["solved_fraction"]}
+        c5 = run_leg("a1_config_distr_rejection", "closed_loop", 0, 5, 2, scenarios=args.scenarios)
+        c5["mpc"].close()
+        extra["#5"] = {"workload": f"a1_config_distr_rejection: N=50, {args.scenarios} closed-loop scenarios cut across {world} GPU(s), a step = plant step + RTI solve of every scenario",
+                       "value": c5["value"], "unit": UNIT, "scaling": "strong", "steps": 5, "warmup": 2, "ms_per_step": c5["ms_dev"] / 5,
+                       "e2e": c5["e2e_value"], "solved_fraction": c5["solved_fraction"]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    solves_per_instance = 1 + args.gait_opt
-    value = total * solves_per_instance * args.steps / (ms_dev * 1e-3)
-    sz = mpc.sizes(0)
     peaks = {}
     if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             peaks = json.load(f)
     hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     alg_bytes = B * ipm_algorithmic_bytes(N, sz["nu"], sz["n_samples"], sz["n_eebox"], sz["n_eq"])
-    achieved = alg_bytes / (kms["ipm"] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ipm_dram_bytes_per_launch.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f)
+    mean_iters = float(np.mean(res["iters"]))
+    flops = B * ipm_algorithmic_flops(N, sz["nu"], sz["nf"], sz["n_samples"], mean_iters, leg["mean_refined_iters"])
+    try:
+        fp64_peak, fp64_src = bg.measure_fp64_peak(local_rank), "measured in this run: register-resident FP64 FMA chains (bgg_measure_fp64_peak)"
+    except Exception as e:  # noqa: BLE001
+        fp64_peak, fp64_src = 37.0, f"fallback, nominal ({e})"
+    tf = flops / (kms["ipm"] * 1e-3) / 1e12
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if args.closed_loop else "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
+        "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": leg["ms_dev"] / args.steps, "higher_is_better": True, "scaling": "strong" if args.closed_loop else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "decision_vars": sz["n"], "spline_vars": sz["nu"],
-                   "ineq_rows": sz["m_ineq"], "eq_rows": 12 * (N + 1) + sz["n_eq"], "qp_solver": "interior point, tol 1e-8",
+                   "ineq_rows": sz["m_ineq"], "eq_rows": 12 * (N + 1) + sz["n_eq"],
+                   "qp_solver": "interior point (homogeneous self-dual embedding, Clarabel's algorithm), tolerances 1e-8",
                    "l2": "inputs larger than L2 (instance + workspace state is > 1 GB per 4096 instances)",
-                   "solved_fraction": solved / total, "mean_ipm_iters": float(np.mean(res["iters"]))},
+                   "solved_fraction": leg["solved_fraction"], "mean_ipm_iters": mean_iters, "mean_refined_iters": leg["mean_refined_iters"]},
         "clocks": clocks,
-        "e2e": {"value": total * (1 if not args.gait_opt else 1) * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0 if args.closed_loop else B * (13 + 1 + 12) * 8,
-                "d2h_bytes_per_step": B * 248, "timing": "wall clock around bgg_solve_batch, synchronised both sides"},
-        "gpu_launches": int(launches),
-        "gait_opt": ({"candidates": args.gait_opt, "instances_with_gradient": gait_stats["grad_ok"],
-                      "argmin_histogram": gait_stats["best_hist"].tolist(),
-                      "gait_steps_per_s": total * args.steps / (ms_dev * 1e-3)} if args.gait_opt else None),
+        "e2e": {"value": leg["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": leg["h2d"], "d2h_bytes_per_step": leg["d2h"],
+                "timing": "wall clock around the host-buffer call (bgg_solve_batch: inputs up, status / iterations / step length / cost and "
+                          "the decision vector of every instance back), synchronised both sides"},
+        "gpu_launches": int(leg["launches"]),
+        "gait_opt": ({"candidates": args.gait_opt, "instances_with_gradient": leg["gait_stats"]["grad_ok"],
+                      "argmin_histogram": leg["gait_stats"]["best_hist"].tolist(),
+                      "gait_steps_per_s": leg["total"] * args.steps / (leg["ms_dev"] * 1e-3)} if args.gait_opt else None),
         "kernel_ms": kms,
         "latency": lat,
-        "roofline": {"kernel": "k_ipm", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                     "note": "FP64-pipe / latency bound by design: the QP is shared-memory resident, HBM holds only its "
-                             "compulsory inputs and outputs"},
+        # the bound that binds: k_ipm keeps its QP in shared memory for the ~17 iterations of a solve, HBM sees only the
+        # compulsory inputs and outputs (secondary entry below)
+        "roofline": {"kernel": "k_ipm", "bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                     "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                     "traffic_source": (traffic or {}).get("source", "none: no ncu capture of this build committed"),
+                     "peak_source": fp64_src,
+                     "flops_per_launch": flops, "kernel_share_of_step": kms["ipm"] / sum(kms.values()),
+                     "hbm": {"achieved": alg_bytes / (kms["ipm"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes / (kms["ipm"] * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg_bytes}},
+        "configs": extra or None,
     }
-    # FP64 pipe: the ceiling that does bound k_ipm (north_star: "FP64 pipe utilisation reported against B200 peak")
-    try:
-        fp64_peak = bg.measure_fp64_peak(local_rank)
-        flops = B * ipm_algorithmic_flops(N, sz["nu"], sz["nf"], float(np.mean(res["iters"])))
-        line["fp64"] = {"kernel": "k_ipm", "achieved_tflops": flops / (kms["ipm"] * 1e-3) / 1e12, "peak_tflops": fp64_peak,
-                        "frac": flops / (kms["ipm"] * 1e-3) / 1e12 / fp64_peak,
-                        "peak_source": "measured here: register-resident FMA chains (bgg_measure_fp64_peak)"}
-    except Exception as e:  # noqa: BLE001
-        line["fp64"] = {"error": str(e)}
     if world == 1:
         sample = args.cpu_sample or 8 * cores
         v, el = oracle_throughput(args.config, sample, 20, 2, cores)
         p50, p95 = oracle_latency(args.config, 30)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{sample} instances x 20 RTI solves (2 warm-up) on {cores} threads, {el:.1f} s",
+                                "what": "restated reference algorithm (same assembly, Clarabel's interior-point algorithm with an envelope LDL'); "
+                                        "not the reference binary, which needs Eigen / pinocchio / Clarabel (absent here)",
+                                "sample": f"{sample} instances of the same synthetic workload x 20 RTI solves (2 warm-up) on {cores} threads, {el:.1f} s",
                                 "latency_p50_ms": p50, "latency_p95_ms": p95}
     print(json.dumps(line))
     if world > 1:

@@ -43,7 +43,8 @@ class Sizes(C.Structure):
                                          "iters", "ls_iters", "error")] + \
                [("nfv", C.c_int32 * 4), ("npv", C.c_int32 * 4), ("fbase", C.c_int32 * 4), ("pbase", C.c_int32 * 4)] + \
                [(n, C.c_double) for n in ("t0", "alpha", "cost", "prim_res", "dual_res", "gap", "eq_violation", "step_norm",
-                                          "merit", "merit_dd")] + [("ee_box", C.c_double * 2), ("qp_cost", C.c_double)]
+                                          "merit", "merit_dd")] + [("ee_box", C.c_double * 2), ("qp_cost", C.c_double),
+                                                                     ("refined_iters", C.c_int32), ("no_iterate", C.c_int32)]
 
 
 # numpy view of the POD bgg::Instance / bgg::FootSpline (csrc/bgg_types.cuh)
@@ -71,10 +72,10 @@ def lib():
         L.bgg_batch_reset.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int]
         L.bgg_set_warm_states.argtypes = [C.c_void_p, _dp, C.c_int]
         L.bgg_set_contact_times.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, C.c_int]
-        L.bgg_solve_batch.argtypes = [C.c_void_p, _dp, _dp, _dp, _ip, _ip, _dp, _dp]
+        L.bgg_solve_batch.argtypes = [C.c_void_p, _dp, _dp, _dp, _ip, _ip, _dp, _dp, _dp, C.c_int]
         L.bgg_upload_inputs.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.bgg_solve_resident.argtypes = [C.c_void_p]
-        L.bgg_download_results.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp]
+        L.bgg_download_results.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, _dp, C.c_int]
         L.bgg_synchronize.argtypes = [C.c_void_p]
         L.bgg_advance_plant.argtypes = [C.c_void_p, C.c_double]
         L.bgg_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -215,13 +216,18 @@ class BatchedMPC:
         self._chk(self.L.bgg_set_contact_times(self.h, first, t.shape[0], _d(t), t.shape[2]))
 
     # --- solves ---------------------------------------------------------------------------------------------------
-    def GetRealTimeUpdate(self, state, init_time, ee_start_locations):
-        """One RTI solve per instance. Returns dict(status, iters, alpha, cost) of numpy arrays [B]."""
+    def GetRealTimeUpdate(self, state, init_time, ee_start_locations, z_out=None):
+        """One RTI solve per instance. Returns dict(status, iters, alpha, cost) of numpy arrays [B]; with z_out (a float64
+        array [B][z_stride]) also the decision vectors after the line-search update (MPC::GetQPSolution) in z_out."""
         s, t, e = self._inputs(state, init_time, ee_start_locations)
         st, it = np.zeros(self.B, np.int32), np.zeros(self.B, np.int32)
         al, co = np.zeros(self.B), np.zeros(self.B)
-        self._chk(self.L.bgg_solve_batch(self.h, _d(s), _d(t), _d(e), _i(st), _i(it), _d(al), _d(co)))
-        return dict(status=st, iters=it, alpha=al, cost=co)
+        zp, zs = (None, 0) if z_out is None else (_d(z_out), z_out.shape[1])
+        self._chk(self.L.bgg_solve_batch(self.h, _d(s), _d(t), _d(e), _i(st), _i(it), _d(al), _d(co), zp, zs))
+        out = dict(status=st, iters=it, alpha=al, cost=co)
+        if z_out is not None:
+            out["z"] = z_out
+        return out
 
     Solve = GetRealTimeUpdate
 
@@ -246,11 +252,15 @@ class BatchedMPC:
     def solve_resident(self):
         self._chk(self.L.bgg_solve_resident(self.h))
 
-    def download(self):
+    def download(self, z_out=None):
         st, it = np.zeros(self.B, np.int32), np.zeros(self.B, np.int32)
         al, co = np.zeros(self.B), np.zeros(self.B)
-        self._chk(self.L.bgg_download_results(self.h, _i(st), _i(it), _d(al), _d(co)))
-        return dict(status=st, iters=it, alpha=al, cost=co)
+        zp, zs = (None, 0) if z_out is None else (_d(z_out), z_out.shape[1])
+        self._chk(self.L.bgg_download_results(self.h, _i(st), _i(it), _d(al), _d(co), zp, zs))
+        out = dict(status=st, iters=it, alpha=al, cost=co)
+        if z_out is not None:
+            out["z"] = z_out
+        return out
 
     def advance_plant(self, dt):
         self._chk(self.L.bgg_advance_plant(self.h, dt))

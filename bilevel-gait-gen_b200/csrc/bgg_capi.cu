@@ -37,6 +37,9 @@ struct bgg_handle {
     double *h_state = nullptr, *h_t0 = nullptr, *h_ee = nullptr;
     WsHeader* h_hdr = nullptr;   // pinned [batch]
     WsHeader* d_hdr = nullptr;   // compact copy of the headers [batch]
+    double* d_zout = nullptr;    // compact copy of the decision vectors [batch][zcap], allocated on first use
+    double* h_zout = nullptr;    // pinned
+    int zcap = 0;
     int* d_max = nullptr;        // batch maxima (nu, n_samples) of the current solve
     int* h_max = nullptr;        // pinned
     int last_nu_max = 0, last_ns_max = 0;   // batch maxima of the last solve (shared-memory sizing of later kernels)
@@ -53,6 +56,15 @@ struct bgg_handle {
     char* d_ls_ws = nullptr;
     double *d_ls_state = nullptr, *d_ls_t0 = nullptr, *d_ls_ee = nullptr;
 };
+
+// decision vectors after the line-search update, compacted to [B][stride] (entries n .. stride-1 of a row are zero)
+__global__ void k_gather_z(WsLayout L, const char* __restrict__ ws, double* __restrict__ out, int stride) {
+    const int b = blockIdx.x;
+    const char* w = ws + static_cast<size_t>(b) * L.stride;
+    const int n = reinterpret_cast<const WsHeader*>(w + L.hdr)->n;
+    const double* z = reinterpret_cast<const double*>(w + L.zprev);
+    for (int i = threadIdx.x; i < stride; i += blockDim.x) out[static_cast<size_t>(b) * stride + i] = (i < n) ? z[i] : 0.0;
+}
 
 __global__ void k_gather_headers(WsLayout L, const char* __restrict__ ws, WsHeader* __restrict__ out, int B) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,6 +254,10 @@ static void free_batch(bgg_handle* h) {
     cudaFree(h->d_t0);
     cudaFree(h->d_ee);
     cudaFree(h->d_hdr);
+    cudaFree(h->d_zout);
+    cudaFreeHost(h->h_zout);
+    h->d_zout = h->h_zout = nullptr;
+    h->zcap = 0;
     cudaFreeHost(h->h_state);
     cudaFreeHost(h->h_t0);
     cudaFreeHost(h->h_ee);
@@ -407,14 +423,39 @@ int bgg_advance_plant(bgg_handle* h, double dt) {
     return BGG_OK;
 }
 
-int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double* alpha, double* cost) {
+int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double* alpha, double* cost, double* z, int z_stride) {
     if (!h || !h->batch) return fail(BGG_EINVAL, "no batch");
+    if (z && z_stride < kNx * (h->P.N + 1)) return fail(BGG_EINVAL, "z_stride is smaller than the state part of the decision vector");
     CU(cudaSetDevice(h->device));
     const int B = h->batch;
     k_gather_headers<<<(B + 127) / 128, 128, 0, h->stream>>>(h->L, h->d_ws, h->d_hdr, B);
     h->launches += 1;
     CU(cudaMemcpyAsync(h->h_hdr, h->d_hdr, sizeof(WsHeader) * static_cast<size_t>(B), cudaMemcpyDeviceToHost, h->stream));
+    if (z) {
+        const int n_max = kNx * (h->P.N + 1) + h->P.max_nu;
+        const int stride = z_stride < n_max ? z_stride : n_max;
+        if (h->zcap < stride) {
+            cudaFree(h->d_zout);
+            cudaFreeHost(h->h_zout);
+            h->d_zout = h->h_zout = nullptr;
+            h->zcap = 0;
+            CU(cudaMalloc(&h->d_zout, 8 * static_cast<size_t>(B) * n_max));
+            CU(cudaMallocHost(&h->h_zout, 8 * static_cast<size_t>(B) * n_max));
+            h->zcap = n_max;
+        }
+        k_gather_z<<<B, 128, 0, h->stream>>>(h->L, h->d_ws, h->d_zout, stride);
+        h->launches += 1;
+        CU(cudaMemcpyAsync(h->h_zout, h->d_zout, 8 * static_cast<size_t>(B) * stride, cudaMemcpyDeviceToHost, h->stream));
+    }
     CU(cudaStreamSynchronize(h->stream));
+    if (z) {
+        const int n_max = kNx * (h->P.N + 1) + h->P.max_nu;
+        const int stride = z_stride < n_max ? z_stride : n_max;
+        for (int b = 0; b < B; ++b) {
+            if (!h->h_hdr[b].error && h->h_hdr[b].n > z_stride) return fail(BGG_EINVAL, "an instance has more decision variables than z_stride");
+            std::memcpy(z + static_cast<size_t>(b) * z_stride, h->h_zout + static_cast<size_t>(b) * stride, 8 * static_cast<size_t>(stride));
+        }
+    }
     for (int b = 0; b < B; ++b) {
         const WsHeader& w = h->h_hdr[b];
         if (status) status[b] = w.error ? BGG_OTHER : w.status;
@@ -428,12 +469,12 @@ int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double*
 }
 
 int bgg_solve_batch(bgg_handle* h, const double* state, const double* t0, const double* ee_start, int32_t* status,
-                    int32_t* iters, double* alpha, double* cost) {
+                    int32_t* iters, double* alpha, double* cost, double* z, int z_stride) {
     int rc = bgg_upload_inputs(h, state, t0, ee_start);
     if (rc) return rc;
     rc = bgg_solve_resident(h);
     if (rc) return rc;
-    return bgg_download_results(h, status, iters, alpha, cost);
+    return bgg_download_results(h, status, iters, alpha, cost, z, z_stride);
 }
 
 int bgg_synchronize(bgg_handle* h) {
@@ -502,6 +543,8 @@ int bgg_get_sizes(bgg_handle* h, int b, bgg_sizes* out) {
     out->gap = w.gap; out->eq_violation = w.eq_violation; out->step_norm = w.step_norm; out->merit = w.merit;
     out->merit_dd = w.merit_dd; out->ee_box[0] = w.ee_box[0]; out->ee_box[1] = w.ee_box[1];
     out->qp_cost = w.qp_cost;
+    out->refined_iters = w.refined_iters;
+    out->no_iterate = w.no_iterate;
     return BGG_OK;
 }
 

@@ -458,6 +458,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     double tau = 1.0, kap = 1.0, mu_first = 0.0;
     double res_p = 0, res_d = 0, gap = 0, gscale = 1, bz = 0, aty_n = 0, zn = 1, pc = 0;
     bool have_point = false;
+    int n_refined = 0;
     for (it = -1; it <= P.ipm_max_iter; ++it) {
         double uHu = 0, rt = 0, mu = 0;
         bool refine_now = false;
@@ -534,7 +535,8 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             // refinement of the solves pays for itself only once W = z / s has spread over many decades: it starts when mu
             // has fallen to ipm_refine_mu_frac of its first value
             if (it == 0) mu_first = mu;
-            refine_now = mu <= P.ipm_refine_mu_frac * mu_first;
+            refine_now = P.ipm_refine > 0 && mu <= P.ipm_refine_mu_frac * mu_first;
+            n_refined += refine_now ? 1 : 0;
         }
         if (!build_and_factor()) {
             status = kOther;
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             __syncthreads();
             PROF(14);
             add_Ct(S.ds, x, S.a3, inv_delta);
-            solve_K(x, refine_now && P.ipm_refine > 0 && pass != 1);   // the affine step only steers sigma: not refined
+            solve_K(x, refine_now && pass != 1);   // the affine step only steers sigma: not refined
             double* yx = (pass == 0) ? S.y1 : S.dnu;
             apply_C(x, tslot, yx, 0.0);
             if (tid < neq) yx[tid] = (yx[tid] - S.a3[tid]) * inv_delta;
@@ -731,6 +733,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     if (tid == 0) {
         Hd->status = status;
         Hd->no_iterate = have_point ? 0 : 1;
+        Hd->refined_iters = n_refined;
         Hd->iters = it;
         Hd->prim_res = res_p;
         Hd->dual_res = res_d;

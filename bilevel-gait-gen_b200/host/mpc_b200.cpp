@@ -230,7 +230,7 @@ Trajectory MPC::Solve(const vector_t& state, double init_time, const std::vector
     FlattenEE(ee_start_locations, ee);
     int32_t status = 0, iters = 0;
     const auto tic = std::chrono::steady_clock::now();   // utils::Timer, utils/timer.cpp:16-23
-    Check(bgg_solve_batch(h_, state.data(), &init_time, ee, &status, &iters, &alpha_, &cost_));
+    Check(bgg_solve_batch(h_, state.data(), &init_time, ee, &status, &iters, &alpha_, &cost_, nullptr, 0));
     last_solve_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tic).count();
     quality_ = static_cast<SolveQuality>(status);
     iters_ = iters;

@@ -102,14 +102,17 @@ int bgg_set_contact_times(bgg_handle* h, int first, int count, const double* tim
 
 /* One RTI solve for every instance: MPC::GetRealTimeUpdate -> MPCSingleRigidBody::Solve
  * (mpc.cpp:92-108, mpc_single_rigid_body.cpp:25-216).  state [batch][13], t0 [batch], ee_start [batch][4][3].
- * Output arrays may be NULL.  status/iters/ls_iters are int32 [batch]; alpha/cost are double [batch]. */
+ * Output arrays may be NULL.  status/iters are int32 [batch]; alpha/cost are double [batch]; z [batch][z_stride] receives what
+ * the caller of the reference reads back, the decision vector after the line-search update (MPC::GetQPSolution, mpc.cpp:
+ * 1071-1073: [x_0 .. x_N (12 each, tangent) | force spline variables | position spline variables], n <= z_stride entries
+ * per instance, the rest of a row untouched; BGG_EINVAL if an instance has more than z_stride variables). */
 int bgg_solve_batch(bgg_handle* h, const double* state, const double* t0, const double* ee_start, int32_t* status,
-                    int32_t* iters, double* alpha, double* cost);
+                    int32_t* iters, double* alpha, double* cost, double* z, int z_stride);
 
 /* The same solve split for measurement: copy inputs to HBM once, run the kernels on resident data, fetch results. */
 int bgg_upload_inputs(bgg_handle* h, const double* state, const double* t0, const double* ee_start);
 int bgg_solve_resident(bgg_handle* h);
-int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double* alpha, double* cost);
+int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double* alpha, double* cost, double* z, int z_stride);
 int bgg_synchronize(bgg_handle* h);
 /* Closed-loop sweeps on resident data: replace every instance's inputs by the model's own next step -- state = node 1 of
  * the solved trajectory (the plant of apps/mpc_demo.cpp:185 and test/gait_opt_playground.cpp:128), t0 += dt, measured
@@ -132,6 +135,8 @@ typedef struct bgg_sizes {
     double t0, alpha, cost, prim_res, dual_res, gap, eq_violation, step_norm, merit, merit_dd;
     double ee_box[2]; /* foot-box size the last QP was built with (the adapted size lives in the instance) */
     double qp_cost; /* objective of the QP optimum, 1/2 z'Pz + q'z */
+    int32_t refined_iters; /* interior-point iterations of the last solve that ran with iterative refinement */
+    int32_t no_iterate;    /* the solver stopped before its first finite residual evaluation (status Other, previous solution kept) */
 } bgg_sizes;
 int bgg_get_sizes(bgg_handle* h, int instance, bgg_sizes* out);
 
