@@ -312,7 +312,8 @@ def main():
         mpc.synchronize()
         e2e_s = time.perf_counter() - t_start
         barrier()
-        assert np.all(np.isfinite(z_host[res2["status"] == 0]))
+        zs = z_host[res2["status"] == 0]
+        assert np.all(np.isfinite(zs)) and (len(zs) == 0 or np.all(np.abs(zs).max(axis=1) > 0)), "the decision vectors did not come back"
         total = scenarios if mode == "closed_loop" else B * world
         status = res["status"].astype(np.int32)
         if world > 1:

@@ -11,7 +11,7 @@
 using namespace bgg;
 
 static_assert(BGG_MAX_CONTACTS == kMaxContacts, "include/bgg.h and csrc/bgg_ws.cuh disagree");
-static_assert(sizeof(WsHeader) == 248, "bench.py reports the per-instance result record as 248 bytes");
+static_assert(sizeof(WsHeader) == 256, "per-instance result record (header) is 256 bytes");
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -226,7 +226,7 @@ int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) 
     P.ipm_tol_infeas = cfg->ipm_tol_infeas > 0 ? cfg->ipm_tol_infeas : 1e-8;
     P.ipm_max_iter = cfg->ipm_max_iter > 0 ? cfg->ipm_max_iter : 50;
     P.ipm_refine = cfg->ipm_refine < 0 ? 0 : (cfg->ipm_refine == 0 ? 1 : cfg->ipm_refine);
-    P.ipm_refine_mu_frac = cfg->ipm_refine_after < 0 ? 1e300 : pow(10.0, -static_cast<double>(cfg->ipm_refine_after == 0 ? 4 : cfg->ipm_refine_after));
+    P.ipm_refine_mu_frac = cfg->ipm_refine_after < 0 ? 1e300 : pow(10.0, -static_cast<double>(cfg->ipm_refine_after == 0 ? 8 : cfg->ipm_refine_after));
     h->L = make_layout(P.N, P.max_nu);
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);

@@ -182,9 +182,11 @@ static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double*
                 }
                 if (ey != nullptr && part == 0) {
                     double se = 0;
+                    const int grp = ci.foot * 2 + ci.coord;   // an equality row touches the position columns of one (foot, coord) only
                     #pragma unroll 1
                     for (int r = 0; r < c.neq; ++r) {
                         const EqRow& q = c.eq[r];
+                        if (q.pad != grp) continue;
                         for (int i = 0; i < q.cnt; ++i)
                             if (q.col[i] == col) se += ey[r] * q.w[i];
                     }
@@ -459,6 +461,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     double res_p = 0, res_d = 0, gap = 0, gscale = 1, bz = 0, aty_n = 0, zn = 1, pc = 0;
     bool have_point = false;
     int n_refined = 0;
+    bool confirm = false;
     for (it = -1; it <= P.ipm_max_iter; ++it) {
         double uHu = 0, rt = 0, mu = 0;
         bool refine_now = false;
@@ -469,7 +472,10 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             for (int i = tid; i < nu; i += nth) S.rd[i] = 0.0;
             __syncthreads();
             add_Ct(S.lam, S.rd, S.nueq, 1.0);
-            apply_C(S.u, S.rp, S.re, tau);
+            // rz and re are linear in the iterate: after a step they are updated with the very products the step was built
+            // from (below), and evaluated from scratch only at the first iteration and to confirm convergence
+            const bool fresh_rz = (it == 0) || confirm;
+            if (fresh_rz) apply_C(S.u, S.rp, S.re, tau);
             double r8[8] = {0, 0, 0, 0, 0, 0, 0, 1.0};   // sums: u'Hu, g'u, d'z, s'z ; maxima: |C'z + E'y|, |rx|, |rz|, z
             #pragma unroll 1
             for (int i = tid; i < nu; i += nth) {
@@ -485,7 +491,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             for (int i = tid; i < m; i += nth) {
                 const double zi = S.lam[i];
                 if (zi > 0.0) {
-                    const double di = rhs_of(i), rz = S.rp[i] + S.s[i] - di * tau;
+                    const double di = rhs_of(i), rz = fresh_rz ? S.rp[i] + S.s[i] - di * tau : S.rp[i];
                     S.rp[i] = rz;
                     r8[2] += di * zi;
                     r8[3] += S.s[i] * zi;
@@ -523,9 +529,15 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             gscale = fmax(1.0, fmin(fabs(pc + cost_const), fabs(dc + cost_const)));   // full objective, as Clarabel's relative gap
             have_point = true;
             if (res_d <= P.ipm_tol_feas * nrm_q && res_p <= P.ipm_tol_feas * nrm_d && gap <= P.ipm_tol_gap * gscale) {
-                status = kSolved;
-                break;
+                if (fresh_rz) {
+                    status = kSolved;
+                    break;
+                }
+                confirm = true;   // same iterate once more, with the primal residuals evaluated from scratch
+                --it;
+                continue;
             }
+            confirm = false;
             // primal infeasibility certificate (Clarabel's is_primal_infeasible): d'z + e'y < 0 with C'z + E'y ~ 0
             if (bz < -P.ipm_tol_infeas && aty_n <= P.ipm_tol_infeas * zn * (-bz)) {
                 status = kPrimalInfeasible;
@@ -622,12 +634,15 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             for (int i = tid; i < m; i += nth) {
                 const double zi = S.lam[i];
                 if (!(zi > 0.0)) continue;
-                const double a2 = S.dl[i];
+                const double a2 = S.dl[i], di = rhs_of(i);
                 const double t = S.ds[i] + dtau * S.wv[i];
-                const double dzv = wrow(i) * (t - a2 - dtau * rhs_of(i));
+                const double dzv = wrow(i) * (t - a2 - dtau * di);
+                const double dsv = -(a2 + scale * S.rp[i]) - (S.s[i] / zi) * dzv;
                 S.dl[i] = dzv;
-                S.ds[i] = -(a2 + scale * S.rp[i]) - (S.s[i] / zi) * dzv;
+                S.ds[i] = dsv;
+                if (pass == 2) S.wv[i] = t + dsv - di * dtau;   // d rz / d alpha = C du + ds - d dtau (C x1 is not needed any more)
             }
+            if (pass == 2 && tid < neq) S.a3[tid] = delta * S.dnu[tid] + dtau * delta * S.y1[tid] - scale * S.re[tid];   // d re / d alpha = E du - e dtau
             if (tid < neq) S.dnu[tid] += dtau * S.y1[tid];
             __syncthreads();
             double amax = 1.0;
@@ -694,8 +709,12 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             if (S.lam[i] > 0.0) {
                 S.s[i] += alpha * S.ds[i];
                 S.lam[i] += alpha * S.dl[i];
+                S.rp[i] += alpha * S.wv[i];
             }
-        if (tid < neq) S.nueq[tid] += alpha * S.dnu[tid];
+        if (tid < neq) {
+            S.nueq[tid] += alpha * S.dnu[tid];
+            S.re[tid] += alpha * S.a3[tid];
+        }
         tau += alpha * dtau;
         kap += alpha * dkap;
         __syncthreads();

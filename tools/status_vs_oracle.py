@@ -15,6 +15,7 @@ NS = int(os.environ.get("NSAMPLE", 64))
 states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=int(os.environ.get("SEED", 0)))
 kw = {}
 if os.environ.get("REFINE"): kw["ipm_refine"] = int(os.environ["REFINE"])
+if os.environ.get("REFINE_AFTER"): kw["ipm_refine_after"] = int(os.environ["REFINE_AFTER"])
 gpu = common.make_gpu(cfg_name, B, states, **kw)
 hist, ith = [], []
 for it in range(STEPS):
