@@ -279,19 +279,19 @@ bgg_robot RobotConstsFromURDF(const std::string& urdf_path, const std::map<std::
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) Ir[i][j] += b.I.a[i][j] + b.m * ((i == j ? dd : 0.0) - d[i] * d[j]);
     }
-    // inverse of the symmetric 3 x 3
-    const double det = Ir[0][0] * (Ir[1][1] * Ir[2][2] - Ir[1][2] * Ir[2][1]) - Ir[0][1] * (Ir[1][0] * Ir[2][2] - Ir[1][2] * Ir[2][0]) +
-                       Ir[0][2] * (Ir[1][0] * Ir[2][1] - Ir[1][1] * Ir[2][0]);
+    // Ir_.inverse() as Eigen evaluates it for a fixed 3 x 3 matrix (Eigen/src/LU/InverseImpl.h): cofactors times 1 / det,
+    // the determinant expanded along the first column (single_rigid_body_model.cpp:37)
+    auto cof = [&](int i, int j) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return Ir[i1][j1] * Ir[i2][j2] - Ir[i1][j2] * Ir[i2][j1];
+    };
+    const double c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+    const double det = (c0 * Ir[0][0] + c1 * Ir[1][0]) + c2 * Ir[2][0];
+    const double invdet = 1.0 / det;
     double inv[3][3];
-    inv[0][0] = (Ir[1][1] * Ir[2][2] - Ir[1][2] * Ir[2][1]) / det;
-    inv[0][1] = (Ir[0][2] * Ir[2][1] - Ir[0][1] * Ir[2][2]) / det;
-    inv[0][2] = (Ir[0][1] * Ir[1][2] - Ir[0][2] * Ir[1][1]) / det;
-    inv[1][0] = (Ir[1][2] * Ir[2][0] - Ir[1][0] * Ir[2][2]) / det;
-    inv[1][1] = (Ir[0][0] * Ir[2][2] - Ir[0][2] * Ir[2][0]) / det;
-    inv[1][2] = (Ir[0][2] * Ir[1][0] - Ir[0][0] * Ir[1][2]) / det;
-    inv[2][0] = (Ir[1][0] * Ir[2][1] - Ir[1][1] * Ir[2][0]) / det;
-    inv[2][1] = (Ir[0][1] * Ir[2][0] - Ir[0][0] * Ir[2][1]) / det;
-    inv[2][2] = (Ir[0][0] * Ir[1][1] - Ir[0][1] * Ir[1][0]) / det;
+    inv[0][0] = c0 * invdet; inv[0][1] = c1 * invdet; inv[0][2] = c2 * invdet;
+    inv[1][0] = cof(0, 1) * invdet; inv[1][1] = cof(1, 1) * invdet; inv[2][2] = cof(2, 2) * invdet;
+    inv[1][2] = cof(2, 1) * invdet; inv[2][1] = cof(1, 2) * invdet; inv[2][0] = cof(0, 2) * invdet;
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) {
             rb.Ir[3 * i + j] = Ir[i][j];

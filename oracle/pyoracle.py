@@ -12,6 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "liboracle.so")
 REF_SPLINES_SO = os.path.join(_HERE, "_ref", "libref_splines.so")
+REF_MPC_SO = os.path.join(_HERE, "_ref", "libref_mpc.so")   # the reference's own MPC sources over stand-in headers (ref_shim/)
 
 FORCE, POSITION = 0, 1
 NO_DERIV, FULL_DERIV, EMPTY = 0, 1, 2
@@ -25,7 +26,7 @@ def build(force=False):
     """Compile the oracle (and oracle/_ref when /root/reference is present). Building the checker is not using it."""
     if force or not os.path.exists(ORACLE_SO):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference/mpc/spline") and (force or not os.path.exists(REF_SPLINES_SO)):
+    if os.path.isdir("/root/reference/mpc/spline") and (force or not os.path.exists(REF_SPLINES_SO) or not os.path.exists(REF_MPC_SO)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -97,6 +98,50 @@ def load(which="oracle"):
 
 def have_ref():
     return os.path.exists(REF_SPLINES_SO)
+
+
+def have_ref_mpc():
+    return os.path.exists(REF_MPC_SO)
+
+
+_ref_mpc_lib = None
+
+
+def load_ref_mpc():
+    """The reference's own MPC sources compiled here (oracle/Makefile: _ref/libref_mpc.so); same entry-point names as the oracle."""
+    global _ref_mpc_lib
+    if _ref_mpc_lib is None:
+        lib = C.CDLL(REF_MPC_SO, mode=os.RTLD_NOW)
+        lib.orc_mpc_last_error.restype = C.c_char_p
+        lib.orc_last_error = lib.orc_mpc_last_error
+        lib.orc_mpc_create_ref.restype = C.c_void_p
+        lib.orc_mpc_create_ref.argtypes = [C.POINTER(_MpcInfo), C.POINTER(_RobotConsts), _dp]
+        lib.orc_mpc_destroy.argtypes = [C.c_void_p]
+        lib.orc_mpc_set_ipm.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]
+        lib.orc_mpc_set_costs.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+        lib.orc_mpc_set_warm_states.argtypes = [C.c_void_p, _dp]
+        lib.orc_mpc_solve.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int]
+        lib.orc_mpc_initial_run.argtypes = [C.c_void_p, _dp, _dp]
+        lib.orc_mpc_set_contact_times.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int]
+        lib.orc_mpc_sizes.argtypes = [C.c_void_p, _ip]
+        lib.orc_mpc_get_A.argtypes = [C.c_void_p, _ip, _ip, _dp]
+        lib.orc_mpc_get_P.argtypes = [C.c_void_p, _ip, _ip, _dp]
+        lib.orc_mpc_get_vectors.argtypes = [C.c_void_p, _dp, _dp, C.c_char_p]
+        lib.orc_mpc_get_prev_qp_sol.argtypes = [C.c_void_p, _dp]
+        lib.orc_mpc_get_qp_solution.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+        lib.orc_mpc_get_stats.argtypes = [C.c_void_p, _dp]
+        lib.orc_mpc_get_states.argtypes = [C.c_void_p, _dp]
+        lib.orc_mpc_init_time.restype = C.c_double
+        lib.orc_mpc_init_time.argtypes = [C.c_void_p]
+        lib.orc_mpc_cost.restype = C.c_double
+        lib.orc_mpc_cost.argtypes = [C.c_void_p]
+        lib.orc_mpc_force_at.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp]
+        lib.orc_mpc_ee_at.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp]
+        lib.orc_mpc_num_contacts.argtypes = [C.c_void_p, C.c_int]
+        lib.orc_mpc_get_contact_times.argtypes = [C.c_void_p, C.c_int, _dp, _ip]
+        lib.orc_mpc_gait_gradient.argtypes = [C.c_void_p, _dp, C.c_int]
+        _ref_mpc_lib = lib
+    return _ref_mpc_lib
 
 
 class FootSpline:
@@ -357,8 +402,10 @@ class SrbMpc:
     """The oracle's restatement of mpc::MPCSingleRigidBody (live path)."""
 
     def __init__(self, num_nodes, dt, consts, friction_coef=0.5, force_bound=150.0, swing_height=0.075, foot_offset=0.015,
-                 ee_box_size=(0.15, 0.15), force_cost=0.0, _handle=None):
-        self.lib = load()
+                 ee_box_size=(0.15, 0.15), force_cost=0.0, _handle=None, which="oracle"):
+        """which = "oracle": the restatement (liboracle.so); "ref": the reference's own sources compiled here (libref_mpc.so)."""
+        self.which = which
+        self.lib = load() if which == "oracle" else load_ref_mpc()
         self.N = num_nodes
         if _handle is not None:
             self.h = _handle
@@ -370,7 +417,13 @@ class SrbMpc:
         rc.Ir_inv[:] = np.asarray(consts["Ir_inv"], dtype=float).ravel().tolist()
         rc.hip_xy[:] = np.asarray(consts["hip_offsets_xy"], dtype=float).ravel().tolist()
         rc.gravity[:] = list(consts["gravity"])
-        self.h = self.lib.orc_mpc_create(C.byref(info), C.byref(rc))
+        if which == "ref":
+            # the reference adds its +-0.1 (y) and +0.025 (x) offsets to the raw hip-joint translation itself
+            # (single_rigid_body_model.cpp:289-305): hand it the translations of models/a1_description/urdf/a1.urdf
+            hip = np.ascontiguousarray(np.asarray(consts["hip_joint_translation"], dtype=float))
+            self.h = self.lib.orc_mpc_create_ref(C.byref(info), C.byref(rc), _dptr(hip))
+        else:
+            self.h = self.lib.orc_mpc_create(C.byref(info), C.byref(rc))
         if not self.h:
             raise OracleError(self.lib.orc_last_error().decode())
 
@@ -437,6 +490,19 @@ class SrbMpc:
     def set_contact_times(self, ee, times):
         t = np.ascontiguousarray(times, dtype=np.float64)
         self._chk(self.lib.orc_mpc_set_contact_times(self.h, ee, _dptr(t), len(t)))
+
+    def gait_gradient(self):
+        """(which="ref" only) dH/dtheta through the reference's own derivative chain (MPCController::GaitOpt, :518-552);
+        None when the last solve was not `Solved`."""
+        out = np.zeros(64)
+        n = self._chk(self.lib.orc_mpc_gait_gradient(self.h, _dptr(out), 64))
+        return out[:n].copy() if n else None
+
+    def contact_times(self, ee):
+        n = self.lib.orc_mpc_num_contacts(self.h, ee)
+        t, ty = np.zeros(n), np.zeros(n, dtype=np.int32)
+        self.lib.orc_mpc_get_contact_times(self.h, ee, _dptr(t), _iptr(ty))
+        return t, ty
 
     def sizes(self):
         out = np.zeros(14, dtype=np.int32)

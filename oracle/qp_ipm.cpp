@@ -399,21 +399,27 @@ IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const
     return res;
 }
 
-QpSolution IpmQpSolver::Solve(const QpData& data, const Vec& /*warm_start*/, bool /*is_real_time*/) {
-    const std::vector<char> eq = data.RowIsEquality();
-    // elimination order: [x_k, multipliers of dynamics block k] per node, then the spline variables, then the
-    // remaining equality multipliers -- keeps the envelope of the state chain 36 wide.
-    const int n = data.num_vars, nblk = data.num_dynamics / 12;
+// The MPC's elimination order -- [x_k, multipliers of dynamics block k] per node, then the spline variables, then the
+// remaining equality multipliers: keeps the envelope of the state chain 36 wide -- shared by the oracle's QpSolver and by
+// the stand-in behind the reference's ClarabelInterface (ref_shim/ref_mpc_capi.cpp), so both run the same arithmetic.
+IpmResult IpmSolveMpcOrder(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const std::vector<char>& is_eq, int num_dynamics,
+                           const IpmSettings& st) {
+    const int n = P.cols, nblk = num_dynamics / 12;
     std::vector<int> order;
     int me = 0;
-    for (char c : eq) me += c;
+    for (char c : is_eq) me += c;
     for (int k = 0; k < nblk; k++) {
         for (int i = 0; i < 12; i++) order.push_back(12 * k + i);
         for (int i = 0; i < 12; i++) order.push_back(n + 12 * k + i);   // dynamics rows are the first equality rows
     }
     for (int j = 12 * nblk; j < n; j++) order.push_back(j);
-    for (int e = data.num_dynamics; e < me; e++) order.push_back(n + e);
-    const IpmResult r = IpmSolve(data.P, data.cost_linear, data.A, data.ub, eq, order, settings);
+    for (int e = num_dynamics; e < me; e++) order.push_back(n + e);
+    return IpmSolve(P, q, A, b, is_eq, order, st);
+}
+
+QpSolution IpmQpSolver::Solve(const QpData& data, const Vec& /*warm_start*/, bool /*is_real_time*/) {
+    const std::vector<char> eq = data.RowIsEquality();
+    const IpmResult r = IpmSolveMpcOrder(data.P, data.cost_linear, data.A, data.ub, eq, data.num_dynamics, settings);
     QpSolution out;
     out.x = r.x;
     out.dual = r.y;

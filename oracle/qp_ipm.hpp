@@ -38,6 +38,9 @@ struct IpmResult {
 IpmResult IpmSolve(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const std::vector<char>& is_eq,
                    const std::vector<int>& order, const IpmSettings& s);
 
+IpmResult IpmSolveMpcOrder(const Csc& P, const Vec& q, const Csc& A, const Vec& b, const std::vector<char>& is_eq, int num_dynamics,
+                           const IpmSettings& s);
+
 class IpmQpSolver : public QpSolver {
 public:
     IpmSettings settings;

@@ -24,6 +24,24 @@ import xml.etree.ElementTree as ET
 import numpy as np
 
 
+def inverse3_cofactor(M):
+    """Ir_.inverse() as Eigen evaluates it for a fixed 3 x 3 matrix (Eigen/src/LU/InverseImpl.h, compute_inverse<.., 3>): cofactors
+    times 1 / det, the determinant expanded along the first column.  Plain Python floats, same operation order."""
+    m = [[float(M[i][j]) for j in range(3)] for i in range(3)]
+
+    def cof(i, j):
+        i1, i2, j1, j2 = (i + 1) % 3, (i + 2) % 3, (j + 1) % 3, (j + 2) % 3
+        return m[i1][j1] * m[i2][j2] - m[i1][j2] * m[i2][j1]
+    c0, c1, c2 = cof(0, 0), cof(1, 0), cof(2, 0)
+    det = (c0 * m[0][0] + c1 * m[1][0]) + c2 * m[2][0]
+    invdet = 1.0 / det
+    r = [[0.0] * 3 for _ in range(3)]
+    r[0][0], r[0][1], r[0][2] = c0 * invdet, c1 * invdet, c2 * invdet
+    r[1][0], r[1][1], r[2][2] = cof(0, 1) * invdet, cof(1, 1) * invdet, cof(2, 2) * invdet
+    r[1][2], r[2][1], r[2][0] = cof(2, 1) * invdet, cof(1, 2) * invdet, cof(0, 2) * invdet
+    return r
+
+
 def rpy_to_R(r, p, y):
     cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
     Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
@@ -98,9 +116,10 @@ def main(urdf_path, out_path, joint_cfg):
     for m, c, I in bodies:
         d = c - com
         Ir += I + m * (d @ d * np.eye(3) - np.outer(d, d))
-    hips = []
+    hips, hips_raw = [], []
     for name in ("FL_hip_joint", "FR_hip_joint", "RL_hip_joint", "RR_hip_joint"):
         t = joint_pos[name].copy()                      # root joint sits at the base origin
+        hips_raw.append([float(v) for v in t])
         t[1] += 0.1 if t[1] >= 0 else -0.1              # single_rigid_body_model.cpp:291-297
         t[0] += 0.025                                   # :299-305 (both branches add 0.025)
         hips.append([float(t[0]), float(t[1])])
@@ -110,8 +129,9 @@ def main(urdf_path, out_path, joint_cfg):
         "mass": float(mass),
         "com_in_base": [float(v) for v in com],
         "Ir": [[float(v) for v in row] for row in Ir],
-        "Ir_inv": [[float(v) for v in row] for row in np.linalg.inv(Ir)],
+        "Ir_inv": [[float(v) for v in row] for row in inverse3_cofactor(Ir)],
         "hip_offsets_xy": hips,
+        "hip_joint_translation": hips_raw,   # oMi[hip joint] - oMi[root] before the reference's own offsets
         "gravity": [0.0, 0.0, -9.81],
     }
     with open(out_path, "w") as f:
