@@ -146,6 +146,26 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+struct DevPool {   // scratch device allocations of one call, released on every exit path
+    std::vector<void*> p;
+    ~DevPool() { for (void* q_ : p) cudaFree(q_); }
+    template <typename T> T* get(size_t nelem) {
+        void* d = nullptr;
+        if (cudaMalloc(&d, sizeof(T) * (nelem ? nelem : 1)) != cudaSuccess) return nullptr;
+        p.push_back(d);
+        return static_cast<T*>(d);
+    }
+};
+
+namespace bgg {
+constexpr int kQpMaxN_capi = 128;
+size_t qp_ws_doubles(int n, int mi, int me);
+int launch_qp_generic(int count, int n, int m, int mi, int me, int nnzP, int nnzA, const int* Pcol, const int* Prow, const double* Pval,
+                      const int* Acol, const int* Arow, const double* Aval, const double* q, const double* b, const int* in_rows,
+                      const int* eq_rows, const int* row_slot, double* ws, double* x, double* y, double* s, int32_t* status, int32_t* iters,
+                      double tol_feas, double tol_gap, double tol_inf, double eps, double delta, int max_iter, int max_smem, cudaStream_t stream);
+}  // namespace bgg
+
 extern "C" {
 
 int bgg_measure_fp64_peak(int device, double* tflops) {
@@ -475,6 +495,61 @@ int bgg_solve_batch(bgg_handle* h, const double* state, const double* t0, const 
     rc = bgg_solve_resident(h);
     if (rc) return rc;
     return bgg_download_results(h, status, iters, alpha, cost, z, z_stride);
+}
+
+int bgg_qp_solve_batch(bgg_handle* h, int count, int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx, const double* P_val,
+                       const int32_t* A_colptr, const int32_t* A_rowidx, const double* A_val, const double* q, const double* b,
+                       const uint8_t* is_eq, double* x, double* y, double* s, int32_t* status, int32_t* iters) {
+    if (!h || count <= 0 || n <= 0 || m < 0 || !P_colptr || !P_rowidx || !P_val || !A_colptr || !A_rowidx || !A_val || !q || !b || !is_eq || !x)
+        return fail(BGG_EINVAL, "null argument");
+    if (n > kQpMaxN_capi) return fail(BGG_EINVAL, "bgg_qp_solve_batch handles at most 128 variables (the MPC QP goes through bgg_solve_batch)");
+    CU(cudaSetDevice(h->device));
+    const int nnzP = P_colptr[n], nnzA = A_colptr[n];
+    // rows: equality rows, inequality rows with at least one stored entry (an empty row reads 0 + s = b and is reported s = b, y = 0)
+    std::vector<int> cnt(m, 0), row_slot(m, -1), in_rows, eq_rows;
+    for (int k = 0; k < nnzA; ++k) {
+        if (A_rowidx[k] < 0 || A_rowidx[k] >= m) return fail(BGG_EINVAL, "row index out of range");
+        cnt[A_rowidx[k]]++;
+    }
+    for (int r = 0; r < m; ++r) {
+        if (is_eq[r]) { row_slot[r] = -(static_cast<int>(eq_rows.size()) + 2); eq_rows.push_back(r); }
+        else if (cnt[r] > 0) { row_slot[r] = static_cast<int>(in_rows.size()); in_rows.push_back(r); }
+    }
+    const int mi = static_cast<int>(in_rows.size()), me = static_cast<int>(eq_rows.size());
+    const size_t wsd = qp_ws_doubles(n, mi, me);
+    DevPool dev;
+    int *dPc = dev.get<int>(n + 1), *dPr = dev.get<int>(nnzP), *dAc = dev.get<int>(n + 1), *dAr = dev.get<int>(nnzA), *dIn = dev.get<int>(mi), *dEq = dev.get<int>(me),
+        *dSlot = dev.get<int>(m);
+    double *dPv = dev.get<double>(static_cast<size_t>(count) * nnzP), *dAv = dev.get<double>(static_cast<size_t>(count) * nnzA), *dq = dev.get<double>(static_cast<size_t>(count) * n),
+           *db = dev.get<double>(static_cast<size_t>(count) * m), *dws = dev.get<double>(static_cast<size_t>(count) * wsd), *dx = dev.get<double>(static_cast<size_t>(count) * n),
+           *dy = dev.get<double>(static_cast<size_t>(count) * m), *dsl = dev.get<double>(static_cast<size_t>(count) * m);
+    int32_t *dst = dev.get<int32_t>(count), *dit = dev.get<int32_t>(count);
+    if (!dPc || !dPr || !dAc || !dAr || !dIn || !dEq || !dSlot || !dPv || !dAv || !dq || !db || !dws || !dx || !dy || !dsl || !dst || !dit)
+        return fail(BGG_ENOMEM, "device allocation failed");
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpyAsync(dPc, P_colptr, 4 * (n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dPr, P_rowidx, 4 * static_cast<size_t>(nnzP), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dAc, A_colptr, 4 * (n + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dAr, A_rowidx, 4 * static_cast<size_t>(nnzA), cudaMemcpyHostToDevice, st));
+    if (mi) CU(cudaMemcpyAsync(dIn, in_rows.data(), 4 * static_cast<size_t>(mi), cudaMemcpyHostToDevice, st));
+    if (me) CU(cudaMemcpyAsync(dEq, eq_rows.data(), 4 * static_cast<size_t>(me), cudaMemcpyHostToDevice, st));
+    if (m) CU(cudaMemcpyAsync(dSlot, row_slot.data(), 4 * static_cast<size_t>(m), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dPv, P_val, 8 * static_cast<size_t>(count) * nnzP, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dAv, A_val, 8 * static_cast<size_t>(count) * nnzA, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dq, q, 8 * static_cast<size_t>(count) * n, cudaMemcpyHostToDevice, st));
+    if (m) CU(cudaMemcpyAsync(db, b, 8 * static_cast<size_t>(count) * m, cudaMemcpyHostToDevice, st));
+    if (launch_qp_generic(count, n, m, mi, me, nnzP, nnzA, dPc, dPr, dPv, dAc, dAr, dAv, dq, db, dIn, dEq, dSlot, dws, dx, dy, dsl, dst, dit, h->P.ipm_tol_feas,
+                          h->P.ipm_tol_gap, h->P.ipm_tol_infeas, h->P.ipm_reg_eps, h->P.ipm_eq_delta, h->P.ipm_max_iter, h->max_smem, st))
+        return fail(BGG_EINVAL, "the QP needs more shared memory than the device offers");
+    h->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(x, dx, 8 * static_cast<size_t>(count) * n, cudaMemcpyDeviceToHost, st));
+    if (y && m) CU(cudaMemcpyAsync(y, dy, 8 * static_cast<size_t>(count) * m, cudaMemcpyDeviceToHost, st));
+    if (s && m) CU(cudaMemcpyAsync(s, dsl, 8 * static_cast<size_t>(count) * m, cudaMemcpyDeviceToHost, st));
+    if (status) CU(cudaMemcpyAsync(status, dst, 4 * static_cast<size_t>(count), cudaMemcpyDeviceToHost, st));
+    if (iters) CU(cudaMemcpyAsync(iters, dit, 4 * static_cast<size_t>(count), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return BGG_OK;
 }
 
 int bgg_synchronize(bgg_handle* h) {

@@ -331,7 +331,114 @@ const QPData& MPC::GetQPData() const {
     d.num_start_ee_constraints_ = sz.n_eq - sz.n_td;
     d.num_equality_ = dims[3];
     d.num_inequality_ = dims[4];
+    d.sparse_cost_.rows = d.sparse_cost_.cols = n;    // P is diagonal on this path (mpc.cpp:542-564, 791-802, 1090-1095)
+    d.sparse_cost_.outer.resize(n + 1);
+    d.sparse_cost_.inner.resize(n);
+    d.sparse_cost_.values.resize(n);
+    for (int i = 0; i < n; ++i) {
+        d.sparse_cost_.outer[i] = i;
+        d.sparse_cost_.inner[i] = i;
+        d.sparse_cost_.values[i] = pd[i];
+    }
+    d.sparse_cost_.outer[n] = n;
+    d.constraints_ = {Dynamics, ForceBox, FrictionCone, EndEffectorLocation, TDPosition, EndEffectorStart};   // single_rigid_body_model.cpp:22-29
     return d;
+}
+
+// ------------------------------------------------------------------------------------------------ solver seam
+std::string QPInterface::GetSolveQualityAsString() const {   // qp_interface.cpp:19-41
+    switch (GetSolveQuality()) {
+        case Solved: return "Solved";
+        case SolvedInacc: return "Solved Inaccurate";
+        case MaxIter: return "Max Iterations";
+        case PrimalInfeasible: return "Primal Infeasible";
+        case DualInfeasible: return "Dual Infeasible";
+        case PrimalInfeasibleInacc: return "Primal Infeasible Inaccurate";
+        case DualInfeasibleInacc: return "Dual Infeasible Inaccurate";
+        case Unsolved: return "Unsolved";
+        default: return "Other";
+    }
+}
+
+static bgg_handle* MakeSolverHandle() {   // the seam needs a device, a stream and the solver settings: a handle without a batch
+    bgg_config cfg{};
+    cfg.num_nodes = 8;
+    cfg.integrator_dt = 0.05;
+    cfg.ee_box_size[0] = cfg.ee_box_size[1] = 0.15;
+    bgg_robot rb{};
+    rb.mass = 1.0;
+    for (int i = 0; i < 3; ++i) rb.Ir[4 * i] = rb.Ir_inv[4 * i] = 1.0;
+    bgg_handle* h = nullptr;
+    Check(bgg_create(&cfg, &rb, &h));
+    return h;
+}
+ClarabelInterface::ClarabelInterface(const QPData& data, bool verbose) : QPInterface(data.num_decision_vars), h_(MakeSolverHandle()), verbose_(verbose) {}
+ClarabelInterface::ClarabelInterface(const ClarabelInterface& other)
+    : QPInterface(other.num_decision_vars_), h_(MakeSolverHandle()), verbose_(other.verbose_), is_eq_(other.is_eq_),
+      solve_quality_(other.solve_quality_), dual_(other.dual_), primal_(other.primal_), slacks_(other.slacks_), dx_(other.dx_) {}
+ClarabelInterface& ClarabelInterface::operator=(const ClarabelInterface& other) {
+    if (this != &other) {
+        num_decision_vars_ = other.num_decision_vars_;
+        verbose_ = other.verbose_;
+        is_eq_ = other.is_eq_;
+        solve_quality_ = other.solve_quality_;
+        dual_ = other.dual_;
+        primal_ = other.primal_;
+        slacks_ = other.slacks_;
+        dx_ = other.dx_;
+    }
+    return *this;
+}
+ClarabelInterface::~ClarabelInterface() { bgg_destroy(h_); }
+
+void ClarabelInterface::SetupQP(QPData& data, const vector_t& /*warm_start*/) {
+    // cone list in constraint-block order: Zero cones for Dynamics / TDPosition / EndEffectorStart / Raibert, Nonnegative
+    // cones for EndEffectorLocation / ForceBox / FrictionCone (clarabel_interface.cpp:29-64)
+    is_eq_.clear();
+    for (const Constraints c : data.constraints_) {
+        int n = 0;
+        uint8_t eq = 0;
+        switch (c) {
+            case Dynamics: n = data.num_dynamics_constraints; eq = 1; break;
+            case EndEffectorLocation: n = data.num_ee_location_constraints_; break;
+            case ForceBox: n = data.num_force_box_constraints_; break;
+            case FrictionCone: n = data.num_cone_constraints_; break;
+            case TDPosition: n = data.num_td_pos_constraints_; eq = 1; break;
+            case EndEffectorStart: n = data.num_start_ee_constraints_; eq = 1; break;
+            case Raibert: n = data.num_raibert_constraints_; eq = 1; break;
+            case JointForwardKinematics: throw std::runtime_error("not supported yet");
+            case JointBox: throw std::runtime_error("Joint box not implemented with clarabel yet");
+        }
+        is_eq_.insert(is_eq_.end(), static_cast<size_t>(n), eq);
+    }
+    if (static_cast<int>(is_eq_.size()) != data.sparse_constraint_.rows) throw std::runtime_error("constraint blocks do not add up to the rows of the constraint matrix");
+}
+
+vector_t ClarabelInterface::Solve(const QPData& data) {
+    const int n = data.sparse_constraint_.cols, m = data.sparse_constraint_.rows;
+    if (n > 128)
+        throw std::runtime_error("ClarabelInterface over bgg_qp_solve_batch takes up to 128 variables; the MPC QP is solved inside MPC::Solve (bgg_solve_batch)");
+    primal_.resize(n);
+    dual_.resize(m);
+    slacks_.resize(m);
+    int32_t status = 0, iters = 0;
+    Check(bgg_qp_solve_batch(h_, 1, n, m, data.sparse_cost_.outer.data(), data.sparse_cost_.inner.data(), data.sparse_cost_.values.data(),
+                             data.sparse_constraint_.outer.data(), data.sparse_constraint_.inner.data(), data.sparse_constraint_.values.data(),
+                             data.cost_linear.data(), data.ub_.data(), is_eq_.data(), primal_.data(), dual_.data(), slacks_.data(), &status, &iters));
+    solve_quality_ = static_cast<SolveQuality>(status);
+    if (solve_quality_ == PrimalInfeasible) {
+        const std::string error = "Primal infeasible.";
+        throw (error);   // what the caller catches (mpc_single_rigid_body.cpp:115-129)
+    }
+    return primal_;
+}
+
+vector_t ClarabelInterface::Computedx(const SparseCsc& P, const vector_t& q, const vector_t& xstar) {
+    dx_.resize(q.size());
+    for (int i = 0; i < q.size(); ++i) dx_(i) = q(i);
+    for (int j = 0; j < P.cols; ++j)
+        for (int k = P.outer[j]; k < P.outer[j + 1]; ++k) dx_(P.inner[k]) += P.values[k] * xstar(j);
+    return dx_;
 }
 
 bool MPC::ComputeDerivativeTerms() {

@@ -142,13 +142,63 @@ struct SparseCsc {   // stands in for Eigen::SparseMatrix<double> (column-major 
     int nonZeros() const { return static_cast<int>(values.size()); }
     double coeff(int r, int c) const;
 };
+enum Constraints {   // mpc/include/qp/qp_data.h:17-27
+    Dynamics, JointForwardKinematics, EndEffectorLocation, ForceBox, JointBox, FrictionCone, TDPosition, Raibert, EndEffectorStart
+};
 struct QPData {
     SparseCsc sparse_constraint_;
+    SparseCsc sparse_cost_;              // P (diagonal on the MPC path); what ClarabelInterface::SetupQP hands to the solver
+    std::vector<Constraints> constraints_;   // block order of the rows (single_rigid_body_model.cpp:22-29)
     vector_t cost_diag_, cost_linear, ub_;
     int num_decision_vars = 0, num_dynamics_constraints = 0, num_force_box_constraints_ = 0, num_cone_constraints_ = 0,
         num_ee_location_constraints_ = 0, num_td_pos_constraints_ = 0, num_start_ee_constraints_ = 0, num_raibert_constraints_ = 0;
     int num_equality_ = 0, num_inequality_ = 0;
     int GetTotalNumConstraints() const { return num_equality_ + num_inequality_; }
+};
+
+// The solver seam (mpc/include/qp/qp_interface.h:30-65) and its live implementation (mpc/include/qp/clarabel_interface.h:43-106,
+// mpc/qp/clarabel_interface.cpp:18-155), over bgg_qp_solve_batch: the interior-point kernel of the CUDA path on the QP it is handed.
+class QPInterface {
+public:
+    explicit QPInterface(int num_decision_vars) : num_decision_vars_(num_decision_vars) {}
+    virtual ~QPInterface() {}
+    virtual void SetupQP(QPData& data, const vector_t& warm_start) = 0;
+    virtual vector_t Solve(const QPData& data) = 0;
+    virtual vector_t GetInfinity(int size) const { return vector_t::Constant(size, 1e30); }   // qp_interface.cpp:13-17
+    virtual SolveQuality GetSolveQuality() const = 0;
+    std::string GetSolveQualityAsString() const;
+    virtual vector_t GetDualSolution() const = 0;
+    virtual void ConfigureForInitialRun() = 0;
+    virtual void ConfigureForRealTime(double run_time_iters) = 0;
+
+protected:
+    int num_decision_vars_;
+    vector_t prev_qp_sol_;
+};
+
+class ClarabelInterface : public QPInterface {
+public:
+    ClarabelInterface(const QPData& data, bool verbose);
+    ClarabelInterface(const ClarabelInterface& other);
+    ClarabelInterface& operator=(const ClarabelInterface& other);
+    ~ClarabelInterface() override;
+    void SetupQP(QPData& data, const vector_t& warm_start) override;   // builds the cone list from data.constraints_ (:29-64)
+    vector_t Solve(const QPData& data) override;                         // throws const std::string& "Primal infeasible." (:112-114)
+    SolveQuality GetSolveQuality() const override { return solve_quality_; }
+    vector_t GetDualSolution() const override { return dual_; }
+    vector_t GetSlacks() const { return slacks_; }
+    void ConfigureForInitialRun() override {}                            // the reference only moves tol_gap (:166-175); the kernel's are fixed
+    void ConfigureForRealTime(double) override {}
+    vector_t Computedx(const SparseCsc& P, const vector_t& q, const vector_t& xstar);   // dx = P x* + q (:604-612)
+    vector_t Getdx() const { return dx_; }
+    void SetVerbosity(bool verbose) { verbose_ = verbose; }
+
+private:
+    bgg_handle* h_ = nullptr;
+    bool verbose_ = false;
+    std::vector<uint8_t> is_eq_;
+    SolveQuality solve_quality_ = Unsolved;
+    vector_t dual_, primal_, slacks_, dx_;
 };
 
 class MPC;
@@ -228,6 +278,54 @@ public:
     bool ComputeParamPartialsClarabel(const Trajectory& traj, QPPartials& partials, int ee, int idx);   // :642-792
     std::vector<vector_2t> GetEEBoxCenter();                                                             // :1060-1063
     double GetModifiedCost(int num_nodes) const { (void)num_nodes; return cost_; }
+};
+
+// mpc::MPCCentroidal (mpc/include/mpc_centroidal.h:15-221).  The reference declares this class and defines none of it
+// (mpc/mpc_centroidal.cpp is commented out), so nothing can be in parity with it; the adapter gives code written
+// against that header the live single-rigid-body MPC: feet at the nominal A1 stance where the header's signatures carry none.
+class MPCCentroidal {
+public:
+    MPCCentroidal(const MPCInfo& info, const std::string& robot_urdf) : mpc_(info, robot_urdf) {}
+    MPCCentroidal(const MPCInfo& info, const bgg_robot& robot) : mpc_(info, robot) {}
+    Trajectory CreateInitialRun(const vector_t& state) { return mpc_.CreateInitialRun(state, ee_); }
+    Trajectory GetRealTimeUpdate(double /*run_time_iters*/, const vector_t& state, double init_time) { return mpc_.GetRealTimeUpdate(state, init_time, ee_, false); }
+    Trajectory Solve(const vector_t& state, double init_time) { return mpc_.Solve(state, init_time, ee_); }
+    void SetWarmStartTrajectory(const Trajectory& trajectory) { mpc_.SetWarmStartTrajectory(trajectory); }
+    void SetQuadraticFinalCost(const matrix_t& Phi) { mpc_.SetQuadraticFinalCost(Phi); }
+    void SetLinearFinalCost(const vector_t& w) { mpc_.SetLinearFinalCost(w); }
+    void AddQuadraticTrackingCost(const vector_t& state_des, const matrix_t& Q) { mpc_.AddQuadraticTrackingCost(state_des, Q); }
+    static std::vector<std::vector<double>> CreateDefaultSwitchingTimes(int num_switches, int num_ee, double horizon) {
+        return MPC::CreateDefaultSwitchingTimes(num_switches, num_ee, horizon);
+    }
+    void SetDefaultGaitTrajectory(Gaits gait, int num_polys, const std::array<std::array<double, 3>, 4>& ee_pos) {
+        ee_.clear();
+        for (const auto& p : ee_pos) ee_.emplace_back(p[0], p[1], p[2]);
+        mpc_.SetDefaultGaitTrajectory(gait, num_polys, ee_);
+    }
+    void SetStateTrajectoryWarmStart(const std::vector<vector_t>& states) { mpc_.SetStateTrajectoryWarmStart(states); }
+    void AddForceCost(double weight) { mpc_.AddForceCost(weight); }
+    void PrintStats() { mpc_.PrintStats(); }
+    controller::Contact GetDesiredContacts(double time) const { return mpc_.GetDesiredContacts(time); }
+    Trajectory GetTrajectory() const { return mpc_.GetTrajectory(); }
+    vector_t GetForceTarget(double time) const {
+        vector_t f(12);
+        const Trajectory t = mpc_.GetTrajectory();
+        for (int e = 0; e < 4; ++e) { const vector_3t v = t.GetForce(e, time); for (int c = 0; c < 3; ++c) f(3 * e + c) = v(c); }
+        return f;
+    }
+    int GetNode(double time) const { return mpc_.GetNode(time); }
+    int GetNumDecisionVars() const { return mpc_.GetNumDecisionVars(); }
+    int GetNumConstraints() const { return mpc_.GetNumConstraints(); }
+    bool ComputeDerivativeTerms() { return mpc_.ComputeDerivativeTerms(); }
+    bool GetQPPartials(QPPartials& partials) const { partials.source = &mpc_; return mpc_.GetSolveQuality() == Solved; }
+    bool ComputeParamPartials(const Trajectory& traj, QPPartials& partials, int ee, int idx) { return mpc_.ComputeParamPartialsClarabel(traj, partials, ee, idx); }
+    vector_t GetQPSolution() const { return mpc_.GetQPSolution(); }
+    MPCSingleRigidBody& Live() { return mpc_; }
+
+private:
+    MPCSingleRigidBody mpc_;
+    std::vector<vector_3t> ee_ = {vector_3t(0.1526, 0.12523, 0.011089), vector_3t(0.1526, -0.12523, 0.011089),
+                                  vector_3t(-0.208321844, 0.1363286, 0.01444), vector_3t(-0.208321844, -0.1363286, 0.01444)};   // test/mpc_test.cpp:97-101
 };
 
 class GaitOptimizer {   // mpc/include/gait_optimizer.h:23-171

@@ -109,6 +109,19 @@ int bgg_set_contact_times(bgg_handle* h, int first, int count, const double* tim
 int bgg_solve_batch(bgg_handle* h, const double* state, const double* t0, const double* ee_start, int32_t* status,
                     int32_t* iters, double* alpha, double* cost, double* z, int z_stride);
 
+/* The solver seam on its own: QPInterface::SetupQP + Solve (mpc/include/qp/qp_interface.h:30-65) as ClarabelInterface implements
+ * them (mpc/qp/clarabel_interface.cpp:29-155), for `count` independent QPs that share one sparsity pattern:
+ *     min 1/2 x'Px + q'x   s.t.  A x + s = b ,  s = 0 on the rows with is_eq != 0 (Zero cone), s >= 0 on the others (Nonnegative cone).
+ * P [n x n] and A [m x n] in compressed-sparse-column form as Eigen::SparseMatrix holds them (P: a triangle or the full symmetric
+ * matrix); P_val [count][nnz(P)], A_val [count][nnz(A)], q [count][n], b [count][m].  Outputs x [count][n], y / s [count][m]
+ * (multipliers and slacks in the caller's row order), status (mpc::SolveQuality) and iteration counts; y, s, status, iters may be
+ * NULL.  Same interior-point iteration and tolerances as bgg_solve_batch, on dense data: n <= 128 (the reference's 3-variable
+ * cross-solver QP, test/mpc_test.cpp:857-1005; the 42-variable whole-body QP of controllers/qp_control.cpp).  The MPC QP itself
+ * goes through bgg_solve_batch, whose kernel exploits its structure. */
+int bgg_qp_solve_batch(bgg_handle* h, int count, int n, int m, const int32_t* P_colptr, const int32_t* P_rowidx, const double* P_val,
+                       const int32_t* A_colptr, const int32_t* A_rowidx, const double* A_val, const double* q, const double* b,
+                       const uint8_t* is_eq, double* x, double* y, double* s, int32_t* status, int32_t* iters);
+
 /* The same solve split for measurement: copy inputs to HBM once, run the kernels on resident data, fetch results. */
 int bgg_upload_inputs(bgg_handle* h, const double* state, const double* t0, const double* ee_start);
 int bgg_solve_resident(bgg_handle* h);

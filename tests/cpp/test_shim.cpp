@@ -3,6 +3,8 @@
 // solve quality, then the gait optimiser's derivative -> LP -> line search sequence of MPCController::GaitOpt
 // (controllers/mpc_controller.cpp:518-573, 322-343).  Prints "key value" lines that tests/test_host_shim.py checks
 // against the oracle.  Needs a GPU (the library has no CPU fallback).
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -77,6 +79,7 @@ int main(int argc, char** argv) {
         std::printf("num_decision_vars %d\n", mpc.GetNumDecisionVars());
         std::printf("num_constraints %d\n", mpc.GetNumConstraints());
         std::printf("cost %.12e\n", mpc.GetCost());
+        const double cost_after_rt = mpc.GetCost();
         const QPData& data = mpc.GetQPData();
         std::printf("qp_rows %d\nqp_cols %d\nqp_nnz %d\n", data.sparse_constraint_.rows, data.sparse_constraint_.cols, data.sparse_constraint_.nonZeros());
         std::printf("num_equality %d\nnum_inequality %d\n", data.num_equality_, data.num_inequality_);
@@ -134,6 +137,94 @@ int main(int argc, char** argv) {
                 std::printf("yaml_num_nodes %d\nyaml_friction %.6f\nyaml_frames %zu\n", from_file.num_nodes, from_file.friction_coef,
                             from_file.ee_frames.size());
             }
+        }
+        {   // "Clarabel Solver" of test/mpc_test.cpp:857-953: the 3-variable QP through the solver seam (QPData + ClarabelInterface::SetupQP /
+            // Solve), here on the CUDA path.  Rows in Clarabel form: the two equalities, then G x <= ub and -G x <= -lb.
+            QPData qp;
+            qp.num_decision_vars = 3;
+            qp.constraints_ = {Dynamics, ForceBox};   // a Zero cone of 2 rows and a Nonnegative cone of 4 rows
+            qp.num_dynamics_constraints = 2;
+            qp.num_force_box_constraints_ = 4;
+            qp.num_equality_ = 2;
+            qp.num_inequality_ = 4;
+            const double Pd[3] = {3.001, 4.0, 0.5};
+            qp.sparse_cost_.rows = qp.sparse_cost_.cols = 3;
+            qp.sparse_cost_.outer = {0, 1, 2, 3};
+            qp.sparse_cost_.inner = {0, 1, 2};
+            qp.sparse_cost_.values = {Pd[0], Pd[1], Pd[2]};
+            const double A[6][3] = {{1, 1, 0}, {1.3, 0, 0.2}, {-2, 0, 0.9}, {1, 8, 5}, {2, 0, -0.9}, {-1, -8, -5}};
+            const double b[6] = {1, 3, 3.1, 13.3, 2, 5};
+            qp.sparse_constraint_.rows = 6;
+            qp.sparse_constraint_.cols = 3;
+            qp.sparse_constraint_.outer.push_back(0);
+            for (int j = 0; j < 3; ++j) {
+                for (int i = 0; i < 6; ++i)
+                    if (A[i][j] != 0.0) {   // SparseMatrixBuilder drops exact zeros (utils/sparse_matrix_builder.cpp:25)
+                        qp.sparse_constraint_.inner.push_back(i);
+                        qp.sparse_constraint_.values.push_back(A[i][j]);
+                    }
+                qp.sparse_constraint_.outer.push_back(static_cast<int>(qp.sparse_constraint_.inner.size()));
+            }
+            qp.cost_linear = vector_t(3);
+            qp.cost_linear(0) = 0.1; qp.cost_linear(1) = 4.6; qp.cost_linear(2) = 2.0;
+            qp.ub_ = vector_t(6);
+            for (int i = 0; i < 6; ++i) qp.ub_(i) = b[i];
+            ClarabelInterface clarabel(qp, false);
+            clarabel.SetupQP(qp, vector_t::Zero(3));
+            const vector_t xs = clarabel.Solve(qp);
+            std::printf("qp3_quality %d\nqp3_x %.12e %.12e %.12e\n", static_cast<int>(clarabel.GetSolveQuality()), xs(0), xs(1), xs(2));
+            const vector_t dx = clarabel.Computedx(qp.sparse_cost_, qp.cost_linear, xs);
+            const vector_t dual = clarabel.GetDualSolution();
+            double stat = 0;   // stationarity dx + A'y = 0 (the dx of :955-958 with the returned multipliers)
+            for (int j = 0; j < 3; ++j) {
+                double r = dx(j);
+                for (int i = 0; i < 6; ++i) r += A[i][j] * dual(i);
+                stat = std::max(stat, std::abs(r));
+            }
+            std::printf("qp3_stationarity %.3e\n", stat);
+            // an infeasible QP throws the string the reference's Solve() catches (clarabel_interface.cpp:112-114)
+            QPData bad = qp;
+            bad.ub_(2) = -50.0;   // -2 x0 + 0.9 x2 <= -50 contradicts the equalities and the other box rows
+            bad.ub_(4) = -50.0;
+            bool caught = false;
+            try {
+                clarabel.SetupQP(bad, vector_t::Zero(3));
+                clarabel.Solve(bad);
+            } catch (const std::string& e) {
+                caught = (e == "Primal infeasible.");
+            }
+            std::printf("qp3_infeasible_throws %d\n", caught ? 1 : 0);
+        }
+        {   // MPC::AdjustForCurrentContacts (mpc.cpp:1195-1203): a foot that is measured in contact up to 70 ms before its planned
+            // touch-down is put in contact now; one that is far from its touch-down is left alone
+            MPCSingleRigidBody m2 = mpc;
+            const Trajectory before = m2.GetTrajectory();
+            const double t_now = before.GetTime(0);
+            int early = -1;
+            double td = 0;
+            for (int e = 0; e < 4; ++e)
+                if (!before.GetDesiredContacts(t_now).in_contact_.at(e)) { early = e; td = before.GetNextContactTime(e, t_now); break; }
+            std::printf("adjust_swing_foot %d\n", early);
+            if (early >= 0) {
+                controller::Contact c(4);
+                for (int e = 0; e < 4; ++e) c.in_contact_.at(e) = before.GetDesiredContacts(td - 0.05).in_contact_.at(e);
+                c.in_contact_.at(early) = true;
+                m2.AdjustForCurrentContacts(td - 0.05, c);    // 50 ms early: adjusted
+                std::printf("adjust_near %d\n", m2.GetTrajectory().GetDesiredContacts(td - 0.05).in_contact_.at(early) ? 1 : 0);
+                MPCSingleRigidBody m3 = mpc;
+                m3.AdjustForCurrentContacts(td - 0.15, c);    // 150 ms early: outside the 70 ms window, unchanged
+                std::printf("adjust_far %d\n", m3.GetTrajectory().GetDesiredContacts(td - 0.15).in_contact_.at(early) ? 1 : 0);
+            }
+        }
+        {   // mpc::MPCCentroidal adapter (mpc/include/mpc_centroidal.h:15-221): the header's call sequence reaches the live MPC
+            MPCCentroidal cen(info, ReadRobot(argv[1]));
+            cen.SetStateTrajectoryWarmStart(std::vector<vector_t>(info.num_nodes + 1, init_state));
+            cen.AddQuadraticTrackingCost(des_alg, Q);
+            cen.SetQuadraticFinalCost(Q);
+            cen.SetLinearFinalCost(lin);
+            cen.CreateInitialRun(init_state);
+            cen.GetRealTimeUpdate(6000, init_state, 0.0);
+            std::printf("centroidal_vars %d\ncentroidal_cost_equal %d\n", cen.GetNumDecisionVars(), cen.Live().GetCost() == cost_after_rt ? 1 : 0);
         }
         std::printf("done 1\n");
     } catch (const std::exception& e) {

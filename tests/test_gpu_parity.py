@@ -167,10 +167,19 @@ def test_sparse_qp_export_matches_reference_assembly(cfg_name):
     gpu = common.make_gpu(cfg_name, B, states)
     gpu.GetRealTimeUpdate(states, t0, ee)
     qps = gpu.GetQPData(0, B)
+    import pyoracle as po
     for b in range(B):
         o = common.make_oracle(cfg_name, states[b])
         o.assemble(states[b], 0.0, ee[b])
         _assert_same_qp(qps[b], o.qp())
+        if po.have_ref_mpc():
+            # ... and against the reference's OWN assembly code (oracle/_ref/libref_mpc.so: mpc_single_rigid_body.cpp, mpc.cpp,
+            # qp_data.cpp, sparse_matrix_builder.cpp compiled from /root/reference; travels to the GPU box prebuilt)
+            r = po.SrbMpc(cfg["num_nodes"], cfg["integrator_dt"], wl.robot(), which="ref", **wl.mpc_kwargs(cfg))
+            r.set_costs(wl.target_tangent(cfg), np.asarray(cfg["Q"], float))
+            r.set_warm_states(np.tile(states[b], (cfg["num_nodes"] + 1, 1)))
+            r.solve(states[b], 0.0, ee[b])
+            _assert_same_qp(qps[b], r.qp())
 
 
 def test_receding_horizon_with_mirrored_trajectory():
@@ -683,3 +692,56 @@ def test_full_size_disturbance_sweep_properties():
         assert np.all(np.isfinite(x))
         mom.append(np.linalg.norm(x[0, 3:5]))
     assert np.median(mom) < 0.85 * np.median(mom0), (np.median(mom), np.median(mom0))
+
+
+def test_generic_qp_interface_on_the_references_own_qp():
+    """QPInterface::SetupQP / Solve on the CUDA path (bgg_qp_solve_batch): the reference's own 3-variable cross-solver QP
+    (test/mpc_test.cpp:857-904; its Clarabel and OSQP solutions must agree to 1e-4, :951-953) against the closed-form optimum,
+    then a batch of random strictly convex QPs and an infeasible one against the oracle's restatement of the same solver."""
+    import scipy.sparse as sp
+    import pyoracle as po
+    cfg_name = "a1_configuration"
+    gpu = common.make_gpu(cfg_name, 1)
+    P = np.diag([3.001, 4.0, 0.5])
+    q = np.array([0.1, 4.6, 2.0])
+    Ae, be = np.array([[1.0, 1.0, 0.0], [1.3, 0.0, 0.2]]), np.array([1.0, 3.0])
+    G, lo, hi = np.array([[-2.0, 0.0, 0.9], [1.0, 8.0, 5.0]]), np.array([-2.0, -5.0]), np.array([3.1, 13.3])
+    A = np.vstack([Ae, G, -G])                       # Clarabel form: equalities, then G x <= hi and -G x <= -lo
+    b = np.concatenate([be, hi, -lo])
+    is_eq = np.array([1, 1, 0, 0, 0, 0], bool)
+    r = gpu.SolveQP(sp.csc_matrix(P), q, sp.csc_matrix(A), b, is_eq)
+    assert r["status"][0] == 0
+    o = po.ipm_solve(sp.csc_matrix(P), q, sp.csc_matrix(A), b, is_eq)
+    assert o["status"] == 0
+    # closed form (tests/test_oracle_qp.py: two equalities leave one degree of freedom, the QP is a 1-D quadratic on an interval)
+    import test_oracle_qp
+    x_star = test_oracle_qp.exact_solution()
+    assert np.abs(r["x"][0] - x_star).max() <= 1e-4 * max(1.0, np.abs(x_star).max())
+    assert np.abs(r["x"][0] - o["x"]).max() <= 1e-6
+    assert np.abs(P @ r["x"][0] + q + A.T @ r["y"][0]).max() <= 1e-6      # dx = P x + q and the multipliers (:958)
+    # random strictly convex QPs of one pattern, one batch
+    rng = np.random.default_rng(2)
+    n, me, mi, count = 24, 4, 40, 16
+    Ps, As, qs, bs = [], [], [], []
+    for _ in range(count):
+        M = rng.normal(size=(n, n))
+        Ps.append(sp.csc_matrix(np.triu(M @ M.T + 0.1 * np.eye(n))))
+        Am = rng.normal(size=(me + mi, n))
+        xf = rng.normal(size=n)
+        bs.append(np.concatenate([Am[:me] @ xf, Am[me:] @ xf + rng.uniform(0.0, 1.0, mi)]))
+        As.append(sp.csc_matrix(Am))
+        qs.append(rng.normal(size=n))
+    eq = np.array([1] * me + [0] * mi, bool)
+    r = gpu.SolveQP(Ps, np.array(qs), As, np.array(bs), eq)
+    for k in range(count):
+        Pf = Ps[k].toarray()
+        Pf = Pf + Pf.T - np.diag(np.diag(Pf))
+        o = po.ipm_solve(sp.csc_matrix(Pf), qs[k], As[k], bs[k], eq)
+        assert r["status"][k] == o["status"] == 0
+        assert abs(int(r["iters"][k]) - o["iters"]) <= 1
+        assert np.abs(r["x"][k] - o["x"]).max() <= 1e-6 * max(1.0, np.abs(o["x"]).max())
+        assert np.abs(r["y"][k] - o["y"]).max() <= 1e-5 * max(1.0, np.abs(o["y"]).max())
+    # an infeasible QP: x <= -1 and -x <= -1 (x >= 1)
+    r = gpu.SolveQP(sp.csc_matrix(np.array([[1.0]])), np.array([0.0]), sp.csc_matrix(np.array([[1.0], [-1.0]])), np.array([-1.0, -1.0]),
+                    np.array([0, 0], bool))
+    assert r["status"][0] == 3

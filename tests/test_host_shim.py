@@ -111,6 +111,18 @@ force_cost: 0.000
     rows = log[header + 2:]
     assert len(rows) == 2 and rows[0][:15].strip() == "10" and rows[1][:15].strip() == "11" and "Solved" in rows[0]
 
+    # the solver seam on the reference's own 3-variable QP (test/mpc_test.cpp:857-953): quality, primal within its 1e-4 margin of
+    # the closed-form optimum, stationarity with the returned multipliers, and the "Primal infeasible." throw
+    import test_oracle_qp
+    assert kv["qp3_quality"] == ["0"]
+    assert np.abs(np.array([float(v) for v in kv["qp3_x"]]) - test_oracle_qp.exact_solution()).max() < 1e-4
+    assert float(kv["qp3_stationarity"][0]) < 1e-6
+    assert kv["qp3_infeasible_throws"] == ["1"]
+    # AdjustForCurrentContacts: inside the 70 ms window the foot is put in contact, outside it is not (mpc.cpp:1195-1203)
+    assert int(kv["adjust_swing_foot"][0]) >= 0 and kv["adjust_near"] == ["1"] and kv["adjust_far"] == ["0"]
+    # the MPCCentroidal adapter runs the same solves as the live class
+    assert kv["centroidal_vars"] == ["372"] and kv["centroidal_cost_equal"] == ["1"]
+
     cfg_name = "a1_configuration"
     cfg = wl.CONFIGS[cfg_name]
     init = np.asarray(cfg["srb_init"], float)
