@@ -298,6 +298,10 @@ def main():
 
         # end to end through the public call with HOST buffers: H2D of the step's inputs and D2H of its results (status, iteration
         # count, step length, cost AND the decision vector a controller consumes) inside the timed region
+        if mode == "closed_loop":       # untimed: the first read-back allocates the pinned staging buffers of the decision vectors
+            mpc.download(z_out=z_host)
+        else:
+            mpc.GetRealTimeUpdate(st, t0, ee, z_out=z_host)
         barrier()
         t_start = time.perf_counter()
         for _ in range(steps):

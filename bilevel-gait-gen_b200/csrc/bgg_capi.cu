@@ -40,9 +40,19 @@ struct bgg_handle {
     double* d_zout = nullptr;    // compact copy of the decision vectors [batch][zcap], allocated on first use
     double* h_zout = nullptr;    // pinned
     int zcap = 0;
-    int* d_max = nullptr;        // batch maxima (nu, n_samples) of the current solve
-    int* h_max = nullptr;        // pinned
-    int last_nu_max = 0, last_ns_max = 0;   // batch maxima of the last solve (shared-memory sizing of later kernels)
+    // Shared-memory sizing without a host round trip inside a solve: every solve measures its batch maxima (nu, n_samples) on the
+    // device and ships them to pinned memory behind an event; the NEXT solve's first pass is launched with the latest maxima that
+    // have arrived (worst case until the first ones do), instances that outgrew them are caught by a second pass.  One record
+    // for the main batch, one for the line-search children (their contact schedules differ from the parents').
+    struct Caps {
+        int* d_max = nullptr;        // device: maxima of the solve in flight
+        int* h_max = nullptr;        // pinned
+        cudaEvent_t ev = nullptr;
+        bool pending = false;
+        int nu = 0, ns = 0;          // 0: unknown (launch with the worst case)
+    };
+    Caps caps_main, caps_ls;
+    int last_nu_max = 0, last_ns_max = 0;   // caps the main batch's last solve was launched with (sizing of k_gradient)
     int max_smem = 0;
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -261,8 +271,11 @@ int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) 
     }
     for (auto& e : h->ev) cudaEventCreate(&e);
     for (auto& e : h->user_ev) cudaEventCreate(&e);
-    cudaMalloc(&h->d_max, 2 * sizeof(int));
-    cudaMallocHost(&h->h_max, 2 * sizeof(int));
+    for (bgg_handle::Caps* c : {&h->caps_main, &h->caps_ls}) {
+        cudaMalloc(&c->d_max, 2 * sizeof(int));
+        cudaMallocHost(&c->h_max, 2 * sizeof(int));
+        cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming);
+    }
     *out = h;
     return BGG_OK;
 }
@@ -298,6 +311,11 @@ static void free_batch(bgg_handle* h) {
     h->d_hdr = nullptr;
     h->h_hdr = nullptr;
     h->batch = 0;
+    for (bgg_handle::Caps* c : {&h->caps_main, &h->caps_ls}) {   // sizes of another batch say nothing about the next one
+        c->pending = false;
+        c->nu = c->ns = 0;
+    }
+    h->last_nu_max = h->last_ns_max = 0;
 }
 
 void bgg_destroy(bgg_handle* h) {
@@ -309,8 +327,11 @@ void bgg_destroy(bgg_handle* h) {
         if (e) cudaEventDestroy(e);
     for (auto& e : h->user_ev)
         if (e) cudaEventDestroy(e);
-    cudaFree(h->d_max);
-    cudaFreeHost(h->h_max);
+    for (bgg_handle::Caps* c : {&h->caps_main, &h->caps_ls}) {
+        cudaFree(c->d_max);
+        cudaFreeHost(c->h_max);
+        if (c->ev) cudaEventDestroy(c->ev);
+    }
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -402,26 +423,47 @@ int bgg_upload_inputs(bgg_handle* h, const double* state, const double* t0, cons
     return BGG_OK;
 }
 
-// steps 1-11 of MPCSingleRigidBody::Solve for `B` instances living in (inst, ws) with inputs (state, t0, ee) on the device
-static int solve_pipeline(bgg_handle* h, Instance* inst, char* ws, const double* state, const double* t0, const double* ee, int B,
-                          bool profile) {
+static void refresh_caps(bgg_handle::Caps& caps) {
+    if (caps.pending && cudaEventQuery(caps.ev) == cudaSuccess) {   // the last solve's maxima have arrived
+        caps.nu = caps.h_max[0] > 0 ? caps.h_max[0] : 8;
+        caps.ns = caps.h_max[1];
+        caps.pending = false;
+    }
+}
+
+// steps 1-11 of MPCSingleRigidBody::Solve for `B` instances living in (inst, ws) with inputs (state, t0, ee) on the device.
+// Nothing here waits for the device.
+static int solve_pipeline(bgg_handle* h, bgg_handle::Caps& caps, Instance* inst, char* ws, const double* state, const double* t0, const double* ee,
+                          int B, bool profile) {
+    refresh_caps(caps);
+    const int worst_nu = h->L.max_nu, worst_ns = kMaxSamples;
+    const int nu_cap = caps.nu > 0 ? caps.nu : worst_nu, ns_cap = caps.nu > 0 ? caps.ns : worst_ns;
     if (profile) cudaEventRecord(h->ev[0], h->stream);
     launch_prepare(h->P, inst, state, t0, ee, h->L, ws, B, h->stream);
-    // shared memory (and with it the number of CTAs per SM) is sized from this batch's actual problem sizes
-    launch_batch_max(h->L, ws, B, h->d_max, h->stream);
-    CU(cudaMemcpyAsync(h->h_max, h->d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    launch_batch_max(h->L, ws, B, caps.d_max, (nu_cap + 7) / 8 * 8, ns_cap, h->stream);
+    if (!caps.pending) {   // (a copy still in flight keeps its slot: the host must not see a half-written pair)
+        CU(cudaMemcpyAsync(caps.h_max, caps.d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventRecord(caps.ev, h->stream));
+        caps.pending = true;
+    }
     if (profile) cudaEventRecord(h->ev[1], h->stream);
-    CU(cudaStreamSynchronize(h->stream));
-    const int nu_max = h->h_max[0] > 0 ? h->h_max[0] : 8, ns_max = h->h_max[1];
-    h->last_nu_max = nu_max;
-    h->last_ns_max = ns_max;
-    launch_condense(h->P, h->L, ws, B, nu_max, h->stream);
+    launch_condense(h->P, h->L, ws, B, nu_cap, 0, h->stream);
     if (profile) cudaEventRecord(h->ev[2], h->stream);
-    launch_ipm(h->P, h->L, ws, B, nu_max, ns_max, h->stream);
+    launch_ipm(h->P, h->L, ws, B, nu_cap, ns_cap, 0, h->stream);
     if (profile) cudaEventRecord(h->ev[3], h->stream);
-    launch_finish(h->P, inst, h->L, ws, B, h->stream);
+    launch_finish(h->P, inst, h->L, ws, B, 0, h->stream);
     if (profile) cudaEventRecord(h->ev[4], h->stream);
     h->launches += 5;
+    if (nu_cap < worst_nu || ns_cap < worst_ns) {   // second pass: the instances that outgrew the caps (CTAs of all others return at once)
+        launch_condense(h->P, h->L, ws, B, worst_nu, 2, h->stream);
+        launch_ipm(h->P, h->L, ws, B, worst_nu, worst_ns, 2, h->stream);
+        launch_finish(h->P, inst, h->L, ws, B, 2, h->stream);
+        h->launches += 3;
+    }
+    if (&caps == &h->caps_main) {
+        h->last_nu_max = nu_cap;
+        h->last_ns_max = ns_cap;
+    }
     CU(cudaGetLastError());
     return BGG_OK;
 }
@@ -430,7 +472,7 @@ int bgg_solve_resident(bgg_handle* h) {
     if (!h || !h->batch) return fail(BGG_EINVAL, "no batch");
     if (!h->costs_set) return fail(BGG_ESTATE, "bgg_set_costs has not been called");
     CU(cudaSetDevice(h->device));
-    return solve_pipeline(h, h->d_inst, h->d_ws, h->d_state, h->d_t0, h->d_ee, h->batch, h->profiling);
+    return solve_pipeline(h, h->caps_main, h->d_inst, h->d_ws, h->d_state, h->d_t0, h->d_ee, h->batch, h->profiling);
 }
 
 int bgg_advance_plant(bgg_handle* h, double dt) {
@@ -723,6 +765,12 @@ int bgg_gait_gradient_batch(bgg_handle* h, int32_t* status, int32_t* n_contacts,
     if (!h->last_nu_max) return fail(BGG_ESTATE, "bgg_gait_gradient_batch needs a solve first");
     CU(cudaSetDevice(h->device));
     const int B = h->batch;
+    CU(cudaStreamSynchronize(h->stream));
+    refresh_caps(h->caps_main);   // the main batch's own maxima of its last solve (not the line-search children's)
+    if (h->caps_main.nu > 0) {
+        h->last_nu_max = h->caps_main.nu;
+        h->last_ns_max = h->caps_main.ns;
+    }
     // 14 KB of the opt-in shared memory are taken by the kernel's static arrays (the four staged foot splines)
     if (launch_gradient(h->P, h->d_inst, h->L, h->d_ws, B, h->last_nu_max, h->last_ns_max, h->max_smem - 14 * 1024, h->stream))
         return fail(BGG_EINVAL, "the gait-gradient kernel needs more shared memory than the device offers for this many spline variables");
@@ -804,7 +852,7 @@ int bgg_line_search_batch(bgg_handle* h, int K, const double* xk, const double* 
     CU(cudaMemcpyAsync(d_vec + nv, step, 8 * nv, cudaMemcpyHostToDevice, h->stream));
     launch_ls_expand(h->d_inst, h->d_ls_inst, h->batch, K, d_vec, d_vec + nv, h->d_state, h->d_t0, h->d_ee, h->d_ls_state, h->d_ls_t0,
                      h->d_ls_ee, h->stream);
-    rc = solve_pipeline(h, h->d_ls_inst, h->d_ls_ws, h->d_ls_state, h->d_ls_t0, h->d_ls_ee, static_cast<int>(C), false);
+    rc = solve_pipeline(h, h->caps_ls, h->d_ls_inst, h->d_ls_ws, h->d_ls_state, h->d_ls_t0, h->d_ls_ee, static_cast<int>(C), false);
     if (rc) return rc;
     launch_ls_select(h->d_inst, h->d_ls_inst, h->L, h->d_ls_ws, h->batch, K, d_best, d_costs, d_q, h->stream);
     h->launches += 2;

@@ -23,12 +23,12 @@ static size_t finish_smem_bytes(const WsLayout& L) {
     return 2 * sizeof(FootSpline) * kNumEE + 8 * (4 * n_max + static_cast<size_t>(kNx) * (L.N + 1) + 64 + static_cast<size_t>(kNumEE) * 6 * L.N);
 }
 
-__global__ void __launch_bounds__(128) k_finish(Params P, Instance* __restrict__ inst, WsLayout L, char* __restrict__ ws_base) {
+__global__ void __launch_bounds__(128) k_finish(Params P, Instance* __restrict__ inst, WsLayout L, char* __restrict__ ws_base, int want) {
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     Instance& I = inst[b];
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
     WsHeader* Hd = reinterpret_cast<WsHeader*>(ws + L.hdr);
-    if (Hd->error) return;
+    if (Hd->error || Hd->pass_state != want) return;
     const NodeLin* nodes = reinterpret_cast<const NodeLin*>(ws + L.nodes);
     double* zprev_g = reinterpret_cast<double*>(ws + L.zprev);
     double* zqp_g = reinterpret_cast<double*>(ws + L.zqp);
@@ -282,14 +282,15 @@ __global__ void __launch_bounds__(128) k_finish(Params P, Instance* __restrict__
         Hd->cost = cost_new;
         Hd->merit = P.merit_mu * dfin + cost_rt;
         Hd->merit_dd = merit_dd;
+        Hd->pass_state = 1;   // done: the second pass of this solve leaves the instance alone
     }
 }
 
-void launch_finish(const Params& P, Instance* inst, const WsLayout& L, char* ws, int B, cudaStream_t stream) {
+void launch_finish(const Params& P, Instance* inst, const WsLayout& L, char* ws, int B, int want, cudaStream_t stream) {
     const size_t smem = finish_smem_bytes(L);
     // per device and context, so set on every launch (see launch_ipm)
     cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    k_finish<<<B, 128, smem, stream>>>(P, inst, L, ws);
+    k_finish<<<B, 128, smem, stream>>>(P, inst, L, ws, want);
 }
 
 }  // namespace bgg

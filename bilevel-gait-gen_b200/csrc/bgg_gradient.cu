@@ -70,6 +70,15 @@ __global__ void __launch_bounds__(256, 1) k_gradient(Params P, const Instance* _
         for (int i = tid; i < kNumEE * kMaxContacts; i += nth) gdH[i] = 0.0;
         return;
     }
+    if (Hd->nu > cap_nu || 6 * Hd->n_samples + 2 * Hd->n_eebox > cap_rows) {   // larger than the shared memory this launch was sized for
+        if (tid == 0) {
+            gi->status = 2;
+            gi->n_theta = 0;
+            for (int e = 0; e < kNumEE; ++e) gi->nct[e] = 0;
+        }
+        for (int i = tid; i < kNumEE * kMaxContacts; i += nth) gdH[i] = 0.0;
+        return;
+    }
     const NodeLin* nodes = reinterpret_cast<const NodeLin*>(ws + L.nodes);
     const Sample* samples = reinterpret_cast<const Sample*>(ws + L.samples);
     const EqRow* eqs = reinterpret_cast<const EqRow*>(ws + L.eq);

@@ -238,10 +238,11 @@ size_t ipm_smem_bytes(const WsLayout& L) {   // worst case for the configured ca
     return ipm_smem_core(L.N, L.max_nu, L.max_rows, kMaxSamples);
 }
 
-__global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi, int cap_nu, int cap_rows) {
+__global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi, int cap_nu, int cap_rows, int want) {
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
     WsHeader* Hd = reinterpret_cast<WsHeader*>(ws + L.hdr);
+    if (!Hd->error && Hd->pass_state != want) return;   // not this pass's instance (uniform over the CTA)
     if (Hd->error) {   // k_prepare refused the instance: no QP, no iterate (k_finish keeps the previous solution)
         if (tid == 0) {
             Hd->status = kOther;
@@ -764,7 +765,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     (void)gscale;
 }
 
-void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, cudaStream_t stream) {
+void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, cudaStream_t stream) {
     const IpmCaps c = ipm_caps(L, nu_max, ns_max);
     const size_t smem = ipm_smem_for(L, c);
     // the opt-in is per device and context: set on every launch (a second handle on another GPU, or another host thread,
@@ -775,7 +776,7 @@ void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max,
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, k_ipm, 256, smem);
         fprintf(stderr, "k_ipm: dynamic smem %zu B, caps nu %d rows %d, stage_phi %d, resident CTAs per SM %d\n", smem, c.nu, c.rows, c.stage_phi, nblk);
     }
-    k_ipm<<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows);
+    k_ipm<<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want);
 }
 
 }  // namespace bgg

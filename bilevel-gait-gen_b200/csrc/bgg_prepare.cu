@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(128) k_prepare(Params P, Instance* __restrict_
         sh.ls_iters = 0;
         sh.no_iterate = 0;
         sh.refined_iters = 0;
-        sh.pad1 = 0;
+        sh.pass_state = 0;
         sh.cost = 0.0;      // k_finish writes these; a refused instance (error != 0) must not carry stale or uninitialised values
         sh.qp_cost = 0.0;
         sh.alpha = 0.0;

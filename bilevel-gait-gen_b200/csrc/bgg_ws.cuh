@@ -23,7 +23,9 @@ struct WsHeader {
     int32_t error;                        // bit 0: too many knots, bit 1: nu > max_nu, bit 2: too many samples
     int32_t status, iters, ls_iters;
     int32_t no_iterate;                   // the solver stopped before its first finite residual evaluation: u holds nothing
-    int32_t refined_iters, pad1;          // iterations of the last solve that ran with iterative refinement
+    int32_t refined_iters;                // iterations of the last solve that ran with iterative refinement
+    int32_t pass_state;                   // 0 pending, 1 solved by this launch sequence, 2 larger than the caps the first pass was
+                                          // launched with: picked up by the second pass (worst-case shared memory), see bgg_capi.cu
     double t0;
     double cost_const;                    // 1/2 phi'P phi + q'phi: condensed objective + cost_const = full objective
     double alpha, cost, qp_cost, prim_res, dual_res, gap, eq_violation, step_norm, merit, merit_dd;
