@@ -75,6 +75,7 @@ def lib():
         L.bgg_solve_batch.argtypes = [C.c_void_p, _dp, _dp, _dp, _ip, _ip, _dp, _dp, _dp, C.c_int]
         L.bgg_qp_solve_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _ip, _ip, _dp, _dp, _dp, C.POINTER(C.c_uint8),
                                          _dp, _dp, _dp, _ip, _ip]
+        L.bgg_controller_get_step.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.bgg_upload_inputs.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.bgg_solve_resident.argtypes = [C.c_void_p]
         L.bgg_download_results.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, _dp, C.c_int]
@@ -108,7 +109,7 @@ def lib():
 def exported_symbols():
     """Names include/bgg.h declares; used by the CPU-side ABI test."""
     return ["bgg_last_error", "bgg_device_count", "bgg_measure_fp64_peak", "bgg_create", "bgg_destroy", "bgg_set_costs", "bgg_batch_reset",
-            "bgg_set_warm_states", "bgg_set_contact_times", "bgg_solve_batch", "bgg_qp_solve_batch", "bgg_upload_inputs", "bgg_solve_resident",
+            "bgg_set_warm_states", "bgg_set_contact_times", "bgg_solve_batch", "bgg_qp_solve_batch", "bgg_controller_tick_batch", "bgg_controller_get_step", "bgg_upload_inputs", "bgg_solve_resident",
             "bgg_download_results", "bgg_synchronize", "bgg_advance_plant", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count", "bgg_event_record", "bgg_event_elapsed_ms",
             "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_export_qp_csc", "bgg_gait_gradient_batch", "bgg_optimize_contact_times_batch",
             "bgg_line_search_batch", "bgg_get_adjoint",
@@ -403,6 +404,12 @@ class BatchedMPC:
         dnu, nu, dnue = np.zeros(12 * (self.N + 1)), np.zeros(12 * (self.N + 1)), np.zeros(sz["n_eq"])
         self._chk(self.L.bgg_get_adjoint(self.h, b, _d(dz), _d(dlam), _d(dnu), _d(dnue), _d(nu)))
         return dict(dz=dz, dlam=dlam, dnu_dyn=dnu, dnu_eq=dnue, nu_dyn=nu, sizes=sz)
+
+    def controller_step(self):
+        """The contact-time step of the last GAIT_OPT controller tick (bgg_controller_get_step): dict(step, xk, new_times)."""
+        step, xk, nt = (np.zeros((self.B, NUM_EE, MAX_CONTACTS)) for _ in range(3))
+        self._chk(self.L.bgg_controller_get_step(self.h, _d(step), _d(xk), _d(nt)))
+        return dict(step=step, xk=xk, new_times=nt)
 
     def GetContactTimes(self, first=0, count=None):
         count = self.B - first if count is None else count

@@ -20,6 +20,6 @@ $NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_capi.o csrc/bgg_capi.cu 2> buil
 $NVCC $ARCH -shared -o libbgg_b200.so build/bgg_prepare.o build/bgg_condense.o build/bgg_ipm.o build/bgg_finish.o build/bgg_assemble.o build/bgg_gradient.o build/bgg_gait.o build/bgg_qp.o build/bgg_capi.o -lcudart
 # host shim: the reference's C++ call surface over the C ABI (no CUDA in these translation units) and its test driver
 CXX=${CXX:-g++}
-$CXX -O2 -std=c++17 -Wall -fPIC -shared -o libmpc_b200.so host/mpc_b200.cpp host/urdf_consts.cpp host/config_parser.cpp -L. -lbgg_b200 -Wl,-rpath,'$ORIGIN'
+$CXX -O2 -std=c++17 -Wall -fPIC -shared -o libmpc_b200.so host/mpc_b200.cpp host/mpc_controller_b200.cpp host/urdf_consts.cpp host/config_parser.cpp -L. -lbgg_b200 -Wl,-rpath,'$ORIGIN'
 $CXX -O2 -std=c++17 -Wall -Ihost -o ../tests/cpp/test_shim ../tests/cpp/test_shim.cpp -L. -lmpc_b200 -lbgg_b200 -Wl,-rpath,'$ORIGIN/../../bilevel-gait-gen_b200'
 echo "built $(pwd)/libbgg_b200.so $(pwd)/libmpc_b200.so"

@@ -60,6 +60,15 @@ struct bgg_handle {
     int64_t launches = 0;
     cudaEvent_t user_ev[8] = {};
     bool costs_set = false;
+    // controller tick (bgg_controller_tick_batch): the gait optimiser's step lives on the device between the tick that computes it
+    // and the tick that searches along it; allocated on the first tick
+    double* d_tick = nullptr;        // step | xk | new_times, each [batch][4][kMaxContacts]
+    int32_t* d_tick_i = nullptr;     // LP status [batch][4] | deriv_ready [batch] | ls_best [batch]
+    double* d_tick_ls = nullptr;     // line-search costs [batch * K]
+    int32_t* d_tick_lsq = nullptr;   // line-search quality [batch * K]
+    int tick_ls_cap = 0;
+    double* h_tick = nullptr;        // pinned: dH/dtheta [batch][4][kMaxContacts]
+    int32_t* h_tick_i = nullptr;     // pinned: deriv_ready [batch] | ls_best [batch]
     // line-search children (batch x K copies), allocated on first use
     int ls_cap = 0;
     Instance* d_ls_inst = nullptr;
@@ -74,6 +83,20 @@ __global__ void k_gather_z(WsLayout L, const char* __restrict__ ws, double* __re
     const int n = reinterpret_cast<const WsHeader*>(w + L.hdr)->n;
     const double* z = reinterpret_cast<const double*>(w + L.zprev);
     for (int i = threadIdx.x; i < stride; i += blockDim.x) out[static_cast<size_t>(b) * stride + i] = (i < n) ? z[i] : 0.0;
+}
+
+// controller tick helpers
+__global__ void k_deriv_ready(WsLayout L, const char* __restrict__ ws, int B, int32_t* __restrict__ ready, double* __restrict__ dH) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const char* w = ws + static_cast<size_t>(b) * L.stride;
+    ready[b] = reinterpret_cast<const GradInfo*>(w + L.ginfo)->status == 0 ? 1 : 0;   // GaitOpt returns false unless the solve was Solved
+    const double* g = reinterpret_cast<const double*>(w + L.gdH);
+    for (int i = 0; i < kNumEE * kMaxContacts; ++i) dH[static_cast<size_t>(b) * kNumEE * kMaxContacts + i] = g[i];
+}
+__global__ void k_mask_step(double* __restrict__ step, const int32_t* __restrict__ ready, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * kNumEE * kMaxContacts && !ready[i / (kNumEE * kMaxContacts)]) step[i] = 0.0;   // no derivative: every candidate is the unchanged schedule
 }
 
 __global__ void k_gather_headers(WsLayout L, const char* __restrict__ ws, WsHeader* __restrict__ out, int B) {
@@ -287,6 +310,11 @@ static void free_batch(bgg_handle* h) {
     cudaFree(h->d_t0);
     cudaFree(h->d_ee);
     cudaFree(h->d_hdr);
+    cudaFree(h->d_tick); cudaFree(h->d_tick_i); cudaFree(h->d_tick_ls); cudaFree(h->d_tick_lsq);
+    cudaFreeHost(h->h_tick); cudaFreeHost(h->h_tick_i);
+    h->d_tick = h->d_tick_ls = h->h_tick = nullptr;
+    h->d_tick_i = h->d_tick_lsq = h->h_tick_i = nullptr;
+    h->tick_ls_cap = 0;
     cudaFree(h->d_zout);
     cudaFreeHost(h->h_zout);
     h->d_zout = h->h_zout = nullptr;
@@ -423,12 +451,14 @@ int bgg_upload_inputs(bgg_handle* h, const double* state, const double* t0, cons
     return BGG_OK;
 }
 
+// Take delivery of the maxima of the last solve that measured them.  The event sits right behind that solve's k_prepare /
+// k_batch_max, in front of its condense / interior-point / finish kernels: waiting for it never drains the stream.
 static void refresh_caps(bgg_handle::Caps& caps) {
-    if (caps.pending && cudaEventQuery(caps.ev) == cudaSuccess) {   // the last solve's maxima have arrived
-        caps.nu = caps.h_max[0] > 0 ? caps.h_max[0] : 8;
-        caps.ns = caps.h_max[1];
-        caps.pending = false;
-    }
+    if (!caps.pending) return;
+    cudaEventSynchronize(caps.ev);
+    caps.nu = caps.h_max[0] > 0 ? caps.h_max[0] : 8;
+    caps.ns = caps.h_max[1];
+    caps.pending = false;
 }
 
 // steps 1-11 of MPCSingleRigidBody::Solve for `B` instances living in (inst, ws) with inputs (state, t0, ee) on the device.
@@ -441,11 +471,9 @@ static int solve_pipeline(bgg_handle* h, bgg_handle::Caps& caps, Instance* inst,
     if (profile) cudaEventRecord(h->ev[0], h->stream);
     launch_prepare(h->P, inst, state, t0, ee, h->L, ws, B, h->stream);
     launch_batch_max(h->L, ws, B, caps.d_max, (nu_cap + 7) / 8 * 8, ns_cap, h->stream);
-    if (!caps.pending) {   // (a copy still in flight keeps its slot: the host must not see a half-written pair)
-        CU(cudaMemcpyAsync(caps.h_max, caps.d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaEventRecord(caps.ev, h->stream));
-        caps.pending = true;
-    }
+    CU(cudaMemcpyAsync(caps.h_max, caps.d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(caps.ev, h->stream));
+    caps.pending = true;
     if (profile) cudaEventRecord(h->ev[1], h->stream);
     launch_condense(h->P, h->L, ws, B, nu_cap, 0, h->stream);
     if (profile) cudaEventRecord(h->ev[2], h->stream);
@@ -591,6 +619,108 @@ int bgg_qp_solve_batch(bgg_handle* h, int count, int n, int m, const int32_t* P_
     if (status) CU(cudaMemcpyAsync(status, dst, 4 * static_cast<size_t>(count), cudaMemcpyDeviceToHost, st));
     if (iters) CU(cudaMemcpyAsync(iters, dit, 4 * static_cast<size_t>(count), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return BGG_OK;
+}
+
+static int ensure_ls_children(bgg_handle* h, size_t C) {
+    if (static_cast<int>(C) <= h->ls_cap) return BGG_OK;
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_ls_inst); cudaFree(h->d_ls_ws); cudaFree(h->d_ls_state); cudaFree(h->d_ls_t0); cudaFree(h->d_ls_ee);
+    h->ls_cap = 0;
+    CU(cudaMalloc(&h->d_ls_inst, sizeof(Instance) * C));
+    CU(cudaMalloc(&h->d_ls_ws, h->L.stride * C));
+    CU(cudaMalloc(&h->d_ls_state, 8 * kNxMan * C));
+    CU(cudaMalloc(&h->d_ls_t0, 8 * C));
+    CU(cudaMalloc(&h->d_ls_ee, 8 * 12 * C));
+    CU(cudaMemsetAsync(h->d_ls_ws, 0, h->L.stride * C, h->stream));
+    h->ls_cap = static_cast<int>(C);
+    return BGG_OK;
+}
+
+int bgg_controller_tick_batch(bgg_handle* h, int mode, int K, const double* state, const double* t0, const double* ee_start, int32_t* status,
+                              int32_t* iters, double* alpha, double* cost, double* z, int z_stride, int32_t* deriv_ready, double* dHdtheta,
+                              int32_t* ls_best, double* ls_costs, int32_t* ls_quality) {
+    if (!h || !h->batch || !state || !t0 || !ee_start) return fail(BGG_EINVAL, "null argument / no batch");
+    if (mode < BGG_TICK_SOLVE || mode > BGG_TICK_LINE_SEARCH) return fail(BGG_EINVAL, "mode must be BGG_TICK_SOLVE, BGG_TICK_SOLVE_GAIT_OPT or BGG_TICK_LINE_SEARCH");
+    if (mode == BGG_TICK_LINE_SEARCH && K <= 0) return fail(BGG_EINVAL, "the line search needs K > 0 candidates");
+    if (!h->costs_set) return fail(BGG_ESTATE, "bgg_set_costs has not been called");
+    CU(cudaSetDevice(h->device));
+    const size_t B = h->batch, nv = B * kNumEE * kMaxContacts;
+    if (!h->d_tick) {   // first tick of this batch
+        CU(cudaMalloc(&h->d_tick, 8 * 4 * nv));
+        CU(cudaMalloc(&h->d_tick_i, 4 * (B * kNumEE + 2 * B)));
+        CU(cudaMallocHost(&h->h_tick, 8 * nv));
+        CU(cudaMallocHost(&h->h_tick_i, 4 * 2 * B));
+        CU(cudaMemsetAsync(h->d_tick, 0, 8 * 4 * nv, h->stream));
+        CU(cudaMemsetAsync(h->d_tick_i, 0, 4 * (B * kNumEE + 2 * B), h->stream));
+    }
+    double *d_step = h->d_tick, *d_xk = h->d_tick + nv, *d_times = h->d_tick + 2 * nv, *d_dH = h->d_tick + 3 * nv;
+    int32_t *d_lpst = h->d_tick_i, *d_ready = h->d_tick_i + B * kNumEE, *d_best = d_ready + B;
+    int rc = bgg_upload_inputs(h, state, t0, ee_start);
+    if (rc) return rc;
+    if (mode == BGG_TICK_LINE_SEARCH) {
+        // GaitOptimizer::LineSearch (gait_optimizer.cpp:671-753) from the step of the last GaitOpt tick: K copies, one RTI solve each,
+        // arg-min, SetWarmStartTrajectory(best); instances without a derivative search along a zero step (a plain update)
+        const size_t C = B * K;
+        if ((rc = ensure_ls_children(h, C))) return rc;
+        if (static_cast<int>(C) > h->tick_ls_cap) {
+            CU(cudaStreamSynchronize(h->stream));
+            cudaFree(h->d_tick_ls); cudaFree(h->d_tick_lsq);
+            h->tick_ls_cap = 0;
+            CU(cudaMalloc(&h->d_tick_ls, 8 * C));
+            CU(cudaMalloc(&h->d_tick_lsq, 4 * C));
+            h->tick_ls_cap = static_cast<int>(C);
+        }
+        k_mask_step<<<static_cast<unsigned>((nv + 255) / 256), 256, 0, h->stream>>>(d_step, d_ready, h->batch);
+        launch_ls_expand(h->d_inst, h->d_ls_inst, h->batch, K, d_xk, d_step, h->d_state, h->d_t0, h->d_ee, h->d_ls_state, h->d_ls_t0, h->d_ls_ee, h->stream);
+        if ((rc = solve_pipeline(h, h->caps_ls, h->d_ls_inst, h->d_ls_ws, h->d_ls_state, h->d_ls_t0, h->d_ls_ee, static_cast<int>(C), false))) return rc;
+        launch_ls_select(h->d_inst, h->d_ls_inst, h->L, h->d_ls_ws, h->batch, K, d_best, h->d_tick_ls, h->d_tick_lsq, h->stream);
+        CU(cudaMemsetAsync(d_ready, 0, 4 * B, h->stream));   // deriv_ready_ = false (mpc_controller.cpp:335)
+        h->launches += 3;
+    } else {
+        if ((rc = solve_pipeline(h, h->caps_main, h->d_inst, h->d_ws, h->d_state, h->d_t0, h->d_ee, h->batch, h->profiling))) return rc;
+        if (mode == BGG_TICK_SOLVE_GAIT_OPT) {
+            // MPCController::GaitOpt (:518-573): derivative terms and dH/dtheta, then the contact-time LP; the step stays on the device.
+            // The gradient kernel's dense system is sized exactly: this solve's own maxima (its k_prepare is done by now or in a few
+            // microseconds; the solve kernels are queued behind it, so the device stays busy while the host looks).
+            refresh_caps(h->caps_main);
+            h->last_nu_max = h->caps_main.nu;
+            h->last_ns_max = h->caps_main.ns;
+            if (launch_gradient(h->P, h->d_inst, h->L, h->d_ws, h->batch, h->last_nu_max, h->last_ns_max, h->max_smem - 14 * 1024, h->stream))
+                return fail(BGG_EINVAL, "the gait-gradient kernel needs more shared memory than the device offers for this many spline variables");
+            k_deriv_ready<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->L, h->d_ws, h->batch, d_ready, d_dH);
+            launch_gait_lp(h->d_inst, h->L, h->d_ws, h->batch, nullptr, h->d_t0, 1.0, 1.0, d_step, d_xk, d_times, d_lpst, h->stream);
+            h->launches += 3;
+        } else {
+            CU(cudaMemsetAsync(d_ready, 0, 4 * B, h->stream));   // :344
+        }
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->h_tick_i, d_ready, 4 * 2 * B, cudaMemcpyDeviceToHost, h->stream));
+    if (mode == BGG_TICK_SOLVE_GAIT_OPT && dHdtheta) CU(cudaMemcpyAsync(h->h_tick, d_dH, 8 * nv, cudaMemcpyDeviceToHost, h->stream));
+    rc = bgg_download_results(h, status, iters, alpha, cost, z, z_stride);   // the tick's only wait for the device
+    if (rc) return rc;
+    if (deriv_ready) std::memcpy(deriv_ready, h->h_tick_i, 4 * B);
+    if (ls_best) {
+        if (mode == BGG_TICK_LINE_SEARCH) std::memcpy(ls_best, h->h_tick_i + B, 4 * B);
+        else for (size_t b = 0; b < B; ++b) ls_best[b] = -1;
+    }
+    if (mode == BGG_TICK_SOLVE_GAIT_OPT && dHdtheta) std::memcpy(dHdtheta, h->h_tick, 8 * nv);
+    if (mode == BGG_TICK_LINE_SEARCH) {   // per-candidate record (diagnostics; the stream is idle here)
+        if (ls_costs) CU(cudaMemcpy(ls_costs, h->d_tick_ls, 8 * B * K, cudaMemcpyDeviceToHost));
+        if (ls_quality) CU(cudaMemcpy(ls_quality, h->d_tick_lsq, 4 * B * K, cudaMemcpyDeviceToHost));
+    }
+    return BGG_OK;
+}
+
+int bgg_controller_get_step(bgg_handle* h, double* step, double* xk, double* new_times) {
+    if (!h || !h->batch || !h->d_tick) return fail(BGG_ESTATE, "no controller tick has run");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    const size_t nv = static_cast<size_t>(h->batch) * kNumEE * kMaxContacts;
+    if (step) CU(cudaMemcpy(step, h->d_tick, 8 * nv, cudaMemcpyDeviceToHost));
+    if (xk) CU(cudaMemcpy(xk, h->d_tick + nv, 8 * nv, cudaMemcpyDeviceToHost));
+    if (new_times) CU(cudaMemcpy(new_times, h->d_tick + 2 * nv, 8 * nv, cudaMemcpyDeviceToHost));
     return BGG_OK;
 }
 
@@ -765,7 +895,6 @@ int bgg_gait_gradient_batch(bgg_handle* h, int32_t* status, int32_t* n_contacts,
     if (!h->last_nu_max) return fail(BGG_ESTATE, "bgg_gait_gradient_batch needs a solve first");
     CU(cudaSetDevice(h->device));
     const int B = h->batch;
-    CU(cudaStreamSynchronize(h->stream));
     refresh_caps(h->caps_main);   // the main batch's own maxima of its last solve (not the line-search children's)
     if (h->caps_main.nu > 0) {
         h->last_nu_max = h->caps_main.nu;
@@ -827,17 +956,9 @@ int bgg_line_search_batch(bgg_handle* h, int K, const double* xk, const double* 
     if (!h->costs_set) return fail(BGG_ESTATE, "bgg_set_costs has not been called");
     CU(cudaSetDevice(h->device));
     const size_t B = h->batch, C = B * K, nv = B * kNumEE * kMaxContacts;
-    if (static_cast<int>(C) > h->ls_cap) {
-        CU(cudaStreamSynchronize(h->stream));
-        cudaFree(h->d_ls_inst); cudaFree(h->d_ls_ws); cudaFree(h->d_ls_state); cudaFree(h->d_ls_t0); cudaFree(h->d_ls_ee);
-        h->ls_cap = 0;
-        CU(cudaMalloc(&h->d_ls_inst, sizeof(Instance) * C));
-        CU(cudaMalloc(&h->d_ls_ws, h->L.stride * C));
-        CU(cudaMalloc(&h->d_ls_state, 8 * kNxMan * C));
-        CU(cudaMalloc(&h->d_ls_t0, 8 * C));
-        CU(cudaMalloc(&h->d_ls_ee, 8 * 12 * C));
-        CU(cudaMemsetAsync(h->d_ls_ws, 0, h->L.stride * C, h->stream));
-        h->ls_cap = static_cast<int>(C);
+    {
+        const int rc0 = ensure_ls_children(h, C);
+        if (rc0) return rc0;
     }
     int rc = bgg_upload_inputs(h, state, t0, ee_start);
     if (rc) return rc;

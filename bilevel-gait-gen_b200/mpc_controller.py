@@ -1,66 +1,84 @@
-"""Batched restatement of controller::MPCController's MPC thread (controllers/mpc_controller.cpp:286-399, MPCUpdate, and
-:518-573, GaitOpt) over bgg_b200.BatchedMPC: one tick = one call, every instance of the batch advanced by the same
-three-mode schedule the reference runs for its single robot,
+"""Binding over controller::MPCController of the C++ host layer (host/mpc_controller_b200.{h,cpp}, libmpc_b200.so): the MPC
+thread of the reference's controller (controllers/mpc_controller.cpp:286-399, MPCUpdate, and :518-573, GaitOpt) for a whole
+batch, one call per pass of its loop body -- bgg_controller_tick_batch underneath: a single launch sequence on the stream and a
+single read-back per tick.  The schedule (which of the three modes a pass takes, deriv_ready per robot, the cost reduction) is
+decided in the C++ class; this file only moves arrays."""
+import ctypes as C
+import os
 
-    run_num % gait_opt_freq == 0 and the derivative is ready   ->  GaitOptimizer::LineSearch          (:323-336)
-    (run_num + 1) % gait_opt_freq == 0                           ->  GetRealTimeUpdate, then GaitOpt    (:337-340)
-    otherwise                                                    ->  GetRealTimeUpdate                  (:341-345)
-
-with `deriv_ready` kept per instance (GaitOpt returns false when the last solve was not `Solved`, mpc.cpp:1047-1057).
-In a line-search tick the instances whose derivative is not ready get a zero step: all of their candidates are the
-unchanged contact schedule, i.e. the plain real-time update the reference would run for them.
-
-Host-side pieces of the reference loop that are not on the device path stay with the caller: the mutex-protected state
-hand-off (:304-317), AdjustForCurrentContacts (the C++ shim's MPC::AdjustForCurrentContacts), visualisation and the
-statistics log (host/mpc_b200.cpp: PrintStatLineToFile)."""
 import numpy as np
 
+import bgg_b200 as bg
+
 LS_SIZE = 10   # gait_optimizer.h: LS_SIZE
+MODES = {0: "solve", 1: "solve_and_gait_opt", 2: "line_search"}
+_dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+_lib = None
+
+
+def _shim():
+    global _lib
+    if _lib is None:
+        bg.lib()   # libbgg_b200.so first: the shim links against it
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmpc_b200.so")
+        if not os.path.exists(path):
+            raise bg.BggError(f"{path} is missing: run bilevel-gait-gen_b200/build.sh")
+        L = C.CDLL(path)
+        L.bggc_create.restype = C.c_void_p
+        L.bggc_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.bggc_destroy.argtypes = [C.c_void_p]
+        L.bggc_next_mode.argtypes = [C.c_void_p]
+        L.bggc_run_num.argtypes = [C.c_void_p]
+        L.bggc_mpc_update.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.bggc_results.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, _dp, _ip, _dp, _ip, _dp, _ip]
+        _lib = L
+    return _lib
 
 
 class MPCController:
     def __init__(self, mpc, gait_opt_freq, ls_size=LS_SIZE):
-        self.mpc = mpc
-        self.gait_opt_freq = int(gait_opt_freq)
-        self.ls_size = int(ls_size)
-        self.run_num = 0
-        B = mpc.B
-        self.deriv_ready = np.zeros(B, bool)
-        self.prev_cost = np.full(B, 1e10)     # mpc_controller.cpp:293
-        self.cost_red = np.zeros(B)
+        self.mpc, self.ls_size = mpc, int(ls_size)
+        self.L = _shim()
+        self.c = self.L.bggc_create(mpc.h, mpc.B, mpc.N, int(gait_opt_freq), self.ls_size)
+        if not self.c:
+            raise bg.BggError("MPCController: bad arguments")
         self.lp = None
+
+    def __del__(self):
+        if getattr(self, "c", None):
+            self.L.bggc_destroy(self.c)
+            self.c = None
+
+    @property
+    def run_num(self):
+        return self.L.bggc_run_num(self.c)
 
     def mode(self):
         """'line_search' | 'solve_and_gait_opt' | 'solve' for the coming tick (mpc_controller.cpp:323-345)."""
-        r, f = self.run_num, self.gait_opt_freq
-        if r % f == 0 and r > 0 and self.deriv_ready.any():
-            return "line_search"
-        if (r + 1) % f == 0 and r > 0:
-            return "solve_and_gait_opt"
-        return "solve"
+        return MODES[self.L.bggc_next_mode(self.c)]
 
     def MPCUpdate(self, state, time, ee_locations):
-        """One pass of the while-loop body for the whole batch.  Returns dict(mode, status, cost, best)."""
-        mpc, B = self.mpc, self.mpc.B
-        mode = self.mode()
-        res = dict(mode=mode, best=np.full(B, -1, np.int32))
-        if mode == "line_search":
-            step = self.lp["step"].copy()
-            step[~self.deriv_ready] = 0.0
-            ls = mpc.LineSearch(state, time, ee_locations, self.lp["xk"], step, K=self.ls_size)
-            res.update(best=ls["best"], ls_costs=ls["costs"], quality=ls["quality"])
-            self.deriv_ready[:] = False
-        else:
-            out = mpc.GetRealTimeUpdate(state, time, ee_locations)
-            res.update(status=out["status"], cost=out["cost"], alpha=out["alpha"], iters=out["iters"])
-            self.cost_red = self.prev_cost - out["cost"]
-            self.prev_cost = out["cost"].copy()
-            if mode == "solve_and_gait_opt":   # MPCController::GaitOpt, :518-573
-                g = mpc.ComputeCostFcnDerivWrtContactTimes()
-                self.lp = mpc.OptimizeContactTimes(time)
-                self.deriv_ready = g["status"] == 0
-                res.update(grad_status=g["status"], dHdtheta=g["dHdtheta"])
-            else:
-                self.deriv_ready[:] = False
-        self.run_num += 1
+        """One pass of the while-loop body for the whole batch.  Returns dict(mode, status, cost, ...)."""
+        B, K = self.mpc.B, self.ls_size
+        s = np.ascontiguousarray(state, np.float64)
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(time, np.float64), (B,)))
+        e = np.ascontiguousarray(ee_locations, np.float64)
+        m = self.L.bggc_mpc_update(self.c, s.ctypes.data_as(_dp), t.ctypes.data_as(_dp), e.ctypes.data_as(_dp))
+        if m < 0:
+            raise bg.BggError(bg.lib().bgg_last_error().decode())
+        st, it, rd, best = np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
+        al, co, cr = np.zeros(B), np.zeros(B), np.zeros(B)
+        dH, lc, lq = np.zeros((B, 4, bg.MAX_CONTACTS)), np.zeros((B, K)), np.zeros((B, K), np.int32)
+        self.L.bggc_results(self.c, st.ctypes.data_as(_ip), it.ctypes.data_as(_ip), al.ctypes.data_as(_dp), co.ctypes.data_as(_dp),
+                            cr.ctypes.data_as(_dp), rd.ctypes.data_as(_ip), dH.ctypes.data_as(_dp), best.ctypes.data_as(_ip),
+                            lc.ctypes.data_as(_dp), lq.ctypes.data_as(_ip))
+        self.deriv_ready = rd.astype(bool)
+        self.cost_red = cr
+        res = dict(mode=MODES[m], status=st, iters=it, alpha=al, cost=co, best=best)
+        if MODES[m] == "line_search":
+            res.update(ls_costs=lc, quality=lq)
+        if MODES[m] == "solve_and_gait_opt":
+            self.lp = self.mpc.controller_step()
+            counts = self.mpc.GetContactTimes()[2]
+            res.update(grad_status=np.where(rd != 0, 0, 1), dHdtheta=[np.concatenate([dH[b, e, :counts[b, e]] for e in range(4)]) for b in range(B)])
         return res

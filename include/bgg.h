@@ -206,6 +206,29 @@ int bgg_optimize_contact_times_batch(bgg_handle* h, const double* time, double t
 int bgg_line_search_batch(bgg_handle* h, int K, const double* xk, const double* step, const double* state, const double* t0,
                           const double* ee_start, int32_t* best, double* costs, int32_t* quality);
 
+/* One tick of controller::MPCController's MPC thread for the whole batch (controllers/mpc_controller.cpp:286-399, MPCUpdate, and
+ * :518-573, GaitOpt), ONE call: everything the tick needs is enqueued on the handle's stream -- no intermediate wait for the
+ * device, no allocation after the first tick -- and the call returns after a single read-back.  mode selects the branch the
+ * reference takes for its robot (:323-345):
+ *   BGG_TICK_SOLVE           GetRealTimeUpdate
+ *   BGG_TICK_SOLVE_GAIT_OPT  GetRealTimeUpdate, then GaitOpt: ComputeDerivativeTerms, the QP and contact-time partials,
+ *                            dH/dtheta, OptimizeContactTimes; the step stays on the device for the next line-search tick
+ *   BGG_TICK_LINE_SEARCH     GaitOptimizer::LineSearch over K copies along that step, SetWarmStartTrajectory(best); instances
+ *                            whose derivative was not ready (last solve not Solved) search along a zero step
+ * Outputs (any may be NULL): status / iters / alpha / cost / z as bgg_solve_batch (of the parents; unchanged by a line-search
+ * tick), deriv_ready [batch] (the reference's deriv_ready_ after this tick), dHdtheta [batch][4][BGG_MAX_CONTACTS] (GAIT_OPT
+ * ticks), ls_best [batch] (LINE_SEARCH ticks: arg-min copy, -1 when every copy was infeasible; otherwise -1), ls_costs /
+ * ls_quality [batch][K] (LINE_SEARCH ticks: cost / num_decision_vars and solve quality of every copy). */
+#define BGG_TICK_SOLVE 0
+#define BGG_TICK_SOLVE_GAIT_OPT 1
+#define BGG_TICK_LINE_SEARCH 2
+int bgg_controller_tick_batch(bgg_handle* h, int mode, int K, const double* state, const double* t0, const double* ee_start, int32_t* status,
+                              int32_t* iters, double* alpha, double* cost, double* z, int z_stride, int32_t* deriv_ready, double* dHdtheta,
+                              int32_t* ls_best, double* ls_costs, int32_t* ls_quality);
+/* The contact-time step of the last GAIT_OPT tick (GaitOptimizer::OptimizeContactTimes: step, the times it applies to and the
+ * times after a full step), each [batch][4][BGG_MAX_CONTACTS]; any pointer may be NULL. */
+int bgg_controller_get_step(bgg_handle* h, double* step, double* xk, double* new_times);
+
 /* Adjoint of the last bgg_gait_gradient_batch for one instance (parity tap): dz [n], dlam [m_ineq] (kernel row order),
  * dnu_dyn / nu_dyn [12 (N+1)] (differential and value of the dynamics-row multipliers), dnu_eq [n_eq]. */
 int bgg_get_adjoint(bgg_handle* h, int instance, double* dz, double* dlam, double* dnu_dyn, double* dnu_eq, double* nu_dyn);

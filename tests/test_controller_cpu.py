@@ -1,34 +1,33 @@
-"""Host logic of the batched MPCController schedule (bilevel-gait-gen_b200/mpc_controller.py) against the reference's
-mode rules (controllers/mpc_controller.cpp:323-345), with a stand-in for the CUDA-backed BatchedMPC -- no GPU needed."""
+"""Host logic of controller::MPCController (bilevel-gait-gen_b200/host/mpc_controller_b200.cpp, through its C entry points in
+libmpc_b200.so) against the reference's mode rules (controllers/mpc_controller.cpp:323-345) -- the schedule only, no device work
+(AdvanceWithoutDevice), so no GPU is needed."""
+import ctypes as C
 import os
-import sys
 
 import numpy as np
+import pytest
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "bilevel-gait-gen_b200"))
-import mpc_controller as mc   # noqa: E402
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "bilevel-gait-gen_b200")
+_ip = C.POINTER(C.c_int32)
 
 
-class FakeMPC:
-    def __init__(self, B, grad_ok):
-        self.B, self.grad_ok, self.calls = B, np.asarray(grad_ok), []
+def _shim():
+    so = os.path.join(PKG, "libmpc_b200.so")
+    if not os.path.exists(so):
+        pytest.skip("libmpc_b200.so is not built (python -c 'import __graft_entry__ as g; g.build()')")
+    C.CDLL(os.path.join(PKG, "libbgg_b200.so"), mode=C.RTLD_GLOBAL)
+    L = C.CDLL(so)
+    L.bggc_create.restype = C.c_void_p
+    L.bggc_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.bggc_destroy.argtypes = [C.c_void_p]
+    L.bggc_next_mode.argtypes = [C.c_void_p]
+    L.bggc_run_num.argtypes = [C.c_void_p]
+    L.bggc_advance_without_device.argtypes = [C.c_void_p, _ip]
+    return L
 
-    def GetRealTimeUpdate(self, s, t, e):
-        self.calls.append("solve")
-        return dict(status=np.zeros(self.B, np.int32), cost=np.full(self.B, 10.0 - len(self.calls)), alpha=np.ones(self.B), iters=np.ones(self.B, np.int32))
 
-    def ComputeCostFcnDerivWrtContactTimes(self):
-        self.calls.append("grad")
-        return dict(status=np.where(self.grad_ok, 0, 1).astype(np.int32), dHdtheta=[np.zeros(3)] * self.B)
-
-    def OptimizeContactTimes(self, t):
-        self.calls.append("lp")
-        return dict(step=np.ones((self.B, 4, 12)), xk=np.zeros((self.B, 4, 12)))
-
-    def LineSearch(self, s, t, e, xk, step, K=10):
-        self.calls.append("ls")
-        self.last_step = step.copy()
-        return dict(best=np.zeros(self.B, np.int32), costs=np.zeros((self.B, K)), quality=np.zeros((self.B, K), np.int32))
+MODES = {0: "solve", 1: "solve_and_gait_opt", 2: "line_search"}
 
 
 def reference_modes(freq, deriv_ok, ticks):
@@ -47,31 +46,36 @@ def reference_modes(freq, deriv_ok, ticks):
     return out
 
 
+def _run(L, freq, deriv_ok, ticks):
+    B = len(deriv_ok)
+    c = L.bggc_create(C.c_void_p(1), B, 20, freq, 10)   # the handle is not touched without device work
+    assert c
+    ok = np.asarray(deriv_ok, np.int32)
+    got = []
+    for k in range(ticks):
+        assert L.bggc_run_num(c) == k
+        nxt = L.bggc_next_mode(c)
+        assert L.bggc_advance_without_device(c, ok.ctypes.data_as(_ip)) == nxt
+        got.append(MODES[nxt])
+    L.bggc_destroy(c)
+    return got
+
+
 def test_mode_sequence_matches_the_reference_chain():
+    L = _shim()
     for freq in (2, 3, 5):
-        fake = FakeMPC(3, [True, True, True])
-        c = mc.MPCController(fake, gait_opt_freq=freq)
-        got = [c.MPCUpdate(None, 0.0, None)["mode"] for _ in range(13)]
-        assert got == reference_modes(freq, True, 13)
+        assert _run(L, freq, [1, 1, 1], 13) == reference_modes(freq, True, 13)
 
 
-def test_instances_without_a_derivative_get_a_zero_step():
-    fake = FakeMPC(3, [True, False, True])
-    c = mc.MPCController(fake, gait_opt_freq=2)
-    modes = [c.MPCUpdate(None, 0.0, None)["mode"] for _ in range(3)]
-    assert modes == ["solve", "solve_and_gait_opt", "line_search"]
-    assert np.all(fake.last_step[1] == 0.0) and np.all(fake.last_step[0] == 1.0) and np.all(fake.last_step[2] == 1.0)
-    assert not c.deriv_ready.any()
-    # nobody ready -> the tick is a plain solve, as in the reference
-    fake2 = FakeMPC(2, [False, False])
-    c2 = mc.MPCController(fake2, gait_opt_freq=2)
-    assert [c2.MPCUpdate(None, 0.0, None)["mode"] for _ in range(3)] == reference_modes(2, False, 3)
+def test_line_search_runs_when_any_robot_has_a_derivative_and_not_otherwise():
+    L = _shim()
+    assert _run(L, 2, [1, 0, 1], 7) == reference_modes(2, True, 7)        # a batch searches as soon as one robot can
+    assert _run(L, 2, [0, 0, 0], 7) == reference_modes(2, False, 7)       # no derivative anywhere: the line-search tick is a plain solve
+    assert "line_search" not in _run(L, 3, [0, 0], 10)
 
 
-def test_cost_reduction_bookkeeping():
-    fake = FakeMPC(2, [True, True])
-    c = mc.MPCController(fake, gait_opt_freq=4)
-    c.MPCUpdate(None, 0.0, None)
-    first = c.prev_cost.copy()
-    c.MPCUpdate(None, 0.0, None)
-    assert np.allclose(c.cost_red, first - c.prev_cost)   # cost_red = prev_cost - GetCost(), mpc_controller.cpp:372
+def test_bad_arguments_are_refused():
+    L = _shim()
+    assert not L.bggc_create(None, 4, 20, 3, 10)
+    assert not L.bggc_create(C.c_void_p(1), 0, 20, 3, 10)
+    assert not L.bggc_create(C.c_void_p(1), 4, 20, 0, 10)
