@@ -133,11 +133,21 @@ __global__ void k_warm_states(Instance* inst, int B, int N, const double* __rest
     for (int c = 0; c < kNxMan; ++c) inst[b].states[k][c] = src[c];
 }
 
-__global__ void k_set_contact_times(Instance* inst, int first, int count, const double* __restrict__ times, int nct) {
+// bad[0] counts the feet that were refused: the reference asserts size == GetNumContacts and throws on a negative time
+// (end_effector_splines.cpp:860-892); a foot whose knot list holds another number of contacts than the caller passes would
+// read its neighbour's times
+__global__ void k_set_contact_times(Instance* inst, int first, int count, const double* __restrict__ times, int nct, int* __restrict__ bad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count * kNumEE) return;
     const int b = first + i / kNumEE, e = i % kNumEE;
-    set_contact_times(inst[b].foot[e], times + static_cast<size_t>(i) * nct, nct);
+    const double* t = times + static_cast<size_t>(i) * nct;
+    bool ok = num_contacts(inst[b].foot[e]) == nct;
+    for (int k = 0; ok && k < nct; ++k) ok = t[k] >= 0.0 && (k == 0 || t[k] >= t[k - 1]);
+    if (!ok) {
+        atomicAdd(bad, 1);
+        return;
+    }
+    set_contact_times(inst[b].foot[e], t, nct);
 }
 
 __global__ void k_eval_splines(const Instance* inst, int b, const double* __restrict__ times, int T, double* __restrict__ force,
@@ -426,15 +436,23 @@ int bgg_set_warm_states(bgg_handle* h, const double* states, int per_node) {
 
 int bgg_set_contact_times(bgg_handle* h, int first, int count, const double* times, int nct) {
     if (!h || !times || first < 0 || count <= 0 || first + count > h->batch) return fail(BGG_EINVAL, "bad range");
+    if (nct < 2 || nct > BGG_MAX_CONTACTS) return fail(BGG_EINVAL, "num_contacts must be in [2, BGG_MAX_CONTACTS]");
     CU(cudaSetDevice(h->device));
     const size_t cnt = static_cast<size_t>(count) * kNumEE * nct;
     double* d = nullptr;
     CU(cudaMalloc(&d, 8 * cnt));
     CU(cudaMemcpyAsync(d, times, 8 * cnt, cudaMemcpyHostToDevice, h->stream));
-    k_set_contact_times<<<(count * kNumEE + 127) / 128, 128, 0, h->stream>>>(h->d_inst, first, count, d, nct);
+    int* d_bad = nullptr;
+    CU(cudaMalloc(&d_bad, sizeof(int)));
+    CU(cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream));
+    k_set_contact_times<<<(count * kNumEE + 127) / 128, 128, 0, h->stream>>>(h->d_inst, first, count, d, nct, d_bad);
     CU(cudaGetLastError());
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(d);
+    cudaFree(d_bad);
+    if (bad) return fail(BGG_EINVAL, "contact times refused for " + std::to_string(bad) + " feet: wrong count for the foot's schedule, negative or decreasing times");
     return BGG_OK;
 }
 
@@ -797,6 +815,12 @@ int bgg_get_sizes(bgg_handle* h, int b, bgg_sizes* out) {
 
 int bgg_get_dynamics(bgg_handle* h, int first, int count, double* Ad, double* Bd, double* cd, int nu_stride) {
     if (!h || !Ad || !Bd || !cd || first < 0 || count <= 0 || first + count > h->batch) return fail(BGG_EINVAL, "bad range");
+    for (int b = first; b < first + count; ++b) {
+        bgg_sizes sz;
+        const int rc = bgg_get_sizes(h, b, &sz);
+        if (rc) return rc;
+        if (sz.nu > nu_stride) return fail(BGG_EINVAL, "nu_stride is smaller than an instance's number of spline variables");
+    }
     CU(cudaSetDevice(h->device));
     const size_t N = h->P.N;
     double *dA, *dB, *dc;

@@ -8,7 +8,7 @@ oracle's tolerance.  The oracle's QP solver here is its restatement of the refer
 Solver STATUS is an integer output and is compared for equality -- no instance is skipped.  Both sides default to
 Clarabel's 1e-8 tolerances; where a test compares the MINIMISER to 1e-4 both sides are run at 1e-9 (`TIGHT`): the QP is
 flat in most spline directions (71 of 120 condensed eigenvalues below 1e-2 against 6e8), so two iterates that both meet
-1e-8 can still differ by 1e-3 in u (measured: tools/_tolcheck.py), while the cost already agrees to 1e-4.
+1e-8 can still differ by 1e-3 in u (measured: tools/diag_tolerance.py), while the cost already agrees to 1e-4.
 """
 import numpy as np
 import pytest
@@ -325,7 +325,7 @@ def test_gait_gradient_matches_oracle(cfg_name):
         # The multipliers themselves are unique only under strict complementarity: what the optimality conditions pin
         # down is A_I' lam (= -(P z + q + A_E' nu)), compared at 1e-4; lam at 1e-4 where min(lam + s) shows a clean
         # active set, 1e-2 on a weakly active one (measured 1.9e-3 on instance 1 of the N = 50 batch, whose gradient
-        # still agrees to 2e-7: tools/_graddiag.py)
+        # still agrees to 2e-7: tools/diag_gradient.py)
         qp = o.qp()
         Ain = qp["A"][np.flatnonzero(~qp["is_eq"])]
         assert _rel(Ain.T @ sol["lam"][order], Ain.T @ terms["lam"]) < 1e-4
