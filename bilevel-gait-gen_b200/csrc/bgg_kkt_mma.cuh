@@ -143,10 +143,6 @@ static __device__ __noinline__ void kkt_dense_mma(const KktDenseArgs a, const do
             if (i >= nu) acc[u] = make_double2(i == j ? 1.0 : 0.0, i == j + 1 ? 1.0 : 0.0);
             else if (j >= nu) acc[u] = make_double2(0.0, 0.0);
             if (u >= nslot) acc[u] = make_double2(0.0, 0.0);
-            else if (ib == jb && i < nu) {   // + eps I
-                if (g == 2 * t) acc[u].x += a.eps;
-                else if (g == 2 * t + 1) acc[u].y += a.eps;
-            }
         }
         const int iA = 8 * rowA + g, iB = 8 * rowB + g;
         // position variable i: foot, coordinate, node range and local index (ColInfo, 8 bytes)
@@ -410,6 +406,9 @@ __device__ inline void kkt_assemble_mma(const KktMma& v) {
         for (int s = item.mid; s < item.hi; ++s) acc += mcp[5 * s + item.cp] * v.smp[s].w[item.a2] * v.smp[s].w[item.b2];
         v.K[item.koff] += acc;
     }
+    __syncthreads();
+    // + eps I (static regularisation of the (1,1) block): after the entry tables, which also write the diagonal
+    for (int i = tid; i < nu; i += nth) v.K[chol::at(i, i)] += v.eps;
     __syncthreads();
     KPROF(4);
 }
