@@ -305,7 +305,7 @@ int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) 
     for (auto& e : h->ev) cudaEventCreate(&e);
     for (auto& e : h->user_ev) cudaEventCreate(&e);
     for (bgg_handle::Caps* c : {&h->caps_main, &h->caps_ls}) {
-        cudaMalloc(&c->d_max, 2 * sizeof(int));
+        cudaMalloc(&c->d_max, 3 * sizeof(int));
         cudaMallocHost(&c->h_max, 2 * sizeof(int));
         cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming);
     }
@@ -493,17 +493,18 @@ static int solve_pipeline(bgg_handle* h, bgg_handle::Caps& caps, Instance* inst,
     CU(cudaEventRecord(caps.ev, h->stream));
     caps.pending = true;
     if (profile) cudaEventRecord(h->ev[1], h->stream);
-    launch_condense(h->P, h->L, ws, B, nu_cap, 0, h->stream);
+    launch_condense(h->P, h->L, ws, B, nu_cap, 0, nullptr, h->stream);
     if (profile) cudaEventRecord(h->ev[2], h->stream);
-    launch_ipm(h->P, h->L, ws, B, nu_cap, ns_cap, 0, h->stream);
+    launch_ipm(h->P, h->L, ws, B, nu_cap, ns_cap, 0, nullptr, h->stream);
     if (profile) cudaEventRecord(h->ev[3], h->stream);
-    launch_finish(h->P, inst, h->L, ws, B, 0, h->stream);
+    launch_finish(h->P, inst, h->L, ws, B, 0, nullptr, h->stream);
     if (profile) cudaEventRecord(h->ev[4], h->stream);
     h->launches += 5;
     if (nu_cap < worst_nu || ns_cap < worst_ns) {   // second pass: the instances that outgrew the caps (CTAs of all others return at once)
-        launch_condense(h->P, h->L, ws, B, worst_nu, 2, h->stream);
-        launch_ipm(h->P, h->L, ws, B, worst_nu, worst_ns, 2, h->stream);
-        launch_finish(h->P, inst, h->L, ws, B, 2, h->stream);
+        const int* gate = caps.d_max + 2;   // how many instances k_batch_max marked: zero ends every CTA before it touches its workspace
+        launch_condense(h->P, h->L, ws, B, worst_nu, 2, gate, h->stream);
+        launch_ipm(h->P, h->L, ws, B, worst_nu, worst_ns, 2, gate, h->stream);
+        launch_finish(h->P, inst, h->L, ws, B, 2, gate, h->stream);
         h->launches += 3;
     }
     if (&caps == &h->caps_main) {

@@ -238,7 +238,9 @@ size_t ipm_smem_bytes(const WsLayout& L) {   // worst case for the configured ca
     return ipm_smem_core(L.N, L.max_nu, L.max_rows, kMaxSamples);
 }
 
-__global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi, int cap_nu, int cap_rows, int want) {
+__global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi, int cap_nu, int cap_rows, int want,
+                                                  const int* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
     WsHeader* Hd = reinterpret_cast<WsHeader*>(ws + L.hdr);
@@ -508,13 +510,15 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             uHu = r8[0];
             const double gu = r8[1];
             double ey = 0, n_re = 0;
+            double yn = 0;
             for (int r = 0; r < neq; ++r) {
                 ey += s_eq[r].rhs * S.nueq[r];
                 n_re = fmax(n_re, fabs(S.re[r]));
+                yn = fmax(yn, fabs(S.nueq[r]));
             }
             bz = r8[2] + ey;
             aty_n = r8[4];
-            zn = r8[7];
+            zn = fmax(r8[7], yn);   // max(1, |z|, |y|) over the duals this form keeps (the dynamics multipliers are eliminated)
             rt = kap + gu + bz + uHu / tau;
             mu = (r8[3] + tau * kap) / (m_act + 1);
             pc = (0.5 * uHu / tau + gu) / tau;
@@ -765,7 +769,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     (void)gscale;
 }
 
-void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, cudaStream_t stream) {
+void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, const int* gate, cudaStream_t stream) {
     const IpmCaps c = ipm_caps(L, nu_max, ns_max);
     const size_t smem = ipm_smem_for(L, c);
     // the opt-in is per device and context: set on every launch (a second handle on another GPU, or another host thread,
@@ -776,7 +780,7 @@ void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max,
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, k_ipm, 256, smem);
         fprintf(stderr, "k_ipm: dynamic smem %zu B, caps nu %d rows %d, stage_phi %d, resident CTAs per SM %d\n", smem, c.nu, c.rows, c.stage_phi, nblk);
     }
-    k_ipm<<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want);
+    k_ipm<<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want, gate);
 }
 
 }  // namespace bgg
