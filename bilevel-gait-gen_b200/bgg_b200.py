@@ -81,6 +81,9 @@ def lib():
         L.bgg_download_results.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, _dp, C.c_int]
         L.bgg_synchronize.argtypes = [C.c_void_p]
         L.bgg_advance_plant.argtypes = [C.c_void_p, C.c_double]
+        L.bgg_set_kinematics.argtypes = [C.c_void_p, _dp]
+        L.bgg_ik_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip, _ip]
+        L.bgg_targets_from_traj_batch.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _ip]
         L.bgg_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.bgg_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.bgg_kernel_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -110,7 +113,7 @@ def exported_symbols():
     """Names include/bgg.h declares; used by the CPU-side ABI test."""
     return ["bgg_last_error", "bgg_device_count", "bgg_measure_fp64_peak", "bgg_create", "bgg_destroy", "bgg_set_costs", "bgg_batch_reset",
             "bgg_set_warm_states", "bgg_set_contact_times", "bgg_solve_batch", "bgg_qp_solve_batch", "bgg_controller_tick_batch", "bgg_controller_get_step", "bgg_upload_inputs", "bgg_solve_resident",
-            "bgg_download_results", "bgg_synchronize", "bgg_advance_plant", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count", "bgg_event_record", "bgg_event_elapsed_ms",
+            "bgg_download_results", "bgg_synchronize", "bgg_advance_plant", "bgg_set_kinematics", "bgg_ik_batch", "bgg_targets_from_traj_batch", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count", "bgg_event_record", "bgg_event_elapsed_ms",
             "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_export_qp_csc", "bgg_gait_gradient_batch", "bgg_optimize_contact_times_batch",
             "bgg_line_search_batch", "bgg_get_adjoint",
             "bgg_get_contact_times", "bgg_set_solution", "bgg_get_solution", "bgg_instance_bytes",
@@ -289,6 +292,34 @@ class BatchedMPC:
         if z_out is not None:
             out["z"] = z_out
         return out
+
+    # ---- joint-space targets
+    def SetKinematics(self, robot):
+        """robot["legs"]: hip / thigh / calf joint placements + foot frame + joint axes per leg (tests/golden/a1_robot_consts.json)."""
+        flat = []
+        for leg in robot["legs"]:
+            flat += np.asarray(leg["t"], float).ravel().tolist() + np.asarray(leg["R"], float).ravel().tolist() + np.asarray(leg["axis"], float).ravel().tolist()
+        k = np.ascontiguousarray(flat, np.float64)
+        assert k.size == 228
+        self._chk(self.L.bgg_set_kinematics(self.h, _d(k)))
+
+    def InverseKinematics(self, state, ee_des, joint_guess):
+        """SingleRigidBodyModel::InverseKinematics for a stack of problems: state [n][13], ee_des [n][4][3], joint_guess [n][12]."""
+        st = np.ascontiguousarray(state, np.float64).reshape(-1, 13)
+        n = st.shape[0]
+        ee = np.ascontiguousarray(ee_des, np.float64).reshape(n, 12)
+        g = np.ascontiguousarray(joint_guess, np.float64).reshape(n, 12)
+        q, status, iters = np.zeros((n, 19)), np.zeros(n, np.int32), np.zeros((n, 4), np.int32)
+        self._chk(self.L.bgg_ik_batch(self.h, n, _d(st), _d(ee), _d(g), _d(q), _i(status), _i(iters)))
+        return dict(q=q, status=status, iters=iters)
+
+    def GetTargetsFromTraj(self, time, q_des):
+        """MPCController::GetTargetsFromTraj for the whole batch: time scalar or [B], q_des [B][19] (running IK guess)."""
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(time, np.float64), (self.B,)))
+        q = np.ascontiguousarray(q_des, np.float64).reshape(self.B, 19).copy()
+        v, f, status = np.zeros((self.B, 18)), np.zeros((self.B, 4, 3)), np.zeros(self.B, np.int32)
+        self._chk(self.L.bgg_targets_from_traj_batch(self.h, _d(t), _d(q), _d(v), _d(f), _i(status)))
+        return dict(q_des=q, v_des=v, force_des=f, status=status)
 
     def advance_plant(self, dt):
         self._chk(self.L.bgg_advance_plant(self.h, dt))

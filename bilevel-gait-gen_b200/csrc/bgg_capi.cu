@@ -27,6 +27,8 @@ static int fail(int code, const std::string& msg) {
 struct bgg_handle {
     Params P{};
     WsLayout L{};
+    RobotKin kin{};
+    bool kin_set = false;
     int device = 0;
     int batch = 0;
     cudaStream_t stream = nullptr;
@@ -529,6 +531,68 @@ int bgg_advance_plant(bgg_handle* h, double dt) {
     k_plant_step<<<(tot + 127) / 128, 128, 0, h->stream>>>(h->d_inst, h->batch, dt, h->d_state, h->d_t0, h->d_ee);
     h->launches += 1;
     CU(cudaGetLastError());
+    return BGG_OK;
+}
+
+int bgg_set_kinematics(bgg_handle* h, const bgg_kinematics* kin) {
+    if (!h || !kin) return fail(BGG_EINVAL, "null argument");
+    static_assert(sizeof(bgg_kinematics) == sizeof(RobotKin), "bgg_kinematics and RobotKin share one layout");
+    std::memcpy(&h->kin, kin, sizeof h->kin);
+    for (int e = 0; e < kNumEE; ++e)
+        for (int j = 0; j < 3; ++j) {
+            const double* a = h->kin.leg[e].axis[j];
+            const double n = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+            if (!(std::fabs(n - 1.0) < 1e-9)) return fail(BGG_EINVAL, "joint axes must be unit vectors");
+        }
+    h->kin_set = true;
+    return BGG_OK;
+}
+
+int bgg_ik_batch(bgg_handle* h, int count, const double* state, const double* ee_des, const double* joint_guess, double* q, int32_t* status,
+                 int32_t* iters) {
+    if (!h || count <= 0 || !state || !ee_des || !joint_guess || !q || !status) return fail(BGG_EINVAL, "bad argument");
+    if (!h->kin_set) return fail(BGG_ESTATE, "bgg_set_kinematics has not been called");
+    CU(cudaSetDevice(h->device));
+    DevPool pool;
+    const size_t n = static_cast<size_t>(count);
+    double *ds = pool.get<double>(13 * n), *de = pool.get<double>(12 * n), *dg = pool.get<double>(12 * n), *dq = pool.get<double>(19 * n);
+    int *dst = pool.get<int>(n), *dit = pool.get<int>(4 * n);
+    if (!ds || !de || !dg || !dq || !dst || !dit) return fail(BGG_ECUDA, "out of device memory");
+    CU(cudaMemcpyAsync(ds, state, 8 * 13 * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(de, ee_des, 8 * 12 * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dg, joint_guess, 8 * 12 * n, cudaMemcpyHostToDevice, h->stream));
+    launch_ik(h->kin, count, ds, de, dg, dq, dst, dit, h->stream);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(q, dq, 8 * 19 * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(status, dst, 4 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (iters) CU(cudaMemcpyAsync(iters, dit, 4 * 4 * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BGG_OK;
+}
+
+int bgg_targets_from_traj_batch(bgg_handle* h, const double* time, double* q_des, double* v_des, double* force_des, int32_t* status) {
+    if (!h || !h->batch) return fail(BGG_EINVAL, "no batch");
+    if (!time || !q_des || !v_des || !force_des || !status) return fail(BGG_EINVAL, "null argument");
+    if (!h->kin_set) return fail(BGG_ESTATE, "bgg_set_kinematics has not been called");
+    CU(cudaSetDevice(h->device));
+    DevPool pool;
+    const size_t n = static_cast<size_t>(h->batch);
+    double *dt = pool.get<double>(n), *dq = pool.get<double>(19 * n), *dv = pool.get<double>(18 * n), *df = pool.get<double>(12 * n);
+    int* dst = pool.get<int>(n);
+    if (!dt || !dq || !dv || !df || !dst) return fail(BGG_ECUDA, "out of device memory");
+    CU(cudaMemcpyAsync(dt, time, 8 * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dq, q_des, 8 * 19 * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(dv, 0, 8 * 18 * n, h->stream));
+    CU(cudaMemsetAsync(df, 0, 8 * 12 * n, h->stream));
+    launch_targets_from_traj(h->P, h->kin, h->d_inst, h->batch, dt, dq, dv, df, dst, h->stream);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(q_des, dq, 8 * 19 * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(v_des, dv, 8 * 18 * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(force_des, df, 8 * 12 * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(status, dst, 4 * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return BGG_OK;
 }
 

@@ -66,6 +66,11 @@ __device__ __forceinline__ void block_reduce_multi(double (&v)[NS + NM], double*
 // kernel launchers (each is asynchronous on `stream`)
 void launch_prepare(const Params& P, Instance* inst, const double* state, const double* t0, const double* ee_start,
                     const WsLayout& L, char* ws, int B, cudaStream_t stream);
+// bgg_ik.cu: SingleRigidBodyModel::InverseKinematics / MPCController::GetTargetsFromTraj, one thread per problem
+void launch_ik(const RobotKin& rk, int count, const double* state, const double* ee_des, const double* joint_guess, double* q, int* status,
+               int* iters, cudaStream_t stream);
+void launch_targets_from_traj(const Params& P, const RobotKin& rk, const Instance* inst, int B, const double* time, double* q_des, double* v_des,
+                              double* force_des, int* status, cudaStream_t stream);
 void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int want, const int* gate, cudaStream_t stream);
 void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, const int* gate, cudaStream_t stream);
 // max over the batch of (nu, n_samples) after launch_prepare, written to out[0..1] (device); instances larger than the caps

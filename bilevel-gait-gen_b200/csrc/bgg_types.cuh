@@ -55,6 +55,16 @@ struct Instance {
     int32_t pad_;
 };
 
+// Leg chains for the inverse kinematics (bgg_kinematics of include/bgg.h, same layout)
+struct LegChain {
+    double t[4][3];      // hip / thigh / calf joint and foot frame, each placed in the frame of the joint before it
+    double R[4][9];
+    double axis[3][3];
+};
+struct RobotKin {
+    LegChain leg[kNumEE];
+};
+
 // Handle-wide constants (MPCInfo, mpc.h:39-62, plus what the reference reads out of pinocchio and its cost setters).
 struct Params {
     int32_t N;                 // num_nodes

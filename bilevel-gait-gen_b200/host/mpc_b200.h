@@ -98,6 +98,7 @@ struct MPCInfo {   // mpc.h:39-62
 // (single_rigid_body_model.cpp:33-37), hip offsets incl. the hard-coded shifts (:258-308).
 bgg_robot RobotConstsFromURDF(const std::string& urdf_path);   // nominal A1 joint angles (apps/a1_configuration.yaml:init_config)
 bgg_robot RobotConstsFromURDF(const std::string& urdf_path, const std::map<std::string, double>& joint_cfg);
+bgg_kinematics LegKinematicsFromURDF(const std::string& urdf_path);   // leg chains for the inverse kinematics
 
 // mpc::Trajectory (mpc/include/trajectory.h): a value type.  Here it is the instance POD fetched from the device plus
 // the host build of the spline code the kernels use (csrc/bgg_spline.cuh).

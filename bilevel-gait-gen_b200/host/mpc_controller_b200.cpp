@@ -12,8 +12,18 @@ MPCController::MPCController(bgg_handle* mpc, int batch, int num_nodes, int gait
       status_(batch, BGG_UNSOLVED), iters_(batch, 0), deriv_ready_(batch, 0), ls_best_(batch, -1),
       ls_quality_(static_cast<size_t>(batch) * ls_size, 0), alpha_(batch, 0.0), cost_(batch, 0.0), prev_cost_(batch, 1e10),   // :293
       cost_red_(batch, 0.0), dHdtheta_(static_cast<size_t>(batch) * BGG_NUM_EE * BGG_MAX_CONTACTS, 0.0),
-      ls_costs_(static_cast<size_t>(batch) * ls_size, 0.0), z_(static_cast<size_t>(batch) * z_stride_, 0.0) {
+      ls_costs_(static_cast<size_t>(batch) * ls_size, 0.0), z_(static_cast<size_t>(batch) * z_stride_, 0.0),
+      q_des_(static_cast<size_t>(batch) * BGG_NQ, 0.0), v_des_(static_cast<size_t>(batch) * BGG_NV, 0.0),
+      force_des_(static_cast<size_t>(batch) * BGG_NUM_EE * 3, 0.0), target_status_(batch, 0) {
     if (!mpc || batch <= 0 || gait_opt_freq <= 0 || ls_size <= 0) throw std::runtime_error("MPCController: bad arguments");
+    for (int b = 0; b < batch; ++b) q_des_[static_cast<size_t>(b) * BGG_NQ + 6] = 1.0;   // pinocchio::neutral: identity quaternion
+}
+
+void MPCController::SetInitialConfig(const double* q) { std::copy(q, q + q_des_.size(), q_des_.begin()); }
+
+int MPCController::GetTargetsFromTraj(const double* time) {
+    // the device call overwrites q_des only where the robot's two IK solves converged
+    return bgg_targets_from_traj_batch(mpc_, time, q_des_.data(), v_des_.data(), force_des_.data(), target_status_.data());
 }
 
 MPCController::Mode MPCController::NextMode() const {
@@ -68,6 +78,17 @@ int bggc_mpc_update(void* c, const double* state, const double* time, const doub
     }
 }
 int bggc_advance_without_device(void* c, const int32_t* deriv_ready) { return static_cast<MPCController*>(c)->AdvanceWithoutDevice(deriv_ready); }
+void bggc_set_initial_config(void* c, const double* q) { static_cast<MPCController*>(c)->SetInitialConfig(q); }
+int bggc_targets_from_traj(void* cv, const double* time, double* q_des, double* v_des, double* force_des, int32_t* status) {
+    MPCController* c = static_cast<MPCController*>(cv);
+    const int rc = c->GetTargetsFromTraj(time);
+    if (rc != BGG_OK) return rc;
+    if (q_des) std::copy(c->q_des().begin(), c->q_des().end(), q_des);
+    if (v_des) std::copy(c->v_des().begin(), c->v_des().end(), v_des);
+    if (force_des) std::copy(c->force_des().begin(), c->force_des().end(), force_des);
+    if (status) std::copy(c->target_status().begin(), c->target_status().end(), status);
+    return BGG_OK;
+}
 void bggc_results(void* cv, int32_t* status, int32_t* iters, double* alpha, double* cost, double* cost_red, int32_t* deriv_ready,
                   double* dHdtheta, int32_t* ls_best, double* ls_costs, int32_t* ls_quality) {
     const MPCController& c = *static_cast<MPCController*>(cv);

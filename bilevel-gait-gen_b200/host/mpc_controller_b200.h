@@ -7,8 +7,9 @@
 //     otherwise                                                 ->  GetRealTimeUpdate                  (:341-345)
 //
 // deriv_ready is kept per robot (GaitOpt returns false when the last solve was not Solved, mpc.cpp:1047-1057).  What the
-// reference's class does around this loop -- the std::thread and its five mutexes, the whole-body QPControl, the inverse
-// kinematics of GetTargetsFromTraj, visualisation -- is not on the path and stays with the caller.
+// GetTargetsFromTraj (:414-511: two inverse-kinematics solves and a finite difference per robot) is the batch call
+// bgg_targets_from_traj_batch.  What the reference's class does around this -- the std::thread and its five mutexes, the
+// whole-body QPControl, visualisation -- is not on the path and stays with the caller.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -35,6 +36,17 @@ public:
     // is what its GaitOpt would have reported
     Mode AdvanceWithoutDevice(const int32_t* deriv_ready);
 
+    // q_des_ before the first targets call: the robot's initial configuration (mpc_controller.cpp:50-52), [batch][BGG_NQ]
+    void SetInitialConfig(const double* q);
+    // MPCController::GetTargetsFromTraj (:414-511) for every robot at `time` [batch], from the trajectories of the last pass.
+    // Needs bgg_set_kinematics on the handle.  Returns BGG_OK or a negative code; per-robot outcome in target_status()
+    // (0; 1 "IK did not converge."; 2 "bad interp."; 3 time beyond the trajectory) -- q_des_ of a robot that failed is kept.
+    int GetTargetsFromTraj(const double* time);
+    const std::vector<double>& q_des() const { return q_des_; }                    // [batch][BGG_NQ]
+    const std::vector<double>& v_des() const { return v_des_; }                    // [batch][BGG_NV]
+    const std::vector<double>& force_des() const { return force_des_; }            // [batch][4][3]
+    const std::vector<int32_t>& target_status() const { return target_status_; }
+
     int run_num() const { return run_num_; }
     const std::vector<int32_t>& status() const { return status_; }
     const std::vector<int32_t>& iters() const { return iters_; }
@@ -55,6 +67,8 @@ private:
     int batch_, gait_opt_freq_, ls_size_, z_stride_, run_num_ = 0;
     std::vector<int32_t> status_, iters_, deriv_ready_, ls_best_, ls_quality_;
     std::vector<double> alpha_, cost_, prev_cost_, cost_red_, dHdtheta_, ls_costs_, z_;
+    std::vector<double> q_des_, v_des_, force_des_;
+    std::vector<int32_t> target_status_;
 };
 
 }  // namespace controller
@@ -69,6 +83,9 @@ int bggc_run_num(void* c);
 int bggc_mpc_update(void* c, const double* state, const double* time, const double* ee_locations);
 // copies of the last pass's results; any pointer may be NULL
 int bggc_advance_without_device(void* c, const int32_t* deriv_ready);
+void bggc_set_initial_config(void* c, const double* q);
+// q_des / v_des / force_des / status: copies of the outcome, any may be NULL
+int bggc_targets_from_traj(void* c, const double* time, double* q_des, double* v_des, double* force_des, int32_t* status);
 void bggc_results(void* c, int32_t* status, int32_t* iters, double* alpha, double* cost, double* cost_red, int32_t* deriv_ready,
                   double* dHdtheta, int32_t* ls_best, double* ls_costs, int32_t* ls_quality);
 }

@@ -141,7 +141,8 @@ struct Body {
 
 }  // namespace
 
-bgg_robot RobotConstsFromURDF(const std::string& urdf_path, const std::map<std::string, double>& joint_cfg) {
+namespace {
+void ParseURDF(const std::string& urdf_path, std::map<std::string, Link>& links, std::vector<Joint>& joints) {
     std::FILE* f = std::fopen(urdf_path.c_str(), "rb");
     if (!f) throw std::runtime_error("cannot open URDF " + urdf_path);
     std::string s;
@@ -149,8 +150,6 @@ bgg_robot RobotConstsFromURDF(const std::string& urdf_path, const std::map<std::
     size_t got;
     while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) s.append(buf, got);
     std::fclose(f);
-    std::map<std::string, Link> links;
-    std::vector<Joint> joints;
     size_t pos = 0;
     Tag t;
     std::vector<std::string> stack;
@@ -216,6 +215,13 @@ bgg_robot RobotConstsFromURDF(const std::string& urdf_path, const std::map<std::
         }
         if (!t.self_closing) stack.push_back(t.name);
     }
+}
+}  // namespace
+
+bgg_robot RobotConstsFromURDF(const std::string& urdf_path, const std::map<std::string, double>& joint_cfg) {
+    std::map<std::string, Link> links;
+    std::vector<Joint> joints;
+    ParseURDF(urdf_path, links, joints);
     // the inertial origin's rotation may come after <inertia> in the file: the A1 URDF lists origin first; nothing to fix up
     std::map<std::string, std::vector<const Joint*>> children;
     std::map<std::string, bool> is_child;
@@ -325,9 +331,69 @@ bgg_robot RobotConstsFromURDF(const std::string& urdf_path) {
     return RobotConstsFromURDF(urdf_path, cfg);
 }
 
+// Leg chains for the inverse kinematics (single_rigid_body_model.cpp:314-455): every placement relative to the movable joint before it,
+// fixed joints in between merged the way pinocchio's URDF parser does.
+bgg_kinematics LegKinematicsFromURDF(const std::string& urdf_path) {
+    std::map<std::string, Link> links;
+    std::vector<Joint> joints;
+    ParseURDF(urdf_path, links, joints);
+    std::map<std::string, const Joint*> by_child, by_name;
+    std::map<std::string, bool> is_child;
+    for (const Joint& j : joints) {
+        by_child[j.child] = &j;
+        by_name[j.name] = &j;
+        is_child[j.child] = true;
+    }
+    std::string root;
+    for (const auto& kv : links)
+        if (!is_child.count(kv.first)) root = kv.first;
+    bgg_kinematics kin{};
+    const char* legs[4] = {"FL", "FR", "RL", "RR"};
+    const char* chain[4] = {"_hip_joint", "_thigh_joint", "_calf_joint", "_foot_fixed"};
+    for (int e = 0; e < 4; ++e) {
+        std::string ancestor = root;
+        for (int k = 0; k < 4; ++k) {
+            const std::string name = std::string(legs[e]) + chain[k];
+            const auto it = by_name.find(name);
+            if (it == by_name.end()) throw std::runtime_error("URDF has no joint " + name);
+            const Joint* j = it->second;
+            double t[3] = {j->xyz[0], j->xyz[1], j->xyz[2]};
+            M3 R = j->R;
+            std::string link = j->parent;
+            while (link != ancestor) {
+                const auto up = by_child.find(link);
+                if (up == by_child.end() || up->second->type != "fixed") throw std::runtime_error("URDF: " + name + " does not hang off " + ancestor + " through fixed joints");
+                double rt[3];
+                MulV(up->second->R, t, rt);
+                for (int i = 0; i < 3; ++i) t[i] = up->second->xyz[i] + rt[i];
+                R = Mul(up->second->R, R);
+                link = up->second->parent;
+            }
+            for (int i = 0; i < 3; ++i) kin.leg[e].t[k][i] = t[i];
+            for (int i = 0; i < 3; ++i)
+                for (int c = 0; c < 3; ++c) kin.leg[e].R[k][3 * i + c] = R.a[i][c];
+            if (k < 3) {
+                const double n = std::sqrt(j->axis[0] * j->axis[0] + j->axis[1] * j->axis[1] + j->axis[2] * j->axis[2]);
+                for (int i = 0; i < 3; ++i) kin.leg[e].axis[k][i] = j->axis[i] / n;
+            }
+            ancestor = j->child;
+        }
+    }
+    return kin;
+}
+
 }  // namespace mpc
 
 // C entry point for bindings / tests: 0 on success, -1 on failure (message on stderr)
+extern "C" int bgg_host_leg_kinematics_from_urdf(const char* urdf_path, bgg_kinematics* out) {
+    try {
+        *out = mpc::LegKinematicsFromURDF(urdf_path);
+        return 0;
+    } catch (...) {
+        return -1;
+    }
+}
+
 extern "C" int bgg_host_robot_consts_from_urdf(const char* urdf_path, bgg_robot* out) {
     try {
         *out = mpc::RobotConstsFromURDF(urdf_path);

@@ -30,6 +30,8 @@ def _shim():
         L.bggc_next_mode.argtypes = [C.c_void_p]
         L.bggc_run_num.argtypes = [C.c_void_p]
         L.bggc_mpc_update.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.bggc_set_initial_config.argtypes = [C.c_void_p, _dp]
+        L.bggc_targets_from_traj.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _ip]
         L.bggc_results.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, _dp, _ip, _dp, _ip, _dp, _ip]
         _lib = L
     return _lib
@@ -48,6 +50,21 @@ class MPCController:
         if getattr(self, "c", None):
             self.L.bggc_destroy(self.c)
             self.c = None
+
+    def SetInitialConfig(self, q):
+        """q_des_ before the first targets call (mpc_controller.cpp:50-52): [B][19]."""
+        q = np.ascontiguousarray(q, np.float64).reshape(self.mpc.B, 19)
+        self.L.bggc_set_initial_config(self.c, q.ctypes.data_as(_dp))
+
+    def GetTargetsFromTraj(self, time):
+        """MPCController::GetTargetsFromTraj (mpc_controller.cpp:414-511) for the whole batch; needs mpc.SetKinematics()."""
+        B = self.mpc.B
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(time, np.float64), (B,)))
+        q, v, f, st = np.zeros((B, 19)), np.zeros((B, 18)), np.zeros((B, 4, 3)), np.zeros(B, np.int32)
+        if self.L.bggc_targets_from_traj(self.c, t.ctypes.data_as(_dp), q.ctypes.data_as(_dp), v.ctypes.data_as(_dp), f.ctypes.data_as(_dp),
+                                         st.ctypes.data_as(_ip)) != 0:
+            raise bg.BggError(bg.lib().bgg_last_error().decode())
+        return dict(q_des=q, v_des=v, force_des=f, status=st)
 
     @property
     def run_num(self):

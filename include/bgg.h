@@ -70,6 +70,21 @@ typedef struct bgg_robot {
     double gravity[3];
 } bgg_robot;
 
+/* Leg chains for the inverse kinematics (what mpc/models/single_rigid_body_model.cpp:314-455 reaches through pinocchio's
+ * forwardKinematics / computeFrameJacobian): hip, thigh, calf revolute joint and the foot frame of each leg, every placement
+ * given in the frame of the movable joint before it (the hip in the floating base), rotations row-major, axes in the joint frame.
+ * Leg order FL, FR, RL, RR = pinocchio's joint order for a1.urdf: q = [p, quat xyzw, 4 x (hip, thigh, calf)]. */
+typedef struct bgg_leg_chain {
+    double t[4][3];
+    double R[4][9];
+    double axis[3][3];
+} bgg_leg_chain;
+typedef struct bgg_kinematics {
+    bgg_leg_chain leg[BGG_NUM_EE];
+} bgg_kinematics;
+#define BGG_NQ 19
+#define BGG_NV 18
+
 typedef struct bgg_handle bgg_handle;
 
 const char* bgg_last_error(void);
@@ -131,6 +146,18 @@ int bgg_synchronize(bgg_handle* h);
  * the solved trajectory (the plant of apps/mpc_demo.cpp:185 and test/gait_opt_playground.cpp:128), t0 += dt, measured
  * feet = the trajectory's feet at the new time.  Follow with bgg_solve_resident. */
 int bgg_advance_plant(bgg_handle* h, double dt);
+
+/* ---- joint-space targets */
+int bgg_set_kinematics(bgg_handle* h, const bgg_kinematics* kin);
+/* SingleRigidBodyModel::InverseKinematics (single_rigid_body_model.cpp:314-425) for `count` independent problems: state [count][13]
+ * (manifold SRB state), ee_des [count][4][3], joint_guess [count][12] (the tail of state_guess) -> q [count][19].
+ * status: 0, or 1 where the reference throws "IK did not converge."; iters [count][4] (may be NULL): iterations per foot. */
+int bgg_ik_batch(bgg_handle* h, int count, const double* state, const double* ee_des, const double* joint_guess, double* q, int32_t* status,
+                 int32_t* iters);
+/* MPCController::GetTargetsFromTraj (controllers/mpc_controller.cpp:414-511) for every instance, on the trajectories resident on
+ * the device: time [batch]; q_des [batch][19] is q_des_ (in: the running IK guess, out: the configuration target); v_des [batch][18];
+ * force_des [batch][4][3].  status: 0; 1 "IK did not converge."; 2 "bad interp."; 3 time beyond the trajectory. */
+int bgg_targets_from_traj_batch(bgg_handle* h, const double* time, double* q_des, double* v_des, double* force_des, int32_t* status);
 /* device milliseconds of the four kernels of the last bgg_solve_resident (prepare, condense, ipm, finish),
  * measured with CUDA events on the handle's stream; enable with bgg_set_profiling(h, 1). */
 int bgg_set_profiling(bgg_handle* h, int enable);

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "foot_spline.hpp"
+#include "leg_kinematics.hpp"
 #include "qp_admm.hpp"
 #include "qp_ipm.hpp"
 #include "srb_mpc.hpp"
@@ -472,5 +473,53 @@ double orc_mpc_merit(void* h, const double* z) {
 // quaternion helpers
 void orc_quat_log3(const double* q, double* out) { QuatLog3(q, out); }
 void orc_quat_exp3(const double* v, double* out) { QuatExp3(v, out); }
+
+// ---- inverse kinematics (leg_kinematics.cpp).  `kin_flat`: 4 legs x (t[4][3], R[4][9], axis[3][3]) = 228 doubles
+static kin::RobotKin Kin(const double* kin_flat) {
+    kin::RobotKin rk;
+    static_assert(sizeof(kin::RobotKin) == 228 * sizeof(double), "RobotKin is 228 packed doubles");
+    std::memcpy(&rk, kin_flat, sizeof rk);
+    return rk;
+}
+void orc_kin_exp6(const double* nu, double* R, double* p) {
+    kin::Se3 M;
+    kin::Exp6(nu, M);
+    std::memcpy(R, M.R, sizeof M.R);
+    std::memcpy(p, M.p, sizeof M.p);
+}
+void orc_kin_log6(const double* R, const double* p, double* out) {
+    kin::Se3 M;
+    std::memcpy(M.R, R, sizeof M.R);
+    std::memcpy(M.p, p, sizeof M.p);
+    kin::Log6(M, out);
+}
+void orc_kin_jlog6(const double* R, const double* p, double* J) {
+    kin::Se3 M;
+    std::memcpy(M.R, R, sizeof M.R);
+    std::memcpy(M.p, p, sizeof M.p);
+    kin::Jlog6(M, J);
+}
+// feet: world positions [4][3] and rotations [4][9]; J: the 6 x 18 LOCAL foot-frame Jacobian of foot `ee`
+void orc_kin_fk(const double* kin_flat, const double* q, int ee, double* feet_p, double* feet_R, double* J) {
+    const kin::RobotKin rk = Kin(kin_flat);
+    kin::Se3 joints[13], feet[4];
+    kin::ForwardKinematics(rk, q, joints, feet);
+    for (int e = 0; e < 4; e++) {
+        std::memcpy(feet_p + 3 * e, feet[e].p, sizeof feet[e].p);
+        std::memcpy(feet_R + 9 * e, feet[e].R, sizeof feet[e].R);
+    }
+    kin::FootJacobianLocal(rk, joints, feet, ee, J);
+}
+void orc_kin_integrate(const double* q, const double* v, double* out) { kin::Integrate(q, v, out); }
+int orc_ik(const double* kin_flat, const double* state, const double* ee_des, const double* joint_guess, double* q_out, int* iters) {
+    double ee[4][3];
+    std::memcpy(ee, ee_des, sizeof ee);
+    return kin::InverseKinematics(Kin(kin_flat), state, ee, joint_guess, q_out, iters);
+}
+int orc_mpc_targets_from_traj(void* h, const double* kin_flat, double time, double dt, double mass, const double* Ir_inv, double* q_des,
+                              double* v_des, double* force_des) {
+    ORC_TRY return kin::GetTargetsFromTraj(Kin(kin_flat), M(h).Trajectory(), time, dt, mass, Ir_inv, q_des, v_des, force_des);
+    ORC_CATCH(-1)
+}
 
 }  // extern "C"

@@ -596,3 +596,88 @@ def quat_exp3(v):
     out = np.zeros(4)
     load().orc_quat_exp3(_dptr(v), _dptr(out))
     return out
+
+
+# ---- inverse kinematics (leg_kinematics.cpp); `which` = "oracle" or "ref" (the reference's InverseKinematics over the stand-in)
+def kin_flat(consts):
+    """tests/golden/a1_robot_consts.json["legs"] -> the 228 packed doubles of kin::RobotKin."""
+    out = []
+    for leg in consts["legs"]:
+        out += np.asarray(leg["t"], float).ravel().tolist() + np.asarray(leg["R"], float).ravel().tolist() + np.asarray(leg["axis"], float).ravel().tolist()
+    a = np.ascontiguousarray(out, dtype=np.float64)
+    assert a.size == 228
+    return a
+
+
+def _bind_kin(lib):
+    if getattr(lib, "_kin_bound", False):
+        return lib
+    lib.orc_kin_exp6.argtypes = [_dp, _dp, _dp]
+    lib.orc_kin_log6.argtypes = [_dp, _dp, _dp]
+    lib.orc_kin_jlog6.argtypes = [_dp, _dp, _dp]
+    lib.orc_kin_fk.argtypes = [_dp, _dp, C.c_int, _dp, _dp, _dp]
+    lib.orc_kin_integrate.argtypes = [_dp, _dp, _dp]
+    lib.orc_ik.argtypes = [_dp, _dp, _dp, _dp, _dp, _ip]
+    lib.orc_mpc_targets_from_traj.argtypes = [C.c_void_p, _dp, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp, _dp]
+    lib._kin_bound = True
+    return lib
+
+
+def kin_exp6(nu):
+    nu = np.ascontiguousarray(nu, dtype=np.float64)
+    R, p = np.zeros((3, 3)), np.zeros(3)
+    _bind_kin(load()).orc_kin_exp6(_dptr(nu), _dptr(R), _dptr(p))
+    return R, p
+
+
+def kin_log6(R, p):
+    R, p = np.ascontiguousarray(R, dtype=np.float64), np.ascontiguousarray(p, dtype=np.float64)
+    out = np.zeros(6)
+    _bind_kin(load()).orc_kin_log6(_dptr(R), _dptr(p), _dptr(out))
+    return out
+
+
+def kin_jlog6(R, p):
+    R, p = np.ascontiguousarray(R, dtype=np.float64), np.ascontiguousarray(p, dtype=np.float64)
+    J = np.zeros((6, 6))
+    _bind_kin(load()).orc_kin_jlog6(_dptr(R), _dptr(p), _dptr(J))
+    return J
+
+
+def kin_fk(kin, q, ee=0):
+    """World positions [4][3] / rotations [4][3][3] of the foot frames, and the 6 x 18 LOCAL Jacobian of foot `ee`."""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    fp, fR, J = np.zeros((4, 3)), np.zeros((4, 3, 3)), np.zeros((6, 18))
+    _bind_kin(load()).orc_kin_fk(_dptr(kin), _dptr(q), ee, _dptr(fp), _dptr(fR), _dptr(J))
+    return fp, fR, J
+
+
+def kin_integrate(q, v):
+    q, v = np.ascontiguousarray(q, dtype=np.float64), np.ascontiguousarray(v, dtype=np.float64)
+    out = np.zeros(19)
+    _bind_kin(load()).orc_kin_integrate(_dptr(q), _dptr(v), _dptr(out))
+    return out
+
+
+def ik(kin, state, ee_des, joint_guess, which="oracle"):
+    """SingleRigidBodyModel::InverseKinematics.  Returns (status, q[19], iters[4]); status 1 = "IK did not converge."."""
+    lib = _bind_kin(load()) if which == "oracle" else load_ref_mpc()
+    state = np.ascontiguousarray(state, dtype=np.float64)
+    ee = np.ascontiguousarray(ee_des, dtype=np.float64)
+    g = np.ascontiguousarray(joint_guess, dtype=np.float64)
+    q, it = np.zeros(19), np.zeros(4, np.int32)
+    if which == "oracle":
+        rc = lib.orc_ik(_dptr(kin), _dptr(state), _dptr(ee), _dptr(g), _dptr(q), _iptr(it))
+    else:
+        rc = lib.orc_ref_ik(_dptr(kin), _dptr(state), _dptr(ee), _dptr(g), _dptr(q))
+    return rc, q, it
+
+
+def targets_from_traj(mpc, kin, consts, time, dt, q_des):
+    """MPCController::GetTargetsFromTraj on the oracle's trajectory.  Returns (status, q_des[19], v_des[18], force_des[4][3])."""
+    lib = _bind_kin(mpc.lib)
+    q = np.ascontiguousarray(q_des, dtype=np.float64).copy()
+    v, f = np.zeros(18), np.zeros((4, 3))
+    Ii = np.ascontiguousarray(consts["Ir_inv"], dtype=np.float64)
+    rc = lib.orc_mpc_targets_from_traj(mpc.h, _dptr(kin), time, dt, consts["mass"], _dptr(Ii), _dptr(q), _dptr(v), _dptr(f))
+    return rc, q, v, f

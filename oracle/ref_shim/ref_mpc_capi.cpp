@@ -174,6 +174,34 @@ void* orc_mpc_create_ref(const OrcMpcInfo* ci, const OrcRobotConsts* cr, const d
     CATCH(nullptr)
 }
 void orc_mpc_destroy(void* h) { delete static_cast<Handle*>(h); }
+
+// SingleRigidBodyModel::InverseKinematics (single_rigid_body_model.cpp:314-425) as the reference wrote it, over the pinocchio
+// stand-in.  kin_flat: the 228 packed doubles of oracle::kin::RobotKin.  Returns 0, 1 when it throws "IK did not converge.", -1 else.
+int orc_ref_ik(const double* kin_flat, const double* state, const double* ee_des, const double* joint_guess, double* q_out) {
+    try {
+        auto& c = pinocchio::stub::consts();
+        std::memcpy(&c.kin, kin_flat, sizeof c.kin);
+        c.have_kin = true;
+        if (c.mass == 0) c.mass = 1.0;   // the model's constructor reads mass / inertia; any positive value serves the IK
+        SingleRigidBodyModel model("a1.urdf", {"FL_foot", "FR_foot", "RL_foot", "RR_foot"}, 1, 0.05, vector_t::Zero(19));
+        man_state_t st = man_state_t::Zero(13);
+        for (int i = 0; i < 13; i++) st(i) = state[i];
+        std::vector<vector_3t> ee(4);
+        for (int e = 0; e < 4; e++) ee[e] = vector_3t(ee_des[3 * e], ee_des[3 * e + 1], ee_des[3 * e + 2]);
+        vector_t guess = vector_t::Zero(19);
+        for (int i = 0; i < 12; i++) guess(7 + i) = joint_guess[i];
+        const vector_t ub = vector_t::Zero(12), lb = vector_t::Zero(12);
+        const vector_t q = model.InverseKinematics(st, ee, guess, ub, lb);
+        for (int i = 0; i < 19; i++) q_out[i] = q(i);
+        return 0;
+    } catch (const std::runtime_error& e) {
+        g_err = e.what();
+        return g_err == "IK did not converge." ? 1 : -1;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
 void orc_mpc_set_ipm(void*, double tol_feas, double tol_gap, int max_iter, int refine) {
     if (tol_feas > 0) g_ipm.tol_feas = tol_feas;
     if (tol_gap > 0) g_ipm.tol_gap = tol_gap;

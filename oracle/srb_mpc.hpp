@@ -121,6 +121,7 @@ public:
     FootSpline& Foot(int ee) { return ee_[ee]; }
     const FootSpline& Foot(int ee) const { return ee_[ee]; }
     double InitTime() const { return init_time_; }
+    double NodeDt() const { return node_dt_; }
 
 private:
     void UpdateSplineVarsCount();

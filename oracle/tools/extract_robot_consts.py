@@ -123,6 +123,38 @@ def main(urdf_path, out_path, joint_cfg):
         t[1] += 0.1 if t[1] >= 0 else -0.1              # single_rigid_body_model.cpp:291-297
         t[0] += 0.025                                   # :299-305 (both branches add 0.025)
         hips.append([float(t[0]), float(t[1])])
+    # leg chains for the inverse kinematics (single_rigid_body_model.cpp:314-455): hip / thigh / calf joint and foot frame, each
+    # placed in the frame of the movable joint before it (fixed joints in between merged, as pinocchio's URDF parser does)
+    by_child = {}
+    for plink, lst in children.items():
+        for (jn, jt, c, xyz, R, axis) in lst:
+            by_child[c] = (jn, jt, plink, xyz, R, axis)
+    by_name = {v[0]: (c,) + v for c, v in by_child.items()}
+
+    def placement(jname, ancestor_link):
+        c, jn, jt, plink, xyz, R, axis = by_name[jname]
+        t, Rt = xyz.copy(), R.copy()
+        link = plink
+        while link != ancestor_link:
+            jn2, jt2, plink2, xyz2, R2, _ = by_child[link]
+            assert jt2 == "fixed", (jname, jn2)
+            t, Rt = xyz2 + R2 @ t, R2 @ Rt
+            link = plink2
+        return t, Rt, axis, c
+
+    legs = []
+    for leg in ("FL", "FR", "RL", "RR"):
+        anc = roots[0]
+        ts, Rs, axes = [], [], []
+        for jn in (f"{leg}_hip_joint", f"{leg}_thigh_joint", f"{leg}_calf_joint", f"{leg}_foot_fixed"):
+            t, Rt, axis, child = placement(jn, anc)
+            ts.append([float(v) for v in t])
+            Rs.append([float(v) for v in Rt.reshape(-1)])
+            if not jn.endswith("_fixed"):
+                a = np.asarray(axis, float)
+                axes.append([float(v) for v in a / np.linalg.norm(a)])
+            anc = child
+        legs.append({"t": ts, "R": Rs, "axis": axes})
     out = {
         "robot": "a1",
         "source": "models/a1_description/urdf/a1.urdf + apps/a1_configuration.yaml:init_config",
@@ -133,6 +165,7 @@ def main(urdf_path, out_path, joint_cfg):
         "hip_offsets_xy": hips,
         "hip_joint_translation": hips_raw,   # oMi[hip joint] - oMi[root] before the reference's own offsets
         "gravity": [0.0, 0.0, -9.81],
+        "legs": legs,   # FL, FR, RL, RR: placements of hip / thigh / calf joint and of the foot frame; joint axes
     }
     with open(out_path, "w") as f:
         json.dump(out, f, indent=1)

@@ -39,6 +39,19 @@ def test_urdf_reader_matches_the_robot_constants_fixture():
     assert np.abs(np.array(rb.hip_xy[:]).reshape(4, 2) - np.array(gold["hip_offsets_xy"])).max() < 1e-12
 
 
+@pytest.mark.skipif(not os.path.exists(A1_URDF), reason="the reference's URDF is only present in the build container")
+def test_urdf_reader_extracts_the_leg_chains_of_the_fixture():
+    """host/urdf_consts.cpp: LegKinematicsFromURDF (what the inverse kinematics needs of the model) against tests/golden."""
+    lib = C.CDLL(SHIM_SO)
+    kin = (C.c_double * 228)()
+    assert lib.bgg_host_leg_kinematics_from_urdf(A1_URDF.encode(), kin) == 0
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "a1_robot_consts.json")))
+    want = []
+    for leg in gold["legs"]:
+        want += np.asarray(leg["t"], float).ravel().tolist() + np.asarray(leg["R"], float).ravel().tolist() + np.asarray(leg["axis"], float).ravel().tolist()
+    assert np.abs(np.array(kin[:]) - np.array(want)).max() < 1e-15
+
+
 @pytest.mark.skipif(not os.path.exists("/root/reference/apps"), reason="the reference's YAML files are only present in the build container")
 @pytest.mark.parametrize("name", ["a1_configuration", "a1_gait_opt_config", "a1_config_distr_rejection"])
 def test_config_parser_reads_the_reference_yaml_and_pins_the_named_workloads(name):
