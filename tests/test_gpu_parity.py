@@ -408,12 +408,13 @@ def test_gait_gradient_refuses_unsolved_instances():
         assert np.all(np.isfinite(res["dHdtheta"][b])) and len(res["dHdtheta"][b]) == 20
 
 
-@pytest.mark.parametrize("cfg_name", ["a1_configuration", "a1_gait_opt_config"])
-def test_contact_time_lp_and_line_search_match_oracle(cfg_name):
+@pytest.mark.parametrize("cfg_name,K", [("a1_configuration", 10), ("a1_gait_opt_config", 10), ("a1_gait_opt_config", 64)])
+def test_contact_time_lp_and_line_search_match_oracle(cfg_name, K):
     """SURVEY 8a20-a21: GaitOptimizer::OptimizeContactTimes (the LP over the contact-time step) and
-    GaitOptimizer::LineSearch (LS_SIZE = 10 re-solves, arg-min of cost / n), CUDA path against the oracle."""
+    GaitOptimizer::LineSearch (K re-solves, arg-min of cost / n), CUDA path against the oracle: K = LS_SIZE = 10 as the reference
+    ships it, and K = 64 as BASELINE config #3 asks."""
     cfg = wl.CONFIGS[cfg_name]
-    B = 3
+    B = 3 if K == 10 else 2
     states, _, ee = wl.batched_trot_inputs(cfg, B, seed=21)
     states[0] = cfg["srb_init"]
     ee[0] = wl.EE_NOMINAL
@@ -461,9 +462,8 @@ def test_contact_time_lp_and_line_search_match_oracle(cfg_name):
         assert np.abs(nt_g - nt_o).max() < 1e-9
         steps_o.append(s_g)     # the line search below runs from the CUDA step on both sides
         xk_o.append(x_g)
-    # line search with LS_SIZE = 10 from the same step and -- mirrored -- the same parent trajectory on both sides (a child
-    # QP whose contact times moved by up to 0.1 s amplifies a 1e-7 difference of the parents a thousandfold)
-    K = 10
+    # line search from the same step and -- mirrored -- the same parent trajectory on both sides (a child QP whose contact
+    # times moved by up to 0.1 s amplifies a 1e-7 difference of the parents a thousandfold)
     for b in range(B):
         if steps_o[b] is not None:
             common.mirror_oracle_to_gpu(oracles[b], gpu, b)
@@ -525,6 +525,38 @@ def test_closed_loop_sweep_follows_the_oracle():
         assert [int(h[b]) for h in hist] == st
         assert abs(gpu.get_instance(b)["init_time"] - T * dt) < 1e-12
         assert np.abs(gpu.GetStates(b) - o.states()).max() < 1e-3 * max(1.0, np.abs(o.states()).max())
+
+
+def test_closed_loop_25_ticks_with_mirroring_stays_within_the_parity_bar():
+    """Config #5 (disturbance rejection, N = 50) over 25 closed-loop ticks -- the horizon slides through lift-offs and touch-downs,
+    the QP changes size -- with the oracle's trajectory mirrored into the CUDA instance before every solve, so that what is
+    compared at each tick is one RTI step from identical inputs: same status, cost within 1e-4, trajectory within 1e-4."""
+    cfg_name = "a1_config_distr_rejection"
+    cfg = wl.CONFIGS[cfg_name]
+    B, T, dt = 2, 25, cfg["integrator_dt"]
+    states, t0, ee = wl.disturbance_sweep_inputs(cfg, B, seed=9)
+    gpu = common.make_gpu(cfg_name, B, states)
+    oracles = [common.make_oracle(cfg_name, states[b]) for b in range(B)]
+    s, e, t = states.copy(), ee.copy(), np.zeros(B)
+    sizes_seen = set()
+    for tick in range(T):
+        for b, o in enumerate(oracles):
+            common.mirror_oracle_to_gpu(o, gpu, b)
+        out = gpu.GetRealTimeUpdate(s, t, e)
+        for b, o in enumerate(oracles):
+            st_o = o.solve(s[b], t[b], e[b], real_time=True)
+            assert out["status"][b] == st_o, (tick, b, out["status"][b], st_o)
+            so = o.states()
+            if st_o != 3:   # (primal infeasible: both sides keep the previous solution)
+                co = o.cost()
+                assert abs(out["cost"][b] - co) <= 1e-4 * max(1.0, abs(co)), (tick, b)
+                assert np.abs(gpu.GetStates(b) - so).max() <= 1e-4 * max(1.0, np.abs(so).max()), (tick, b)
+                sizes_seen.add(gpu.sizes(b)["nu"])
+            # the plant of the sweeps: the next measured state is node 1 of the solved trajectory (apps/mpc_demo.cpp:185)
+            t[b] = o.init_time() + dt
+            s[b] = so[1]
+            e[b] = [o.ee_at(k, t[b]) for k in range(4)]
+    assert len(sizes_seen) > 1, "the horizon never changed the QP's size: the test does not cover what it claims"
 
 
 def test_controller_three_mode_schedule_follows_the_oracle():
