@@ -81,6 +81,7 @@ def lib():
         L.bgg_download_results.argtypes = [C.c_void_p, _ip, _ip, _dp, _dp, _dp, C.c_int]
         L.bgg_synchronize.argtypes = [C.c_void_p]
         L.bgg_advance_plant.argtypes = [C.c_void_p, C.c_double]
+        L.bgg_param_partials.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _dp, _ip, _ip, _dp, _dp]
         L.bgg_set_kinematics.argtypes = [C.c_void_p, _dp]
         L.bgg_ik_batch.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip, _ip]
         L.bgg_targets_from_traj_batch.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _ip]
@@ -113,7 +114,7 @@ def exported_symbols():
     """Names include/bgg.h declares; used by the CPU-side ABI test."""
     return ["bgg_last_error", "bgg_device_count", "bgg_measure_fp64_peak", "bgg_create", "bgg_destroy", "bgg_set_costs", "bgg_batch_reset",
             "bgg_set_warm_states", "bgg_set_contact_times", "bgg_solve_batch", "bgg_qp_solve_batch", "bgg_controller_tick_batch", "bgg_controller_get_step", "bgg_upload_inputs", "bgg_solve_resident",
-            "bgg_download_results", "bgg_synchronize", "bgg_advance_plant", "bgg_set_kinematics", "bgg_ik_batch", "bgg_targets_from_traj_batch", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count", "bgg_event_record", "bgg_event_elapsed_ms",
+            "bgg_download_results", "bgg_synchronize", "bgg_advance_plant", "bgg_param_partials", "bgg_set_kinematics", "bgg_ik_batch", "bgg_targets_from_traj_batch", "bgg_set_profiling", "bgg_last_kernel_ms", "bgg_kernel_launch_count", "bgg_event_record", "bgg_event_elapsed_ms",
             "bgg_get_sizes", "bgg_get_dynamics", "bgg_get_condensed", "bgg_export_qp_csc", "bgg_gait_gradient_batch", "bgg_optimize_contact_times_batch",
             "bgg_line_search_batch", "bgg_get_adjoint",
             "bgg_get_contact_times", "bgg_set_solution", "bgg_get_solution", "bgg_instance_bytes",
@@ -292,6 +293,24 @@ class BatchedMPC:
         if z_out is not None:
             out["z"] = z_out
         return out
+
+    def ComputeParamPartialsClarabel(self, b, ee, contact_idx, cap=40000):
+        """MPCSingleRigidBody::ComputeParamPartialsClarabel for one contact time of instance b: dense dA, dG and db in the reference's
+        numbering, or None when the last solve is not Solved."""
+        counts = np.zeros(4, np.int32)
+        Ar, Ac, Av = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+        Gr, Gc, Gv = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+        sz = self.sizes(b)
+        db = np.zeros(sz["n_eq"] + 12 * (self.N + 1))
+        rc = self.L.bgg_param_partials(self.h, b, ee, contact_idx, cap, _i(counts), _i(Ar), _i(Ac), _d(Av), _i(Gr), _i(Gc), _d(Gv), _d(db))
+        if rc == 1:
+            return None
+        self._chk(rc)
+        n = sz["n"]
+        dA, dG = np.zeros((counts[2], n)), np.zeros((counts[3], n))
+        np.add.at(dA, (Ar[:counts[0]], Ac[:counts[0]]), Av[:counts[0]])
+        np.add.at(dG, (Gr[:counts[1]], Gc[:counts[1]]), Gv[:counts[1]])
+        return dict(dA=dA, dG=dG, db=db[:counts[2]], nnz=(int(counts[0]), int(counts[1])))
 
     # ---- joint-space targets (SURVEY 8f row 2)
     def SetKinematics(self, robot):

@@ -17,8 +17,9 @@ $NVCC $ARCH $COMMON -dc -o build/bgg_gradient.o csrc/bgg_gradient.cu 2> build/pt
 $NVCC $ARCH $COMMON -dc -o build/bgg_gait.o csrc/bgg_gait.cu 2> build/ptxas_gait.log
 $NVCC $ARCH $COMMON -dc -o build/bgg_qp.o csrc/bgg_qp.cu 2> build/ptxas_qp.log
 $NVCC $ARCH $COMMON -dc -o build/bgg_ik.o csrc/bgg_ik.cu 2> build/ptxas_ik.log
+$NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_partials.o csrc/bgg_partials.cu 2> build/ptxas_partials.log
 $NVCC $ARCH $COMMON -fmad=false -dc -o build/bgg_capi.o csrc/bgg_capi.cu 2> build/ptxas_capi.log
-$NVCC $ARCH -shared -o libbgg_b200.so build/bgg_prepare.o build/bgg_condense.o build/bgg_ipm.o build/bgg_finish.o build/bgg_assemble.o build/bgg_gradient.o build/bgg_gait.o build/bgg_qp.o build/bgg_ik.o build/bgg_capi.o -lcudart
+$NVCC $ARCH -shared -o libbgg_b200.so build/bgg_prepare.o build/bgg_condense.o build/bgg_ipm.o build/bgg_finish.o build/bgg_assemble.o build/bgg_gradient.o build/bgg_gait.o build/bgg_qp.o build/bgg_ik.o build/bgg_partials.o build/bgg_capi.o -lcudart
 # host shim: the reference's C++ call surface over the C ABI (no CUDA in these translation units) and its test driver
 CXX=${CXX:-g++}
 $CXX -O2 -std=c++17 -Wall -fPIC -shared -o libmpc_b200.so host/mpc_b200.cpp host/mpc_controller_b200.cpp host/urdf_consts.cpp host/config_parser.cpp -L. -lbgg_b200 -Wl,-rpath,'$ORIGIN'

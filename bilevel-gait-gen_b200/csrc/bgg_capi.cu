@@ -878,6 +878,125 @@ int bgg_get_sizes(bgg_handle* h, int b, bgg_sizes* out) {
     return BGG_OK;
 }
 
+int bgg_param_partials(bgg_handle* h, int b, int ee, int contact_idx, int cap, int32_t* counts, int32_t* Ar, int32_t* Ac, double* Av, int32_t* Gr,
+                       int32_t* Gc, double* Gv, double* db) {
+    if (!h || b < 0 || b >= h->batch || ee < 0 || ee >= kNumEE || contact_idx < 0 || cap <= 0 || !counts || !Ar || !Ac || !Av || !Gr || !Gc || !Gv || !db)
+        return fail(BGG_EINVAL, "bad argument");
+    bgg_sizes sz;
+    int rc = bgg_get_sizes(h, b, &sz);
+    if (rc) return rc;
+    if (sz.error) return fail(BGG_ESTATE, "the instance has no QP (k_prepare refused it)");
+    if (sz.status != kSolved) return 1;   // the reference returns false (mpc_single_rigid_body.cpp:644-647)
+    int32_t nct[kNumEE * 1];
+    {
+        std::vector<double> t(kNumEE * kMaxContacts);
+        std::vector<int32_t> ty(kNumEE * kMaxContacts), n(kNumEE);
+        rc = bgg_get_contact_times(h, b, 1, t.data(), ty.data(), n.data());
+        if (rc) return rc;
+        nct[0] = n[ee];
+    }
+    if (contact_idx >= nct[0]) return fail(BGG_EINVAL, "contact_idx is beyond the foot's contact times");
+    CU(cudaSetDevice(h->device));
+    const int N = h->P.N, nu_cap = h->L.max_nu;
+    const size_t nd = param_partials_doubles(N, nu_cap);
+    DevPool pool;
+    double* d_out = pool.get<double>(nd);
+    double* d_ut = pool.get<double>(nu_cap);
+    if (!d_out || !d_ut) return fail(BGG_ECUDA, "out of device memory");
+    launch_param_partials(h->P, h->d_inst, h->L, h->d_ws, b, ee, contact_idx, nu_cap, d_out, d_ut, h->stream);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    std::vector<double> o(nd);
+    CU(cudaMemcpyAsync(o.data(), d_out, 8 * nd, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    // ---- blocks -> triplets in the reference's numbering: columns [states 12 (N + 1) | force variables | position variables]; equality
+    // rows [dynamics | touch-down | foot start]; inequality rows [force box + / - | friction pyramid | foot box + / -]
+    const double dt = h->P.dt, mu = h->P.friction_coef;
+    const int nf = static_cast<int>(o[1]), ns = static_cast<int>(o[22]), ntd = static_cast<int>(o[23]);
+    const int fsi = kNx * (N + 1), psi = fsi + nf;
+    const int num_dyn = kNx * (N + 1), num_loc = 16 * (N - 3), num_start = 2 * kNumEE;
+    const int eq_td = num_dyn, eq_start = num_dyn + ntd, in_cone = 2 * ns, in_loc = 6 * ns;
+    const int num_eq = num_dyn + ntd + num_start, num_in = 6 * ns + num_loc;
+    int na = 0, ng = 0;
+    bool overflow = false;
+    auto putA = [&](int r, int c, double v) {
+        if (v == 0.0) return;
+        if (na < cap) { Ar[na] = r; Ac[na] = c; Av[na] = v; }
+        else overflow = true;
+        ++na;
+    };
+    auto putG = [&](int r, int c, double v) {
+        if (v == 0.0) return;
+        if (ng < cap) { Gr[ng] = r; Gc[ng] = c; Gv[ng] = v; }
+        else overflow = true;
+        ++ng;
+    };
+    for (int i = 0; i < num_eq; ++i) db[i] = 0.0;
+    const double* dyn = o.data() + kPartHdr;
+    const size_t dyn_stride = 9 + 6 * static_cast<size_t>(nu_cap) + 6;
+    const int rowmap[6] = {3, 4, 5, 9, 10, 11};
+    for (int k = 0; k < N; ++k) {   // :651-668: dt * dA, dt * dB, db = -dt * dC
+        const double* dA = dyn + k * dyn_stride;
+        const double* dB = dA + 9;
+        const double* dC = dB + 6 * static_cast<size_t>(nu_cap);
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) putA((k + 1) * kNx + 9 + r, k * kNx + c, dt * dA[3 * r + c]);
+        for (int r = 0; r < 6; ++r) {
+            for (int j = 0; j < sz.nu; ++j) putA((k + 1) * kNx + rowmap[r], fsi + j, dt * dB[static_cast<size_t>(r) * nu_cap + j]);
+            db[(k + 1) * kNx + rowmap[r]] = -(dt * dC[r]);
+        }
+    }
+    const double* frc = dyn + N * dyn_stride;
+    const double* loc = frc + 10 * 3 * 6;
+    const double* start = loc + static_cast<size_t>(N + 1) * 2 * 4;
+    const double* tdp = start + 2 * 4;
+    if (o[18] != 0.0) {   // mpc.cpp:416-531 (force box on z, + rows then - rows) and :240-350 (friction pyramid)
+        const int row0 = static_cast<int>(o[19]);
+        const double pyr[4][3] = {{1, 0, -mu}, {-1, 0, -mu}, {0, 1, -mu}, {0, -1, -mu}};
+        for (int j = 0; j < 2; ++j)
+            for (int i = 0; i < kSamplesPerStance; ++i) {
+                const double* p = frc + (static_cast<size_t>(i) * 3 + 2) * 6;
+                for (int a = 0; a < static_cast<int>(p[1]); ++a) putG(j * ns + row0 + i, fsi + static_cast<int>(p[0]) + a, (j == 0 ? 1.0 : -1.0) * p[2 + a]);
+            }
+        for (int i = 0; i < kSamplesPerStance; ++i)
+            for (int c = 0; c < 3; ++c) {
+                const double* p = frc + (static_cast<size_t>(i) * 3 + c) * 6;
+                for (int fc = 0; fc < 4; ++fc)
+                    for (int a = 0; a < static_cast<int>(p[1]); ++a)
+                        putG(in_cone + 4 * (row0 + i) + fc, fsi + static_cast<int>(p[0]) + a, pyr[fc][c] * p[2 + a]);
+            }
+    }
+    {   // :705-733 foot box of this foot at nodes 4 .. N, + rows then - rows
+        int idx = 2 * ee;
+        for (int node = kEENodeStart; node <= N; ++node) {
+            for (int c = 0; c < 2; ++c) {
+                const double* p = loc + (static_cast<size_t>(node) * 2 + c) * 4;
+                for (int a = 0; a < static_cast<int>(p[1]); ++a) {
+                    putG(in_loc + idx, psi + static_cast<int>(p[0]) + a, p[2 + a]);
+                    putG(in_loc + idx + num_loc / 2, psi + static_cast<int>(p[0]) + a, -p[2 + a]);
+                }
+                idx++;
+            }
+            idx += 2 * (kNumEE - 1);
+        }
+    }
+    if (o[20] != 0.0) {   // :889-927 touch-down rows
+        const int trow = static_cast<int>(o[21]);
+        for (int c = 0; c < 2; ++c) {
+            const double* p = tdp + 5 * c;
+            if (trow + c < ntd) db[eq_td + trow + c] = p[4];
+            for (int a = 0; a < static_cast<int>(p[1]); ++a) putA(eq_td + trow + c, psi + static_cast<int>(p[0]) + a, p[2 + a]);
+        }
+    }
+    for (int c = 0; c < 2; ++c) {   // :733-752: every foot's start-row partial lands on rows 0-1 of the block (kept)
+        const double* p = start + 4 * c;
+        for (int a = 0; a < static_cast<int>(p[1]); ++a) putA(eq_start + c, psi + static_cast<int>(p[0]) + a, p[2 + a]);
+    }
+    counts[0] = na; counts[1] = ng; counts[2] = num_eq; counts[3] = num_in;
+    if (overflow) return fail(BGG_EINVAL, "cap is smaller than the number of non-zeros");
+    return BGG_OK;
+}
+
 int bgg_get_dynamics(bgg_handle* h, int first, int count, double* Ad, double* Bd, double* cd, int nu_stride) {
     if (!h || !Ad || !Bd || !cd || first < 0 || count <= 0 || first + count > h->batch) return fail(BGG_EINVAL, "bad range");
     for (int b = first; b < first + count; ++b) {

@@ -71,6 +71,11 @@ void launch_ik(const RobotKin& rk, int count, const double* state, const double*
                int* iters, cudaStream_t stream);
 void launch_targets_from_traj(const Params& P, const RobotKin& rk, const Instance* inst, int B, const double* time, double* q_des, double* v_des,
                               double* force_des, int* status, cudaStream_t stream);
+// bgg_partials.cu: one contact time's parameter partials written out (ComputeParamPartialsClarabel), blocks described there
+constexpr int kPartHdr = 32;
+__host__ __device__ size_t param_partials_doubles(int N, int nu_cap);
+void launch_param_partials(const Params& P, const Instance* inst, const WsLayout& L, const char* ws, int b, int ee, int idx, int nu_cap, double* out,
+                           double* ut, cudaStream_t stream);
 void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int want, const int* gate, cudaStream_t stream);
 void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, const int* gate, cudaStream_t stream);
 // max over the batch of (nu, n_samples) after launch_prepare, written to out[0..1] (device); instances larger than the caps

@@ -507,7 +507,46 @@ bool MPCSingleRigidBody::ComputeParamPartialsClarabel(const Trajectory& traj, QP
     partials.source = this;
     partials.ee = ee;
     partials.idx = idx;
-    return true;   // the partial itself is generated and contracted on the device (csrc/bgg_gradient.cu)
+    if (!export_partials_) return true;   // gait-optimisation path: the partial is generated and contracted on the device (csrc/bgg_gradient.cu)
+    // the matrices themselves (:648-790), triplets in the reference's numbering -> column-compressed, duplicates summed
+    int32_t counts[4] = {0, 0, 0, 0};
+    int cap = 1 << 15;
+    std::vector<int32_t> Ar, Ac, Gr, Gc;
+    std::vector<double> Av, Gv, db;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        Ar.assign(cap, 0); Ac.assign(cap, 0); Gr.assign(cap, 0); Gc.assign(cap, 0);
+        Av.assign(cap, 0.0); Gv.assign(cap, 0.0);
+        db.assign(static_cast<size_t>(12) * (info_.num_nodes + 1) + 64, 0.0);
+        const int rc = bgg_param_partials(h_, 0, ee, idx, cap, counts, Ar.data(), Ac.data(), Av.data(), Gr.data(), Gc.data(), Gv.data(), db.data());
+        if (rc == 1) return false;
+        if (rc == BGG_OK) break;
+        if (attempt == 1 || std::max(counts[0], counts[1]) <= cap) throw std::runtime_error(std::string("bgg_param_partials: ") + bgg_last_error());
+        cap = std::max(counts[0], counts[1]);
+    }
+    const int n = GetNumDecisionVars();
+    auto to_csc = [n](int rows, int nnz, const std::vector<int32_t>& r, const std::vector<int32_t>& c, const std::vector<double>& v) {
+        std::vector<std::map<int, double>> cols(n);   // setFromTriplets: duplicates summed, rows ascending within a column
+        for (int k = 0; k < nnz; ++k) cols[c[k]][r[k]] += v[k];
+        SparseCsc m;
+        m.rows = rows;
+        m.cols = n;
+        m.outer.assign(n + 1, 0);
+        for (int j = 0; j < n; ++j) {
+            for (const auto& kv : cols[j]) {
+                m.inner.push_back(kv.first);
+                m.values.push_back(kv.second);
+            }
+            m.outer[j + 1] = static_cast<int>(m.values.size());
+        }
+        return m;
+    };
+    partials.dA = to_csc(counts[2], counts[0], Ar, Ac, Av);
+    partials.dG = to_csc(counts[3], counts[1], Gr, Gc, Gv);
+    partials.db = vector_t::Zero(counts[2]);
+    for (int i = 0; i < counts[2]; ++i) partials.db(i) = db[i];
+    partials.dh = vector_t::Zero(counts[3]);
+    partials.dq = vector_t::Zero(n);
+    return true;
 }
 std::vector<vector_2t> MPCSingleRigidBody::GetEEBoxCenter() {
     std::vector<vector_2t> c;

@@ -7,8 +7,9 @@
 // one or two calls of the C ABI.  One shim object = one handle with batch 1; batch drivers use the ABI directly.
 //
 // Deliberate differences: cost matrices are read by their diagonals (every shipped
-// configuration is diagonal); QPPartialsDense / QPPartials are tokens, not 260 x 372 dense matrices -- the contraction
-// they feed (GaitOptimizer::ComputeCostFcnDerivWrtContactTimes) runs on the device without forming them.
+// configuration is diagonal); on the gait-optimisation path QPPartialsDense / QPPartials are tokens, not 260 x 372 dense
+// matrices -- the contraction they feed (GaitOptimizer::ComputeCostFcnDerivWrtContactTimes) runs on the device without forming
+// them; QPPartials carries the real sparse dA / dG / db when the caller asks for them (MPC::SetExportParamPartials).
 #pragma once
 #include <array>
 #include <fstream>
@@ -208,10 +209,13 @@ struct QPPartialsDense {
     const MPC* source = nullptr;
     void SetZero() {}
 };
-struct QPPartials {
+struct QPPartials {   // mpc/include/qp/qp_partials.h:15-35
     const MPC* source = nullptr;
     int ee = -1, idx = -1;
-    void SetZero() {}
+    // filled by ComputeParamPartialsClarabel when MPC::SetExportParamPartials(true) (bgg_param_partials); empty otherwise
+    SparseCsc dA, dG, dP;
+    vector_t db, dh, dq, dl, du;
+    void SetZero() { dA = dG = dP = SparseCsc(); db = dh = dq = dl = du = vector_t(); }
 };
 
 class MPC {
@@ -247,6 +251,9 @@ public:
     void SetVerbosityLevel(MPCVerbosityLevel verbosity) { info_.verbose = verbosity; }
     void AdjustForCurrentContacts(double time, const controller::Contact& contact);   // mpc.cpp:1195-1203
     SolveQuality GetSolveQuality() const { return quality_; }
+    // ComputeParamPartialsClarabel writes the sparse matrices into QPPartials as well (one small kernel and a read-back per call);
+    // off by default: the gait optimiser's own path does not read them
+    void SetExportParamPartials(bool on) { export_partials_ = on; }
     void PrintStats() const;
     void PrintStatLineToFile(std::ofstream& log_file) const;
     double GetAvgCost() const { return solves_ ? cost_sum_ / solves_ : 0.0; }
@@ -263,6 +270,7 @@ protected:
     bgg_robot robot_{};
     bgg_handle* h_ = nullptr;
     SolveQuality quality_ = Unsolved;
+    bool export_partials_ = false;
     double cost_ = 0, cost_sum_ = 0, alpha_ = 0, last_solve_ms_ = 0;
     mutable bool used_log_file_ = false;
     int solves_ = 0, iters_ = 0;

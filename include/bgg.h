@@ -147,6 +147,16 @@ int bgg_synchronize(bgg_handle* h);
  * feet = the trajectory's feet at the new time.  Follow with bgg_solve_resident. */
 int bgg_advance_plant(bgg_handle* h, double dt);
 
+/* MPCSingleRigidBody::ComputeParamPartialsClarabel (mpc/mpc_single_rigid_body.cpp:642-792) for instance b, foot `ee`, contact time
+ * `contact_idx`: the partials of the QP's constraint matrices and equality right-hand side with respect to that contact time, as
+ * triplets in the reference's numbering -- dA (num_eq x n: dynamics | touch-down | foot start), dG (num_ineq x n: force box |
+ * friction pyramid | foot box), db [num_eq]; exact zeros are not listed (utils/sparse_matrix_builder.cpp:25).  The gait-gradient
+ * path (bgg_gait_gradient_batch) never forms these; this is the export for callers that want the matrices (test/mpc_test.cpp:140-236).
+ * counts = [nnz dA, nnz dG, num_eq, num_ineq].  Returns BGG_OK; 1 when the instance's last solve is not Solved (the reference
+ * returns false); a negative code otherwise (cap too small: counts holds the sizes needed). */
+int bgg_param_partials(bgg_handle* h, int b, int ee, int contact_idx, int cap, int32_t* counts, int32_t* Ar, int32_t* Ac, double* Av, int32_t* Gr,
+                       int32_t* Gc, double* Gv, double* db);
+
 /* ---- joint-space targets */
 int bgg_set_kinematics(bgg_handle* h, const bgg_kinematics* kin);
 /* SingleRigidBodyModel::InverseKinematics (single_rigid_body_model.cpp:314-425) for `count` independent problems: state [count][13]

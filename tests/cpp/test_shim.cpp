@@ -226,6 +226,48 @@ int main(int argc, char** argv) {
             cen.GetRealTimeUpdate(6000, init_state, 0.0);
             std::printf("centroidal_vars %d\ncentroidal_cost_equal %d\n", cen.GetNumDecisionVars(), cen.Live().GetCost() == cost_after_rt ? 1 : 0);
         }
+        {   // "Model Partials" of test/mpc_test.cpp:113-236: ComputeParamPartialsClarabel's dA / dG against finite differences of the
+            // assembled constraint matrix when one contact time moves (dynamics, force-box and friction rows, margin 1e-4)
+            const double h = std::sqrt(1e-16);
+            MPCSingleRigidBody base = mpc;
+            base.SetExportParamPartials(true);
+            base.GetRealTimeUpdate(init_state, 0.0, ee, false);
+            const Trajectory traj_u = base.GetTrajectory();          // the trajectory the partials are taken at
+            MPCSingleRigidBody at = base;                            // its QP assembled at traj_u
+            at.SetWarmStartTrajectory(traj_u);
+            at.GetRealTimeUpdate(init_state, 0.0, ee, false);
+            const QPData d1 = at.GetQPData();
+            const std::vector<time_v> times = traj_u.GetContactTimes();
+            double worst_dyn = 0, worst_fb = 0, worst_cone = 0;
+            int checked = 0, nnz_a = 0, nnz_g = 0;
+            const int nd = d1.num_dynamics_constraints, nfb = d1.num_force_box_constraints_, nc = d1.num_cone_constraints_;
+            for (int e = 0; e < 4; ++e)
+                for (int idx = 1; idx < static_cast<int>(times.at(e).size()); ++idx) {
+                    std::vector<time_v> mod = times;
+                    mod.at(e).at(idx).SetTime(mod.at(e).at(idx).GetTime() + h);
+                    MPCSingleRigidBody moved = base;
+                    moved.SetWarmStartTrajectory(traj_u);
+                    moved.UpdateContactTimes(mod);
+                    moved.GetRealTimeUpdate(init_state, 0.0, ee, false);
+                    const QPData d2 = moved.GetQPData();
+                    QPPartials part;
+                    if (!base.ComputeParamPartialsClarabel(traj_u, part, e, idx)) throw std::runtime_error("no partials");
+                    nnz_a += part.dA.nonZeros();
+                    nnz_g += part.dG.nonZeros();
+                    for (int c = 0; c < d1.sparse_constraint_.cols; ++c) {
+                        for (int r = 0; r < nd; ++r)
+                            worst_dyn = std::max(worst_dyn, std::abs(part.dA.coeff(r, c) - (d2.sparse_constraint_.coeff(r, c) - d1.sparse_constraint_.coeff(r, c)) / h));
+                        for (int r = 0; r < nfb; ++r)
+                            worst_fb = std::max(worst_fb, std::abs(part.dG.coeff(r, c) - (d2.sparse_constraint_.coeff(nd + r, c) - d1.sparse_constraint_.coeff(nd + r, c)) / h));
+                        for (int r = 0; r < nc; ++r)
+                            worst_cone = std::max(worst_cone, std::abs(part.dG.coeff(nfb + r, c) -
+                                                                       (d2.sparse_constraint_.coeff(nd + nfb + r, c) - d1.sparse_constraint_.coeff(nd + nfb + r, c)) / h));
+                    }
+                    checked++;
+                }
+            std::printf("partials_checked %d\npartials_nnz %d %d\npartials_fd_dyn %.3e\npartials_fd_fb %.3e\npartials_fd_cone %.3e\n", checked, nnz_a, nnz_g,
+                        worst_dyn, worst_fb, worst_cone);
+        }
         std::printf("done 1\n");
     } catch (const std::exception& e) {
         std::printf("exception %s\n", e.what());

@@ -390,6 +390,40 @@ def test_gait_gradient_kernel_on_injected_solution(cfg_name):
     assert checked == B
 
 
+@pytest.mark.parametrize("cfg_name", ["a1_configuration", "a1_gait_opt_config"])
+def test_param_partials_export_matches_oracle(cfg_name):
+    """bgg_param_partials: the matrices MPCSingleRigidBody::ComputeParamPartialsClarabel (mpc_single_rigid_body.cpp:642-792) fills --
+    model partials of every node, force-box / friction / foot-box / foot-start / touch-down row partials -- for every contact time,
+    against the oracle's restatement (itself checked against finite differences of the assembly the way test/mpc_test.cpp:140-236
+    does, tests/test_oracle_gait.py).  The oracle's updated trajectory is mirrored first, so both sides differentiate the same
+    splines: values within 1e-9, the same non-zero pattern above rounding noise."""
+    cfg = wl.CONFIGS[cfg_name]
+    B = 2
+    states, _, ee = wl.batched_trot_inputs(cfg, B, seed=21)
+    states[0] = cfg["srb_init"]
+    ee[0] = wl.EE_NOMINAL
+    gpu, oracles, out, go = _gradient_case(cfg_name, states, ee)
+    checked = 0
+    for b, o in enumerate(oracles):
+        assert out["status"][b] == 0 and o.qp_solution()["status"] == 0
+        common.mirror_oracle_to_gpu(o, gpu, b)
+        ct = go.contact_times(o)
+        for foot in range(4):
+            for idx in range(len(ct[foot][0])):
+                want = go.param_partials(o, foot, idx)
+                got = gpu.ComputeParamPartialsClarabel(b, foot, idx)
+                for key in ("dA", "dG"):
+                    w = want[key].toarray()
+                    assert got[key].shape == w.shape
+                    assert np.abs(got[key] - w).max() <= 1e-9 * max(1.0, np.abs(w).max()), (b, foot, idx, key)
+                    # same pattern, up to entries that are cancellation residue (1e-16) on one side and exactly 0 on the other
+                    noise = 1e-12 * max(1.0, np.abs(w).max())
+                    assert np.array_equal(np.abs(got[key]) > noise, np.abs(w) > noise), (b, foot, idx, key)
+                assert np.abs(got["db"] - want["db"]).max() <= 1e-9 * max(1.0, np.abs(want["db"]).max()), (b, foot, idx)
+                checked += 1
+    assert checked >= 2 * 16
+
+
 def test_gait_gradient_refuses_unsolved_instances():
     """MPC::ComputeDerivativeTerms returns false unless the last solve was `Solved` (mpc.cpp:1047-1057)."""
     cfg_name = "a1_configuration"
@@ -404,6 +438,7 @@ def test_gait_gradient_refuses_unsolved_instances():
     assert np.any(out["status"] == 3) and np.any(out["status"] == 0), np.bincount(out["status"], minlength=9).tolist()
     for b in np.flatnonzero(out["status"] != 0):
         assert res["status"][b] == 1 and np.all(res["raw"][b] == 0)
+        assert gpu.ComputeParamPartialsClarabel(int(b), 0, 1) is None   # ComputeParamPartialsClarabel returns false likewise (:644-647)
     for b in np.flatnonzero(out["status"] == 0)[:8]:
         assert np.all(np.isfinite(res["dHdtheta"][b])) and len(res["dHdtheta"][b]) == 20
 

@@ -133,6 +133,10 @@ force_cost: 0.000
     assert kv["qp3_infeasible_throws"] == ["1"]
     # AdjustForCurrentContacts: inside the 70 ms window the foot is put in contact, outside it is not (mpc.cpp:1195-1203)
     assert int(kv["adjust_swing_foot"][0]) >= 0 and kv["adjust_near"] == ["1"] and kv["adjust_far"] == ["0"]
+    # the reference's "Model Partials" check (test/mpc_test.cpp:113-236) through the C++ layer: real sparse QPPartials against finite
+    # differences of the assembled constraints, its DERIV_MARGIN = 1e-4
+    assert kv["partials_checked"] == ["16"] and int(kv["partials_nnz"][0]) > 0 and int(kv["partials_nnz"][1]) > 0
+    assert float(kv["partials_fd_dyn"][0]) < 1e-4 and float(kv["partials_fd_fb"][0]) < 1e-4 and float(kv["partials_fd_cone"][0]) < 1e-4
     # the MPCCentroidal adapter runs the same solves as the live class
     assert kv["centroidal_vars"] == ["372"] and kv["centroidal_cost_equal"] == ["1"]
 
