@@ -296,7 +296,8 @@ int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) 
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
     h->max_smem = max_smem;
-    if (ipm_smem_bytes(h->L) > static_cast<size_t>(max_smem) || condense_smem_bytes(h->L) > static_cast<size_t>(max_smem)) {
+    if (ipm_smem_bytes(h->L) > static_cast<size_t>(max_smem) || condense_smem_bytes(h->L) > static_cast<size_t>(max_smem) ||
+        finish_smem_bytes(h->L) > static_cast<size_t>(max_smem)) {
         delete h;
         return fail(BGG_EINVAL, "num_nodes / max_spline_vars need more shared memory than the device offers");
     }

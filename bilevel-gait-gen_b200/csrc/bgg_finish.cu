@@ -18,7 +18,7 @@ __device__ __forceinline__ void cross3f(const double a[3], const double b[3], do
     o[2] = a[0] * b[1] - a[1] * b[0];
 }
 
-static size_t finish_smem_bytes(const WsLayout& L) {
+size_t finish_smem_bytes(const WsLayout& L) {
     const size_t n_max = static_cast<size_t>(kNx) * (L.N + 1) + L.max_nu;
     return 2 * sizeof(FootSpline) * kNumEE + 8 * (4 * n_max + static_cast<size_t>(kNx) * (L.N + 1) + 64 + static_cast<size_t>(kNumEE) * 6 * L.N);
 }
