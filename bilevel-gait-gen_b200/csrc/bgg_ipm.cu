@@ -77,10 +77,12 @@ struct IpmCtx {
 
 // out[0..m) = C v   (v: nu-vector in shared memory); with eout != nullptr also eout[0..neq) = E v - rhs_scale e, computed by the
 // last warp while the others take the samples (no extra barrier)
+// kRowsShared: every row vector lives in shared memory (false in the spilled layout, where some are in the workspace)
+template <bool kRowsShared>
 static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double* v, double* out, double* eout, double rhs_scale) {
     const Smem S = c.S;
     const int *fbase = c.fbase, *pbase = c.pbase, *nfv = c.nfv, *npv = c.npv;
-    __builtin_assume(__isShared(v)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(S.tkc));
+    __builtin_assume(__isShared(v)); if (kRowsShared) __builtin_assume(__isShared(out)); __builtin_assume(__isShared(S.tkc));
     __builtin_assume(__isShared(S.smp)); __builtin_assume(__isShared(S.pw)); __builtin_assume(__isShared(S.pcnt));
     __builtin_assume(__isShared(S.poff)); __builtin_assume(__isShared(fbase)); __builtin_assume(__isShared(pbase));
     __builtin_assume(__isShared(nfv)); __builtin_assume(__isShared(npv));
@@ -127,9 +129,10 @@ static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double
 
 // out[0..nu) += C' y   (y: m-vector; inactive rows carry y == 0); with ey != nullptr also += escale E' ey (the equality rows
 // touch position columns only: the thread that owns the column adds them).  Every output entry is owned by one thread.
+template <bool kRowsShared>
 static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double* y, double* out, const double* ey, double escale) {
     const Smem S = c.S;
-    __builtin_assume(__isShared(y)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(S.ckc));
+    if (kRowsShared) __builtin_assume(__isShared(y)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(S.ckc));
     __builtin_assume(__isShared(S.smp)); __builtin_assume(__isShared(S.pw)); __builtin_assume(__isShared(S.col));
     __builtin_assume(__isShared(S.poff));
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -206,11 +209,13 @@ static __device__ __forceinline__ void ipm_apply_H(const IpmCtx& c, const double
 }
 
 struct IpmCaps {          // per-launch shared-memory sizing, from the actual maxima over the batch
-    int nu, rows, ns, stage_phi;
+    int nu, rows, ns, stage_phi, spill;
 };
-static size_t ipm_smem_core(int N, int nu, int rows, int ns) {
+// spill: the row vectors s, z (they live in the workspace's slack / lam output arrays from the start), rz and the foot-box
+// right-hand sides stay in L2 -- three of the six row vectors on chip instead of six
+static size_t ipm_smem_core(int N, int nu, int rows, int ns, bool spill = false) {
     const size_t kc = 2 * (N - 3), eb = 4 * (N - 3);
-    return 8 * (chol::doubles(nu / 8) + 6 * nu + 6 * static_cast<size_t>(rows) + 2 * eb * 2 + 2 * kc + 5 * kMaxEq + 72 + 2 * eb) +
+    return 8 * (chol::doubles(nu / 8) + 6 * nu + (spill ? 3 : 6) * static_cast<size_t>(rows) + (spill ? 0 : 2 * eb * 2) + 2 * kc + 5 * kMaxEq + 72 + 2 * eb) +
            8 * eb + sizeof(Sample) * static_cast<size_t>(ns) + sizeof(ColInfo) * static_cast<size_t>(nu) + 64;
 }
 static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max) {
@@ -226,18 +231,24 @@ static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max) {
     const size_t phi = 8 * static_cast<size_t>(2 * (L.N - 3)) * c.nu;
     // two CTAs per SM when the core fits twice into the 227 KB; the dense position rows are staged on chip only
     // if that does not cost the second CTA
-    const size_t half = 113 * 1024;
+    const size_t half = 112 * 1024;   // + 1 KB static + 1 KB reserved per CTA, twice, inside the SM's 228 KB
+    c.spill = 0;
     if (core <= half) c.stage_phi = (core + phi <= half) ? 1 : 0;
-    else c.stage_phi = (core + phi <= 225 * 1024) ? 1 : 0;
+    else if (ipm_smem_core(L.N, c.nu, c.rows, c.ns, true) <= half) {
+        // N = 50: 1232 rows.  Two CTAs per SM with three row vectors in L2 beat one CTA with everything on chip
+        c.spill = 1;
+        c.stage_phi = 0;
+    } else c.stage_phi = (core + phi <= 225 * 1024) ? 1 : 0;
     return c;
 }
 static size_t ipm_smem_for(const WsLayout& L, const IpmCaps& c) {
-    return ipm_smem_core(L.N, c.nu, c.rows, c.ns) + (c.stage_phi ? 8 * static_cast<size_t>(2 * (L.N - 3)) * c.nu : 0);
+    return ipm_smem_core(L.N, c.nu, c.rows, c.ns, c.spill != 0) + (c.stage_phi ? 8 * static_cast<size_t>(2 * (L.N - 3)) * c.nu : 0);
 }
 size_t ipm_smem_bytes(const WsLayout& L) {   // worst case for the configured caps (bgg_create's feasibility check)
     return ipm_smem_core(L.N, L.max_nu, L.max_rows, kMaxSamples);
 }
 
+template <bool kSpill>
 __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi, int cap_nu, int cap_rows, int want,
                                                   const int* __restrict__ gate) {
     if (gate && *gate == 0) return;
@@ -274,9 +285,19 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         S.K = p; p += chol::doubles(cap_nu >> 3);
         S.u = p; p += cap_nu; S.du = p; p += cap_nu; S.rd = p; p += cap_nu;
         S.rhs = p; p += cap_nu; S.Hu = p; p += cap_nu; S.x1 = p; p += cap_nu;
-        S.s = p; p += cap_rows; S.lam = p; p += cap_rows; S.ds = p; p += cap_rows; S.dl = p; p += cap_rows;
-        S.rp = p; p += cap_rows; S.wv = p; p += cap_rows;
-        S.d = p; p += 2 * 8 * (N - 3);   // right-hand sides of the foot-box rows only (force rows: see rhs_of)
+        constexpr bool spill = kSpill;
+        if (spill) {   // s and z iterate in the arrays they are reported in; rz and d in the workspace's spill area (L2 resident)
+            S.s = reinterpret_cast<double*>(ws + L.slack);
+            S.lam = reinterpret_cast<double*>(ws + L.lam);
+            S.rp = reinterpret_cast<double*>(ws + L.ipm_spill);
+            S.d = S.rp + L.max_rows;
+        } else {
+            S.s = p; p += cap_rows; S.lam = p; p += cap_rows;
+        }
+        S.ds = p; p += cap_rows; S.dl = p; p += cap_rows;   // adjacent: the KKT assembly's scratch (csrc/bgg_kkt_mma.cuh)
+        if (!spill) { S.rp = p; p += cap_rows; }
+        S.wv = p; p += cap_rows;
+        if (!spill) { S.d = p; p += 2 * 8 * (N - 3); }   // right-hand sides of the foot-box rows only (force rows: see rhs_of)
         S.tkc = p; p += nkc; S.ckc = p; p += nkc;
         S.nueq = p; p += kMaxEq; S.re = p; p += kMaxEq; S.dnu = p; p += kMaxEq; S.y1 = p; p += kMaxEq; S.a3 = p; p += kMaxEq;
         S.red = p; p += 72;   // block_reduce scratch (33) / chol::solve scratch (64)
@@ -382,8 +403,8 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     IpmCtx ctx;
     ctx.S = S; ctx.Hg = Hg; ctx.eq = s_eq; ctx.fbase = s_fbase; ctx.pbase = s_pbase; ctx.nfv = s_nfv; ctx.npv = s_npv;
     ctx.N = N; ctx.nu = nu; ctx.nf = nf; ctx.ns = ns; ctx.ne = ne; ctx.neq = neq; ctx.nkc = nkc; ctx.mu_f = mu_f;
-    auto apply_C = [&](const double* v, double* out, double* eout, double rhs_scale) { PROF(10); ipm_apply_C(ctx, v, out, eout, rhs_scale); PROF(6); };
-    auto add_Ct = [&](const double* y, double* out, const double* ey, double escale) { PROF(10); ipm_add_Ct(ctx, y, out, ey, escale); PROF(7); };
+    auto apply_C = [&](const double* v, double* out, double* eout, double rhs_scale) { PROF(10); ipm_apply_C<!kSpill>(ctx, v, out, eout, rhs_scale); PROF(6); };
+    auto add_Ct = [&](const double* y, double* out, const double* ey, double escale) { PROF(10); ipm_add_Ct<!kSpill>(ctx, y, out, ey, escale); PROF(7); };
     auto apply_H = [&](const double* v, double* out, bool subtract) { PROF(10); ipm_apply_H(ctx, v, out, subtract); PROF(8); };
 
     // K = H + eps I + C' diag(wv) C + E'E/delta in 8 x 8 blocks in shared memory (csrc/bgg_kkt_mma.cuh), then chol::factor in place.
@@ -550,9 +571,10 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
             }
             if (it == P.ipm_max_iter) break;
             // refinement of the solves pays for itself only once W = z / s has spread over many decades: it starts when mu
-            // has fallen to ipm_refine_mu_frac of its first value
+            // has fallen to ipm_refine_mu_frac of its first value; an instance still iterating at ipm_refine_from_iter is a hard
+            // one (the batch average is 17 iterations) and gets it from there on
             if (it == 0) mu_first = mu;
-            refine_now = P.ipm_refine > 0 && mu <= P.ipm_refine_mu_frac * mu_first;
+            refine_now = P.ipm_refine > 0 && (mu <= P.ipm_refine_mu_frac * mu_first || it >= P.ipm_refine_from_iter);
             n_refined += refine_now ? 1 : 0;
         }
         if (!build_and_factor()) {
@@ -774,13 +796,14 @@ void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max,
     const size_t smem = ipm_smem_for(L, c);
     // the opt-in is per device and context: set on every launch (a second handle on another GPU, or another host thread,
     // must not depend on what an earlier launch configured)
-    cudaFuncSetAttribute(k_ipm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(c.spill ? k_ipm<true> : k_ipm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (getenv("BGG_DEBUG_OCC")) {
         int nblk = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, k_ipm, 256, smem);
-        fprintf(stderr, "k_ipm: dynamic smem %zu B, caps nu %d rows %d, stage_phi %d, resident CTAs per SM %d\n", smem, c.nu, c.rows, c.stage_phi, nblk);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, c.spill ? k_ipm<true> : k_ipm<false>, 256, smem);
+        fprintf(stderr, "k_ipm: dynamic smem %zu B, caps nu %d rows %d, stage_phi %d, spill %d, resident CTAs per SM %d\n", smem, c.nu, c.rows, c.stage_phi, c.spill, nblk);
     }
-    k_ipm<<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want, gate);
+    if (c.spill) k_ipm<true><<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want, gate);
+    else k_ipm<false><<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want, gate);
 }
 
 }  // namespace bgg

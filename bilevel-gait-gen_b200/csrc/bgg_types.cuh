@@ -87,7 +87,9 @@ struct Params {
     double ipm_reg_eps;          // static regularisation of the eliminated cone block: W = 1 / (s/z + eps)
     double ipm_tol_infeas;       // infeasibility certificate tolerance (Clarabel tol_infeas_abs / _rel)
     int32_t ipm_max_iter, ipm_refine;
-    double ipm_refine_mu_frac;   // iterative refinement starts once mu <= this fraction of the first iteration's mu
+    double ipm_refine_mu_frac;   // iterative refinement starts once mu <= this fraction of the first iteration's mu ...
+    int32_t ipm_refine_from_iter;   // ... or at this iteration, whichever comes first (an instance that needs this many is a hard one)
+    int32_t pad_refine_;
 };
 
 enum SolveStatus : int32_t {    // mpc::SolveQuality, qp_interface.h:12-22

@@ -77,6 +77,7 @@ struct WsLayout {             // byte offsets inside one instance's workspace
     size_t hdr, nodes, samples, eq, zprev, H, g, phipos, xoff, u, lam, slack, nueq, zqp, dualx;
     size_t gdx, gdz, gdlam, gdnu, gdnue, gdH, ginfo;   // gait-gradient outputs (csrc/bgg_gradient.cu)
     size_t ktab;                                       // item table of the KKT assembly (csrc/bgg_kkt_mma.cuh)
+    size_t ipm_spill;                                  // k_ipm's primal residual rows and foot-box right-hand sides when they do not fit on chip
     int32_t N, max_nu, max_rows, pad;
 };
 
@@ -111,6 +112,7 @@ inline WsLayout make_layout(int N, int max_nu) {
     L.gdH = take(8 * kNumEE * kMaxContacts);                          // dH/dtheta, foot-major
     L.ginfo = take(sizeof(GradInfo));
     L.ktab = take(12 * 1536 + 24 * 512);                              // kMaxKktItems x sizeof(KktItem) + kMaxKktPos x sizeof(KktPos)
+    L.ipm_spill = take(8 * (static_cast<size_t>(L.max_rows) + 16 * static_cast<size_t>(N - 3)));
     L.stride = o;
     return L;
 }

@@ -45,7 +45,8 @@ typedef struct bgg_config {
     int32_t ipm_max_iter;     /* 0 = default 50 */
     int32_t ipm_refine;       /* iterative refinement of the late solves against the regularised matrix: 0 / positive = one step (default), negative = none */
     int32_t ipm_refine_after; /* refine the solves only once the complementarity gap mu has fallen below 10^-k of its first value, k = this field
-                                 (0: library default 8; negative: refine from the first iteration) */
+                                 (0: library default 12, i.e. only solves run to tighter than default tolerances; negative: refine from the first
+                                 iteration).  Independently of k, an instance still iterating at iteration 20 is refined from there on. */
     double integrator_dt;
     double friction_coef;
     double force_bound;

@@ -222,6 +222,27 @@ def test_receding_horizon_with_mirrored_trajectory():
     assert len(seen_sizes) > 1, "the horizon never changed size: the test did not exercise AddPoly/RemovePoly"
 
 
+def test_spline_evaluation_matches_the_reference_pinned_oracle():
+    """bgg_eval_splines (Trajectory::GetForce / GetEndEffectorLocation, csrc/bgg_spline.cuh: value_at) on a solved, mirrored
+    trajectory against the oracle's spline class -- which tests/test_oracle_splines.py pins bit for bit to the reference's own
+    end_effector_splines.cpp.  Same Hermite arithmetic on both sides: equal to the last bits."""
+    cfg_name = "a1_gait_opt_config"
+    cfg = wl.CONFIGS[cfg_name]
+    states, _, ee = wl.batched_trot_inputs(cfg, 1, seed=2)
+    o = common.make_oracle(cfg_name, states[0])
+    for _ in range(3):
+        o.solve(states[0], 0.0, ee[0], real_time=True)
+    gpu = common.make_gpu(cfg_name, 1, states)
+    common.mirror_oracle_to_gpu(o, gpu, 0)
+    times = np.concatenate([np.linspace(0.0, 1.0, 41), np.random.default_rng(0).uniform(0.0, 1.0, 60)])
+    force, pos = gpu.eval_splines(0, times)
+    for i, t in enumerate(times):
+        for e in range(4):
+            fo, po_ = o.force_at(e, t), o.ee_at(e, t)
+            assert np.abs(force[i, e] - fo).max() <= 1e-13 * max(1.0, np.abs(fo).max()), (t, e)
+            assert np.abs(pos[i, e] - po_).max() <= 1e-15, (t, e)
+
+
 def test_batch_entries_are_independent_and_deterministic():
     cfg_name = "a1_configuration"
     cfg = wl.CONFIGS[cfg_name]

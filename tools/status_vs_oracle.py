@@ -18,8 +18,11 @@ if os.environ.get("REFINE"): kw["ipm_refine"] = int(os.environ["REFINE"])
 if os.environ.get("REFINE_AFTER"): kw["ipm_refine_after"] = int(os.environ["REFINE_AFTER"])
 gpu = common.make_gpu(cfg_name, B, states, **kw)
 hist, ith = [], []
+import time
 for it in range(STEPS):
+    tic = time.perf_counter()
     out = gpu.GetRealTimeUpdate(states, t0, ee)
+    print("   wall ms", round(1e3 * (time.perf_counter() - tic), 2), "refined iters mean", np.mean([gpu.sizes(b)["refined_iters"] for b in range(0, B, max(1, B // 64))]))
     hist.append(out["status"].copy()); ith.append(out["iters"].copy())
     print(it, "status hist", np.bincount(out["status"], minlength=9).tolist(), "iters mean", round(float(out["iters"].mean()), 2),
           "max", int(out["iters"].max()), flush=True)
