@@ -362,11 +362,12 @@ def main():
     #      candidates, #5 the 65 536-scenario closed-loop sweep cut across the ranks (strong scaling)
     extra = {}
     if main_mode == "solve" and not args.no_extra_configs:
-        g3 = run_leg("a1_gait_opt_config", "gait", 64, 3, 1, gait_k=64)
+        G3_STEPS, G3_WARM = 6, 3   # the contact times move every step: a few more steps than the solve legs, to average over them
+        g3 = run_leg("a1_gait_opt_config", "gait", 64, G3_STEPS, G3_WARM, gait_k=64)
         g3["mpc"].close()
         extra["#3"] = {"workload": "a1_gait_opt_config: N=50, 64 instances per GPU, per step solve + dH/dtheta + contact-time LP + line search over 64 candidates (65 RTI solves per instance)",
-                       "value": g3["value"], "unit": UNIT, "scaling": "weak", "steps": 3, "warmup": 1, "ms_per_step": g3["ms_dev"] / 3,
-                       "gait_steps_per_s": g3["total"] * 3 / (g3["ms_dev"] * 1e-3), "e2e": g3["e2e_value"],
+                       "value": g3["value"], "unit": UNIT, "scaling": "weak", "steps": G3_STEPS, "warmup": G3_WARM, "ms_per_step": g3["ms_dev"] / G3_STEPS,
+                       "gait_steps_per_s": g3["total"] * G3_STEPS / (g3["ms_dev"] * 1e-3), "e2e": g3["e2e_value"],
                        "instances_with_gradient": g3["gait_stats"]["grad_ok"], "solved_fraction_parents": g3["solved_fraction"]}
         c5 = run_leg("a1_config_distr_rejection", "closed_loop", 0, 5, 2, scenarios=args.scenarios)
         c5["mpc"].close()
