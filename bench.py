@@ -250,7 +250,9 @@ def main():
         dt_plant = c["integrator_dt"]
         gait_stats = {"grad_ok": 0, "best_hist": np.zeros(max(gait_k, 1), np.int64)}
         n_max = 12 * (N + 1) + (args.max_spline_vars or 160)
-        z_host = np.zeros((B, n_max))
+        # the buffer the decision vectors come back into: page-locked, as a controller that reads them every tick would hold it
+        z_pinned = torch.zeros((B, n_max), dtype=torch.float64).pin_memory()
+        z_host = z_pinned.numpy()
 
         def gait_tail():   # MPCController::GaitOpt + GaitOptimizer::LineSearch for every instance of the batch
             g = mpc.ComputeCostFcnDerivWrtContactTimes()

@@ -606,9 +606,15 @@ int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double*
     k_gather_headers<<<(B + 127) / 128, 128, 0, h->stream>>>(h->L, h->d_ws, h->d_hdr, B);
     h->launches += 1;
     CU(cudaMemcpyAsync(h->h_hdr, h->d_hdr, sizeof(WsHeader) * static_cast<size_t>(B), cudaMemcpyDeviceToHost, h->stream));
+    // A caller's buffer that is page-locked (cudaHostAlloc / cudaHostRegister) and has the gathered row length takes the DMA
+    // directly; anything else goes through the handle's own pinned staging buffer and one host copy.
+    bool direct = false;
     if (z) {
         const int n_max = kNx * (h->P.N + 1) + h->P.max_nu;
         const int stride = z_stride < n_max ? z_stride : n_max;
+        cudaPointerAttributes attr{};
+        if (stride == z_stride && cudaPointerGetAttributes(&attr, z) == cudaSuccess && attr.type == cudaMemoryTypeHost) direct = true;
+        cudaGetLastError();   // an unregistered pointer is not an error here
         if (h->zcap < stride) {
             cudaFree(h->d_zout);
             cudaFreeHost(h->h_zout);
@@ -620,7 +626,7 @@ int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double*
         }
         k_gather_z<<<B, 128, 0, h->stream>>>(h->L, h->d_ws, h->d_zout, stride);
         h->launches += 1;
-        CU(cudaMemcpyAsync(h->h_zout, h->d_zout, 8 * static_cast<size_t>(B) * stride, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(direct ? z : h->h_zout, h->d_zout, 8 * static_cast<size_t>(B) * stride, cudaMemcpyDeviceToHost, h->stream));
     }
     CU(cudaStreamSynchronize(h->stream));
     if (z) {
@@ -628,7 +634,7 @@ int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double*
         const int stride = z_stride < n_max ? z_stride : n_max;
         for (int b = 0; b < B; ++b) {
             if (!h->h_hdr[b].error && h->h_hdr[b].n > z_stride) return fail(BGG_EINVAL, "an instance has more decision variables than z_stride");
-            std::memcpy(z + static_cast<size_t>(b) * z_stride, h->h_zout + static_cast<size_t>(b) * stride, 8 * static_cast<size_t>(stride));
+            if (!direct) std::memcpy(z + static_cast<size_t>(b) * z_stride, h->h_zout + static_cast<size_t>(b) * stride, 8 * static_cast<size_t>(stride));
         }
     }
     for (int b = 0; b < B; ++b) {

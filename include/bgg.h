@@ -141,6 +141,8 @@ int bgg_qp_solve_batch(bgg_handle* h, int count, int n, int m, const int32_t* P_
 /* The same solve split for measurement: copy inputs to HBM once, run the kernels on resident data, fetch results. */
 int bgg_upload_inputs(bgg_handle* h, const double* state, const double* t0, const double* ee_start);
 int bgg_solve_resident(bgg_handle* h);
+/* z (optional): [batch][z_stride] decision vectors; a page-locked buffer whose z_stride is the full row length 12 (N + 1) + max_spline_vars
+ * receives the device copy directly, any other buffer goes through the handle's pinned staging area */
 int bgg_download_results(bgg_handle* h, int32_t* status, int32_t* iters, double* alpha, double* cost, double* z, int z_stride);
 int bgg_synchronize(bgg_handle* h);
 /* Closed-loop sweeps on resident data: replace every instance's inputs by the model's own next step -- state = node 1 of
