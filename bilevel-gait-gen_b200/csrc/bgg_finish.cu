@@ -23,7 +23,7 @@ size_t finish_smem_bytes(const WsLayout& L) {
     return 2 * sizeof(FootSpline) * kNumEE + 8 * (4 * n_max + static_cast<size_t>(kNx) * (L.N + 1) + 64 + static_cast<size_t>(kNumEE) * 6 * L.N);
 }
 
-__global__ void __launch_bounds__(128) k_finish(Params P, Instance* __restrict__ inst, WsLayout L, char* __restrict__ ws_base, int want, const int* __restrict__ gate) {
+__global__ void __launch_bounds__(128, 5) k_finish(Params P, Instance* __restrict__ inst, WsLayout L, char* __restrict__ ws_base, int want, const int* __restrict__ gate) {
     if (gate && *gate == 0) return;
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     Instance& I = inst[b];

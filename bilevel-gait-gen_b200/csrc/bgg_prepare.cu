@@ -59,7 +59,7 @@ __device__ __forceinline__ void cross3(const double a[3], const double b[3], dou
     o[2] = a[0] * b[1] - a[1] * b[0];
 }
 
-__global__ void __launch_bounds__(128) k_prepare(Params P, Instance* __restrict__ inst, const double* __restrict__ state_in,
+__global__ void __launch_bounds__(128, 6) k_prepare(Params P, Instance* __restrict__ inst, const double* __restrict__ state_in,
                                                  const double* __restrict__ t0_in, const double* __restrict__ ee_start,
                                                  WsLayout L, char* __restrict__ ws_base) {
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
