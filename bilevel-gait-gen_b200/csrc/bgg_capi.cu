@@ -489,7 +489,13 @@ static int solve_pipeline(bgg_handle* h, bgg_handle::Caps& caps, Instance* inst,
                           int B, bool profile) {
     refresh_caps(caps);
     const int worst_nu = h->L.max_nu, worst_ns = kMaxSamples;
-    const int nu_cap = caps.nu > 0 ? caps.nu : worst_nu, ns_cap = caps.nu > 0 ? caps.ns : worst_ns;
+    int nu_cap = caps.nu > 0 ? caps.nu : worst_nu, ns_cap = caps.nu > 0 ? caps.ns : worst_ns;
+    // Tight sizes matter only while they buy the second CTA per SM; beyond that a margin of two block rows and two stances costs
+    // nothing and keeps a horizon that grows by a knot or a stance out of the second pass
+    if (caps.nu > 0 && !ipm_two_per_sm(h->L, nu_cap, ns_cap)) {
+        nu_cap = nu_cap + 16 < worst_nu ? nu_cap + 16 : worst_nu;
+        ns_cap = ns_cap + 2 * kSamplesPerStance < worst_ns ? ns_cap + 2 * kSamplesPerStance : worst_ns;
+    }
     if (profile) cudaEventRecord(h->ev[0], h->stream);
     launch_prepare(h->P, inst, state, t0, ee, h->L, ws, B, h->stream);
     launch_batch_max(h->L, ws, B, caps.d_max, (nu_cap + 7) / 8 * 8, ns_cap, h->stream);

@@ -244,6 +244,10 @@ static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max) {
 static size_t ipm_smem_for(const WsLayout& L, const IpmCaps& c) {
     return ipm_smem_core(L.N, c.nu, c.rows, c.ns, c.spill != 0) + (c.stage_phi ? 8 * static_cast<size_t>(2 * (L.N - 3)) * c.nu : 0);
 }
+bool ipm_two_per_sm(const WsLayout& L, int nu_max, int ns_max) {   // do these maxima leave room for a second CTA on the SM?
+    const IpmCaps c = ipm_caps(L, nu_max, ns_max);
+    return ipm_smem_for(L, c) <= 112 * 1024;
+}
 size_t ipm_smem_bytes(const WsLayout& L) {   // worst case for the configured caps (bgg_create's feasibility check)
     return ipm_smem_core(L.N, L.max_nu, L.max_rows, kMaxSamples);
 }

@@ -84,6 +84,7 @@ void launch_batch_max(const WsLayout& L, char* ws, int B, int* out, int cap_nu, 
 // `want`: the pass_state an instance must have to be processed (0: first pass, 2: second pass with worst-case caps);
 // `gate`: optional device counter, zero = nothing to do for any CTA of this launch
 size_t finish_smem_bytes(const WsLayout& L);
+bool ipm_two_per_sm(const WsLayout& L, int nu_max, int ns_max);
 void launch_finish(const Params& P, Instance* inst, const WsLayout& L, char* ws, int B, int want, const int* gate, cudaStream_t stream);
 size_t ipm_smem_bytes(const WsLayout& L);
 size_t condense_smem_bytes(const WsLayout& L);
