@@ -261,9 +261,13 @@ def main():
             gait_stats["grad_ok"] = int((g["status"] == 0).sum())
             gait_stats["best_hist"] += np.bincount(np.maximum(ls["best"], 0), minlength=gait_k)
 
+        snapshot = []
+
         def step():
             if mode == "closed_loop":
                 mpc.advance_plant(dt_plant)
+            for b, inst in enumerate(snapshot):   # gait leg: every timed step starts from the same trajectories and contact times
+                mpc.set_instance(b, inst)
             mpc.solve_resident()
             if mode == "gait":
                 gait_tail()
@@ -272,6 +276,10 @@ def main():
         mpc.solve_resident()
         for _ in range(warmup):
             step()
+        if mode == "gait":
+            # a gait-optimisation step moves the contact times, so consecutive steps are different problems (3x spread of the step
+            # time over a dozen steps); the timed steps all repeat the one after the warm-up -- 19 KB per instance re-uploaded per step
+            snapshot = [mpc.get_instance(b).copy() for b in range(B)]
         mpc.synchronize()
         barrier()
         l0 = mpc.launch_count()

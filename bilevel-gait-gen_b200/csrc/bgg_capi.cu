@@ -191,12 +191,18 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
-struct DevPool {   // scratch device allocations of one call, released on every exit path
+// Scratch device allocations of one call, released on every exit path.  Stream-ordered (cudaMallocAsync on the handle's stream, from
+// the device's default pool with its release threshold lifted in bgg_create): after the first calls no allocation reaches the
+// driver.  Plain cudaMalloc / cudaFree per call cost 0.3 - 1 ms each next to the multi-GB line-search workspace, with outliers of
+// hundreds of milliseconds (tools/time_gait_steps.py).
+struct DevPool {
+    cudaStream_t stream;
     std::vector<void*> p;
-    ~DevPool() { for (void* q_ : p) cudaFree(q_); }
+    explicit DevPool(cudaStream_t s) : stream(s) {}
+    ~DevPool() { for (void* q_ : p) cudaFreeAsync(q_, stream); }
     template <typename T> T* get(size_t nelem) {
         void* d = nullptr;
-        if (cudaMalloc(&d, sizeof(T) * (nelem ? nelem : 1)) != cudaSuccess) return nullptr;
+        if (cudaMallocAsync(&d, sizeof(T) * (nelem ? nelem : 1), stream) != cudaSuccess) return nullptr;
         p.push_back(d);
         return static_cast<T*>(d);
     }
@@ -301,6 +307,13 @@ int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) 
         finish_smem_bytes(h->L) > static_cast<size_t>(max_smem)) {
         delete h;
         return fail(BGG_EINVAL, "num_nodes / max_spline_vars need more shared memory than the device offers");
+    }
+    {   // scratch allocations are stream-ordered (DevPool): keep what the pool has grown to instead of returning it at every synchronise
+        cudaMemPool_t mp = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&mp, h->device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete h;
@@ -561,7 +574,7 @@ int bgg_ik_batch(bgg_handle* h, int count, const double* state, const double* ee
     if (!h || count <= 0 || !state || !ee_des || !joint_guess || !q || !status) return fail(BGG_EINVAL, "bad argument");
     if (!h->kin_set) return fail(BGG_ESTATE, "bgg_set_kinematics has not been called");
     CU(cudaSetDevice(h->device));
-    DevPool pool;
+    DevPool pool(h->stream);
     const size_t n = static_cast<size_t>(count);
     double *ds = pool.get<double>(13 * n), *de = pool.get<double>(12 * n), *dg = pool.get<double>(12 * n), *dq = pool.get<double>(19 * n);
     int *dst = pool.get<int>(n), *dit = pool.get<int>(4 * n);
@@ -584,7 +597,7 @@ int bgg_targets_from_traj_batch(bgg_handle* h, const double* time, double* q_des
     if (!time || !q_des || !v_des || !force_des || !status) return fail(BGG_EINVAL, "null argument");
     if (!h->kin_set) return fail(BGG_ESTATE, "bgg_set_kinematics has not been called");
     CU(cudaSetDevice(h->device));
-    DevPool pool;
+    DevPool pool(h->stream);
     const size_t n = static_cast<size_t>(h->batch);
     double *dt = pool.get<double>(n), *dq = pool.get<double>(19 * n), *dv = pool.get<double>(18 * n), *df = pool.get<double>(12 * n);
     int* dst = pool.get<int>(n);
@@ -684,7 +697,7 @@ int bgg_qp_solve_batch(bgg_handle* h, int count, int n, int m, const int32_t* P_
     }
     const int mi = static_cast<int>(in_rows.size()), me = static_cast<int>(eq_rows.size());
     const size_t wsd = qp_ws_doubles(n, mi, me);
-    DevPool dev;
+    DevPool dev(h->stream);
     int *dPc = dev.get<int>(n + 1), *dPr = dev.get<int>(nnzP), *dAc = dev.get<int>(n + 1), *dAr = dev.get<int>(nnzA), *dIn = dev.get<int>(mi), *dEq = dev.get<int>(me),
         *dSlot = dev.get<int>(m);
     double *dPv = dev.get<double>(static_cast<size_t>(count) * nnzP), *dAv = dev.get<double>(static_cast<size_t>(count) * nnzA), *dq = dev.get<double>(static_cast<size_t>(count) * n),
@@ -913,7 +926,7 @@ int bgg_param_partials(bgg_handle* h, int b, int ee, int contact_idx, int cap, i
     CU(cudaSetDevice(h->device));
     const int N = h->P.N, nu_cap = h->L.max_nu;
     const size_t nd = param_partials_doubles(N, nu_cap);
-    DevPool pool;
+    DevPool pool(h->stream);
     double* d_out = pool.get<double>(nd);
     double* d_ut = pool.get<double>(nu_cap);
     if (!d_out || !d_ut) return fail(BGG_ECUDA, "out of device memory");
@@ -1147,28 +1160,24 @@ int bgg_optimize_contact_times_batch(bgg_handle* h, const double* time, double t
     if (!h || !h->batch || !time || !step || !xk || !new_times) return fail(BGG_EINVAL, "null argument / no batch");
     CU(cudaSetDevice(h->device));
     const size_t B = h->batch, nv = B * kNumEE * kMaxContacts;
-    double *d_time, *d_grad = nullptr, *d_out;
-    int32_t* d_st;
-    CU(cudaMalloc(&d_time, 8 * B));
-    CU(cudaMalloc(&d_out, 8 * 3 * nv));
-    CU(cudaMalloc(&d_st, 4 * B * kNumEE));
+    DevPool pool(h->stream);
+    double *d_time = pool.get<double>(B), *d_grad = nullptr, *d_out = pool.get<double>(3 * nv);
+    int32_t* d_st = pool.get<int32_t>(B * kNumEE);
+    if (!d_time || !d_out || !d_st) return fail(BGG_ECUDA, "out of device memory");
     CU(cudaMemcpyAsync(d_time, time, 8 * B, cudaMemcpyHostToDevice, h->stream));
     if (dHdtheta) {
-        CU(cudaMalloc(&d_grad, 8 * nv));
+        d_grad = pool.get<double>(nv);
+        if (!d_grad) return fail(BGG_ECUDA, "out of device memory");
         CU(cudaMemcpyAsync(d_grad, dHdtheta, 8 * nv, cudaMemcpyHostToDevice, h->stream));
     }
     launch_gait_lp(h->d_inst, h->L, h->d_ws, h->batch, d_grad, d_time, trust, alpha, d_out, d_out + nv, d_out + 2 * nv, d_st, h->stream);
     h->launches += 1;
     CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(step, d_out, 8 * nv, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(xk, d_out + nv, 8 * nv, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(new_times, d_out + 2 * nv, 8 * nv, cudaMemcpyDeviceToHost, h->stream));
+    if (status) CU(cudaMemcpyAsync(status, d_st, 4 * B * kNumEE, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(step, d_out, 8 * nv, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(xk, d_out + nv, 8 * nv, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(new_times, d_out + 2 * nv, 8 * nv, cudaMemcpyDeviceToHost));
-    if (status) CU(cudaMemcpy(status, d_st, 4 * B * kNumEE, cudaMemcpyDeviceToHost));
-    cudaFree(d_time);
-    cudaFree(d_out);
-    cudaFree(d_st);
-    if (d_grad) cudaFree(d_grad);
     return BGG_OK;
 }
 
@@ -1184,13 +1193,11 @@ int bgg_line_search_batch(bgg_handle* h, int K, const double* xk, const double* 
     }
     int rc = bgg_upload_inputs(h, state, t0, ee_start);
     if (rc) return rc;
-    double* d_vec;
-    int32_t *d_best, *d_q;
-    double* d_costs;
-    CU(cudaMalloc(&d_vec, 8 * 2 * nv));
-    CU(cudaMalloc(&d_best, 4 * B));
-    CU(cudaMalloc(&d_q, 4 * C));
-    CU(cudaMalloc(&d_costs, 8 * C));
+    DevPool pool(h->stream);
+    double* d_vec = pool.get<double>(2 * nv);
+    int32_t *d_best = pool.get<int32_t>(B), *d_q = pool.get<int32_t>(C);
+    double* d_costs = pool.get<double>(C);
+    if (!d_vec || !d_best || !d_q || !d_costs) return fail(BGG_ECUDA, "out of device memory");
     CU(cudaMemcpyAsync(d_vec, xk, 8 * nv, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_vec + nv, step, 8 * nv, cudaMemcpyHostToDevice, h->stream));
     launch_ls_expand(h->d_inst, h->d_ls_inst, h->batch, K, d_vec, d_vec + nv, h->d_state, h->d_t0, h->d_ee, h->d_ls_state, h->d_ls_t0,
@@ -1200,14 +1207,10 @@ int bgg_line_search_batch(bgg_handle* h, int K, const double* xk, const double* 
     launch_ls_select(h->d_inst, h->d_ls_inst, h->L, h->d_ls_ws, h->batch, K, d_best, d_costs, d_q, h->stream);
     h->launches += 2;
     CU(cudaGetLastError());
+    if (best) CU(cudaMemcpyAsync(best, d_best, 4 * B, cudaMemcpyDeviceToHost, h->stream));
+    if (costs) CU(cudaMemcpyAsync(costs, d_costs, 8 * C, cudaMemcpyDeviceToHost, h->stream));
+    if (quality) CU(cudaMemcpyAsync(quality, d_q, 4 * C, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    if (best) CU(cudaMemcpy(best, d_best, 4 * B, cudaMemcpyDeviceToHost));
-    if (costs) CU(cudaMemcpy(costs, d_costs, 8 * C, cudaMemcpyDeviceToHost));
-    if (quality) CU(cudaMemcpy(quality, d_q, 4 * C, cudaMemcpyDeviceToHost));
-    cudaFree(d_vec);
-    cudaFree(d_best);
-    cudaFree(d_q);
-    cudaFree(d_costs);
     return BGG_OK;
 }
 
