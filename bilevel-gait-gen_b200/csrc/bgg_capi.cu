@@ -323,7 +323,7 @@ int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) 
     for (auto& e : h->user_ev) cudaEventCreate(&e);
     for (bgg_handle::Caps* c : {&h->caps_main, &h->caps_ls}) {
         cudaMalloc(&c->d_max, 3 * sizeof(int));
-        cudaMallocHost(&c->h_max, 2 * sizeof(int));
+        cudaMallocHost(&c->h_max, 3 * sizeof(int));
         cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming);
     }
     *out = h;
@@ -486,53 +486,46 @@ int bgg_upload_inputs(bgg_handle* h, const double* state, const double* t0, cons
     return BGG_OK;
 }
 
-// Take delivery of the maxima of the last solve that measured them.  The event sits right behind that solve's k_prepare /
-// k_batch_max, in front of its condense / interior-point / finish kernels: waiting for it never drains the stream.
-static void refresh_caps(bgg_handle::Caps& caps) {
-    if (!caps.pending) return;
-    cudaEventSynchronize(caps.ev);
-    caps.nu = caps.h_max[0] > 0 ? caps.h_max[0] : 8;
-    caps.ns = caps.h_max[1];
-    caps.pending = false;
-}
+// Kept for the callers that size something from the main batch's maxima: solve_pipeline now takes delivery itself.
+static void refresh_caps(bgg_handle::Caps& caps) { (void)caps; }
 
 // steps 1-11 of MPCSingleRigidBody::Solve for `B` instances living in (inst, ws) with inputs (state, t0, ee) on the device.
-// Nothing here waits for the device.
+//
+// Shared memory (one or two CTAs per SM) is sized from the batch maxima of (spline variables, force samples), which only
+// k_prepare knows.  The solve kernels are enqueued at once with the previous solve's maxima -- the usual case: nothing changed --
+// and while the device works on them the host waits for the event right behind k_prepare / k_batch_max (about a millisecond into
+// the step; the queue behind it is full, the device never idles).  Instances that outgrew the sizes were marked by k_batch_max;
+// if there are any, a second pass is launched for them with the exact new maxima.  (Round 2 first launched that second pass
+// unconditionally with worst-case sizes, one CTA per SM: in a closed-loop sweep every scenario's horizon grows at the same tick,
+// and those ticks took twice as long.)
 static int solve_pipeline(bgg_handle* h, bgg_handle::Caps& caps, Instance* inst, char* ws, const double* state, const double* t0, const double* ee,
                           int B, bool profile) {
-    refresh_caps(caps);
-    const int worst_nu = h->L.max_nu, worst_ns = kMaxSamples;
-    int nu_cap = caps.nu > 0 ? caps.nu : worst_nu, ns_cap = caps.nu > 0 ? caps.ns : worst_ns;
-    // Tight sizes matter only while they buy the second CTA per SM; beyond that a margin of two block rows and two stances costs
-    // nothing and keeps a horizon that grows by a knot or a stance out of the second pass
-    if (caps.nu > 0 && !ipm_two_per_sm(h->L, nu_cap, ns_cap)) {
-        nu_cap = nu_cap + 16 < worst_nu ? nu_cap + 16 : worst_nu;
-        ns_cap = ns_cap + 2 * kSamplesPerStance < worst_ns ? ns_cap + 2 * kSamplesPerStance : worst_ns;
-    }
+    const bool have = caps.nu > 0;
+    auto run_pass = [&](int nu_cap, int ns_cap, int want, bool timed) {
+        if (timed) cudaEventRecord(h->ev[1], h->stream);
+        launch_condense(h->P, h->L, ws, B, nu_cap, want, nullptr, h->stream);
+        if (timed) cudaEventRecord(h->ev[2], h->stream);
+        launch_ipm(h->P, h->L, ws, B, nu_cap, ns_cap, want, nullptr, h->stream);
+        if (timed) cudaEventRecord(h->ev[3], h->stream);
+        launch_finish(h->P, inst, h->L, ws, B, want, nullptr, h->stream);
+        if (timed) cudaEventRecord(h->ev[4], h->stream);
+        h->launches += 3;
+    };
     if (profile) cudaEventRecord(h->ev[0], h->stream);
     launch_prepare(h->P, inst, state, t0, ee, h->L, ws, B, h->stream);
-    launch_batch_max(h->L, ws, B, caps.d_max, (nu_cap + 7) / 8 * 8, ns_cap, h->stream);
-    CU(cudaMemcpyAsync(caps.h_max, caps.d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    launch_batch_max(h->L, ws, B, caps.d_max, have ? (caps.nu + 7) / 8 * 8 : 0, have ? caps.ns : -1, h->stream);   // nothing known: everything is marked
+    CU(cudaMemcpyAsync(caps.h_max, caps.d_max, 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaEventRecord(caps.ev, h->stream));
-    caps.pending = true;
-    if (profile) cudaEventRecord(h->ev[1], h->stream);
-    launch_condense(h->P, h->L, ws, B, nu_cap, 0, nullptr, h->stream);
-    if (profile) cudaEventRecord(h->ev[2], h->stream);
-    launch_ipm(h->P, h->L, ws, B, nu_cap, ns_cap, 0, nullptr, h->stream);
-    if (profile) cudaEventRecord(h->ev[3], h->stream);
-    launch_finish(h->P, inst, h->L, ws, B, 0, nullptr, h->stream);
-    if (profile) cudaEventRecord(h->ev[4], h->stream);
-    h->launches += 5;
-    if (nu_cap < worst_nu || ns_cap < worst_ns) {   // second pass: the instances that outgrew the caps (CTAs of all others return at once)
-        const int* gate = caps.d_max + 2;   // how many instances k_batch_max marked: zero ends every CTA before it touches its workspace
-        launch_condense(h->P, h->L, ws, B, worst_nu, 2, gate, h->stream);
-        launch_ipm(h->P, h->L, ws, B, worst_nu, worst_ns, 2, gate, h->stream);
-        launch_finish(h->P, inst, h->L, ws, B, 2, gate, h->stream);
-        h->launches += 3;
-    }
+    h->launches += 2;
+    if (have) run_pass(caps.nu, caps.ns, 0, profile);
+    CU(cudaEventSynchronize(caps.ev));
+    const int nu_now = caps.h_max[0] > 0 ? caps.h_max[0] : 8, ns_now = caps.h_max[1];
+    if (caps.h_max[2] > 0) run_pass(nu_now, ns_now, 2, profile && !have);
+    caps.nu = nu_now;
+    caps.ns = ns_now;
     if (&caps == &h->caps_main) {
-        h->last_nu_max = nu_cap;
-        h->last_ns_max = ns_cap;
+        h->last_nu_max = nu_now;
+        h->last_ns_max = ns_now;
     }
     CU(cudaGetLastError());
     return BGG_OK;
