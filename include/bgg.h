@@ -138,7 +138,9 @@ int bgg_qp_solve_batch(bgg_handle* h, int count, int n, int m, const int32_t* P_
                        const int32_t* A_colptr, const int32_t* A_rowidx, const double* A_val, const double* q, const double* b,
                        const uint8_t* is_eq, double* x, double* y, double* s, int32_t* status, int32_t* iters);
 
-/* The same solve split for measurement: copy inputs to HBM once, run the kernels on resident data, fetch results. */
+/* The same solve split for measurement: copy inputs to HBM once, run the kernels on resident data, fetch results.
+ * bgg_solve_resident returns with the solve enqueued on the handle's stream; it waits only for the step's first small kernel
+ * (the per-instance set-up, whose sizes decide the shared-memory layout of the rest), not for the solve. */
 int bgg_upload_inputs(bgg_handle* h, const double* state, const double* t0, const double* ee_start);
 int bgg_solve_resident(bgg_handle* h);
 /* z (optional): [batch][z_stride] decision vectors; a page-locked buffer whose z_stride is the full row length 12 (N + 1) + max_spline_vars
