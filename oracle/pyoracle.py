@@ -498,6 +498,24 @@ class SrbMpc:
         n = self._chk(self.lib.orc_mpc_gait_gradient(self.h, _dptr(out), 64))
         return out[:n].copy() if n else None
 
+    def gait_lp(self, time, grad, solution=None):
+        """(which="ref" only, after gait_gradient) GaitOptimizer::OptimizeContactTimes as the reference wrote it.  solution None: returns
+        (2, A dense, lb, ub, q) -- the LP the reference built, recorded by the solver stand-in; with a solution (the LP's optimum, OSQP being
+        absent): returns (0, A, lb, ub, q, new_times) where new_times are the optimiser's contact times after the step, foot-major."""
+        self.lib.orc_mpc_gait_lp.argtypes = [C.c_void_p, C.c_double, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp]
+        g = np.ascontiguousarray(grad, dtype=np.float64)
+        n = len(g)
+        m = 2 * n + 12
+        dims = np.zeros(2, np.int32)
+        A, lb, ub, q, nt = np.zeros((m, n)), np.zeros(m), np.zeros(m), np.zeros(n), np.zeros(n)
+        sol = None if solution is None else np.ascontiguousarray(solution, dtype=np.float64)
+        rc = self.lib.orc_mpc_gait_lp(self.h, float(time), _dptr(g), None if sol is None else _dptr(sol), _iptr(dims), _dptr(A), _dptr(lb),
+                                      _dptr(ub), _dptr(q), _dptr(nt))
+        if rc < 0:
+            raise OracleError(self.lib.orc_last_error().decode())
+        assert (dims[0], dims[1]) == (m, n), dims
+        return (rc, A, lb, ub, q) if rc == 2 else (rc, A, lb, ub, q, nt)
+
     def contact_times(self, ee):
         n = self.lib.orc_mpc_num_contacts(self.h, ee)
         t, ty = np.zeros(n), np.zeros(n, dtype=np.int32)

@@ -1,5 +1,8 @@
-// TEST INFRASTRUCTURE ONLY.  Compile-only stand-in for OsqpEigen::Solver: mpc/include/qp/osqp_interface.h and
-// gait_optimizer.h hold one as a member.  The MPC hot path never calls it (the OSQP branch is dead code).
+// TEST INFRASTRUCTURE ONLY.  Stand-in for OsqpEigen::Solver: mpc/include/qp/osqp_interface.h and gait_optimizer.h hold one as a
+// member.  The MPC hot path never calls it (the OSQP branch is dead code).  GaitOptimizer::OptimizeContactTimes does
+// (gait_optimizer.cpp:185-364): OSQP itself is absent from this image, so the stand-in RECORDS the problem the reference hands over
+// (P, q, A, l, u -- the parity tests compare them with the restatement's) and returns the solution the test driver injected
+// (OsqpEigen::recorded().x), which lets the reference's own post-processing of the step run; without one, solveProblem throws.
 #pragma once
 #include <Eigen/SparseCore>
 #include <memory>
@@ -15,6 +18,15 @@ enum class Status { Solved = 1, SolvedInaccurate = 2, PrimalInfeasibleInaccurate
 enum class ErrorExitFlag { NoError = 0, DataValidationError, SettingsValidationError, LinsysSolverLoadError, LinsysSolverInitError, NonCvxError, MemAllocError, WorkspaceNotInitError };
 
 [[noreturn]] inline void unavailable() { throw std::runtime_error("ref_shim/OsqpEigen: compile-only stand-in"); }
+
+struct Recorded {
+    Eigen::SparseMatrix<double> A, P;
+    Eigen::VectorXd l, u, q;
+    Eigen::VectorXd x;        // injected solution
+    bool have_x = false;
+    int solves = 0;
+};
+inline Recorded& recorded() { static Recorded r; return r; }
 
 class Settings {
 public:
@@ -44,12 +56,12 @@ class Data {
 public:
     void setNumberOfVariables(int) {}
     void setNumberOfConstraints(int) {}
-    template <typename M> bool setHessianMatrix(const M&) { return true; }
-    template <typename M> bool setLinearConstraintsMatrix(const M&) { return true; }
-    template <typename V> bool setGradient(V&) { return true; }
-    template <typename V> bool setLowerBound(V&) { return true; }
-    template <typename V> bool setUpperBound(V&) { return true; }
-    template <typename V> bool setBounds(V&, V&) { return true; }
+    template <typename M> bool setHessianMatrix(const M& P) { recorded().P = P; return true; }
+    template <typename M> bool setLinearConstraintsMatrix(const M& A) { recorded().A = A; return true; }
+    template <typename V> bool setGradient(V& q) { recorded().q = q; return true; }
+    template <typename V> bool setLowerBound(V& l) { recorded().l = l; return true; }
+    template <typename V> bool setUpperBound(V& u) { recorded().u = u; return true; }
+    template <typename V> bool setBounds(V& l, V& u) { recorded().l = l; recorded().u = u; return true; }
     void clearHessianMatrix() {}
     void clearLinearConstraintsMatrix() {}
     bool isSet() const { return false; }
@@ -59,14 +71,18 @@ public:
     Solver() : settings_(new Settings), data_(new Data) {}
     const std::unique_ptr<Settings>& settings() const { return settings_; }
     const std::unique_ptr<Data>& data() const { return data_; }
-    bool initSolver() { unavailable(); }
+    bool initSolver() { return true; }
     bool isInitialized() const { return false; }
     void clearSolver() {}
     bool clearSolverVariables() { return true; }
-    ErrorExitFlag solveProblem() { unavailable(); }
-    Status getStatus() const { return Status::Unsolved; }
-    Eigen::VectorXd getSolution() { unavailable(); }
-    Eigen::VectorXd getDualSolution() { unavailable(); }
+    ErrorExitFlag solveProblem() {
+        if (!recorded().have_x) throw std::runtime_error("ref_shim/OsqpEigen: no solution was injected (OSQP is not in this image)");
+        recorded().solves++;
+        return ErrorExitFlag::NoError;
+    }
+    Status getStatus() const { return recorded().have_x ? Status::Solved : Status::Unsolved; }
+    Eigen::VectorXd getSolution() { return recorded().x; }
+    Eigen::VectorXd getDualSolution() { return Eigen::VectorXd::Zero(recorded().l.size()); }
     double getObjValue() const { return 0; }
     template <typename V> bool setWarmStart(const V&, const V&) { return true; }
     template <typename V> bool setPrimalVariable(const V&) { return true; }

@@ -339,4 +339,52 @@ int orc_mpc_gait_gradient(void* hv, double* out, int cap) {
     return d.size();
     CATCH(-1)
 }
+
+// GaitOptimizer::OptimizeContactTimes (gait_optimizer.cpp:185-364) as the reference wrote it, on the optimiser orc_mpc_gait_gradient
+// set up (contact times of the MPC's trajectory).  grad: dH/dtheta to use (n entries).  solution == NULL: the reference builds its LP,
+// the stand-in solver records it and the call returns 2 with dims = [rows, cols] and the dense A [rows][cols], lb, ub, q filled;
+// solution != NULL: it is handed back as the LP's solution, the reference finishes the step, new_times [n] = its contact times after.
+int orc_mpc_gait_lp(void* hv, double time, const double* grad, const double* solution, int* dims, double* A_dense, double* lb, double* ub,
+                    double* q, double* new_times) {
+    Handle* h = static_cast<Handle*>(hv);
+    if (!h->gait) { g_err = "call orc_mpc_gait_gradient first"; return -1; }
+    GaitOptimizer& g = *h->gait;
+    auto& rec = OsqpEigen::recorded();
+    int n = 0;
+    for (int ee = 0; ee < 4; ee++) n += static_cast<int>(g.GetContactTimes().at(ee).size());
+    g.dHdth = vector_t::Zero(n);
+    for (int i = 0; i < n; i++) g.dHdth(i) = grad[i];
+    rec.have_x = solution != nullptr;
+    if (solution) {
+        rec.x = vector_t::Zero(n);
+        for (int i = 0; i < n; i++) rec.x(i) = solution[i];
+    }
+    auto export_lp = [&]() {
+        dims[0] = rec.A.rows();
+        dims[1] = rec.A.cols();
+        for (int i = 0; i < rec.A.rows(); i++)
+            for (int j = 0; j < rec.A.cols(); j++) A_dense[static_cast<size_t>(i) * rec.A.cols() + j] = rec.A.coeff(i, j);
+        for (int i = 0; i < rec.l.size(); i++) { lb[i] = rec.l(i); ub[i] = rec.u(i); }
+        for (int i = 0; i < rec.q.size(); i++) q[i] = rec.q(i);
+    };
+    try {
+        MuteCout mute;
+        g.OptimizeContactTimes(time, 0.0);
+    } catch (const std::runtime_error& e) {
+        g_err = e.what();
+        if (!solution && g_err.find("no solution was injected") != std::string::npos) {
+            export_lp();
+            return 2;
+        }
+        return -1;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+    export_lp();
+    int k = 0;
+    for (int ee = 0; ee < 4; ee++)
+        for (const auto& t : g.GetContactTimes().at(ee)) new_times[k++] = t.GetTime();
+    return 0;
+}
 }  // extern "C"

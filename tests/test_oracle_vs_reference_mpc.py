@@ -135,3 +135,34 @@ def test_gait_gradient_matches_the_reference_chain(cfg_name):
     n = len(g_o)
     assert n == sum(len(r.contact_times(e)[0]) for e in range(4))
     assert np.abs(g_ref[:n] - g_o).max() <= 1e-9 * max(1.0, np.abs(g_o).max()), (g_ref[:n], g_o)
+
+
+@pytest.mark.parametrize("cfg_name", ["a1_configuration", "a1_gait_opt_config"])
+def test_contact_time_lp_is_the_one_the_reference_builds(cfg_name):
+    """GaitOptimizer::OptimizeContactTimes (gait_optimizer.cpp:185-364: CreatePolytopeConstraint, CreateStartConstraint,
+    CreateTrustRegionConstraint, CreateNextNodeConstraints, the zero Hessian, ConvertQPVecToContactTimes) run as the reference wrote
+    it.  OSQP is absent, so the solver stand-in records the LP the reference hands over and plays back an injected optimum: the
+    restatement's LP (oracle/gait_oracle.py: gait_lp) must be the same matrix and bounds, and the contact times the reference makes of
+    the step must be the restatement's (contact_times_for)."""
+    import gait_oracle as go
+    cfg = wl.CONFIGS[cfg_name]
+    init = np.asarray(cfg["srb_init"], float)
+    r = _make(cfg_name, "ref", init)
+    assert r.initial_run(init, wl.EE_NOMINAL) == 0 and r.solve(init, 0.0, wl.EE_NOMINAL) == 0
+    g = r.gait_gradient()
+    assert g is not None
+    ct = [r.contact_times(e) for e in range(4)]
+    n = sum(len(t) for t, _ in ct)
+    g = g[:n]
+    for time in (0.0, 0.13):
+        A_o, lb_o, ub_o = go.gait_lp(ct, g, time)
+        rc, A_r, lb_r, ub_r, q_r = r.gait_lp(time, g)
+        assert rc == 2
+        assert np.array_equal(A_r, A_o.toarray())
+        assert np.array_equal(lb_r, lb_o) and np.array_equal(ub_r, ub_o) and np.array_equal(q_r, g)
+    step = go.solve_gait_lp(ct, g, 0.0)
+    xk = np.concatenate([t for t, _ in ct])
+    rc, _, _, _, _, new_times = r.gait_lp(0.0, g, step)
+    assert rc == 0
+    want = np.concatenate(go.contact_times_for(ct, xk, step, 1.0))
+    assert np.array_equal(new_times, want), np.abs(new_times - want).max()
