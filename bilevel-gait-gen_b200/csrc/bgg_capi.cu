@@ -503,11 +503,11 @@ static int solve_pipeline(bgg_handle* h, bgg_handle::Caps& caps, Instance* inst,
     const bool have = caps.nu > 0;
     auto run_pass = [&](int nu_cap, int ns_cap, int want, bool timed) {
         if (timed) cudaEventRecord(h->ev[1], h->stream);
-        launch_condense(h->P, h->L, ws, B, nu_cap, want, nullptr, h->stream);
+        launch_condense(h->P, h->L, ws, B, nu_cap, want, h->stream);
         if (timed) cudaEventRecord(h->ev[2], h->stream);
-        launch_ipm(h->P, h->L, ws, B, nu_cap, ns_cap, want, nullptr, h->stream);
+        launch_ipm(h->P, h->L, ws, B, nu_cap, ns_cap, want, h->stream);
         if (timed) cudaEventRecord(h->ev[3], h->stream);
-        launch_finish(h->P, inst, h->L, ws, B, want, nullptr, h->stream);
+        launch_finish(h->P, inst, h->L, ws, B, want, h->stream);
         if (timed) cudaEventRecord(h->ev[4], h->stream);
         h->launches += 3;
     };

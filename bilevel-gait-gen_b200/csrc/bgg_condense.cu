@@ -45,8 +45,7 @@ __device__ __forceinline__ double lds_c(unsigned addr) {
 constexpr int kCondAcc = 21;
 
 template <int NITEM>
-__global__ void __launch_bounds__(256, (NITEM == 1) ? 2 : 1) k_condense(Params P, WsLayout L, char* __restrict__ ws_base, int cap_nu, int want, const int* __restrict__ gate) {
-    if (gate && *gate == 0) return;
+__global__ void __launch_bounds__(256, (NITEM == 1) ? 2 : 1) k_condense(Params P, WsLayout L, char* __restrict__ ws_base, int cap_nu, int want) {
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5, g = lane >> 2, t = lane & 3;
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
@@ -231,7 +230,7 @@ __global__ void __launch_bounds__(256, (NITEM == 1) ? 2 : 1) k_condense(Params P
         }
 }
 
-void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int want, const int* gate, cudaStream_t stream) {
+void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int want, cudaStream_t stream) {
     int cap = (nu_max + 7) / 8 * 8;
     if (cap > L.max_nu) cap = L.max_nu;
     const size_t smem = condense_smem_for(cap);
@@ -239,8 +238,8 @@ void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, int nu
     cudaFuncSetAttribute(k_condense<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     cudaFuncSetAttribute(k_condense<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     // eight warps own one pair of block rows each up to 16 block rows (nu <= 128), two pairs beyond
-    if (cap / 8 <= 16) k_condense<1><<<B, 256, smem, stream>>>(P, L, ws, cap, want, gate);
-    else k_condense<2><<<B, 256, smem, stream>>>(P, L, ws, cap, want, gate);
+    if (cap / 8 <= 16) k_condense<1><<<B, 256, smem, stream>>>(P, L, ws, cap, want);
+    else k_condense<2><<<B, 256, smem, stream>>>(P, L, ws, cap, want);
 }
 
 // Batch maxima of (nu, n_samples) for the shared-memory sizing of the NEXT solve, and the instances that do not fit the caps THIS

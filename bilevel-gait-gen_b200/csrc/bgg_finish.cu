@@ -23,8 +23,7 @@ size_t finish_smem_bytes(const WsLayout& L) {
     return 2 * sizeof(FootSpline) * kNumEE + 8 * (4 * n_max + static_cast<size_t>(kNx) * (L.N + 1) + 64 + static_cast<size_t>(kNumEE) * 6 * L.N);
 }
 
-__global__ void __launch_bounds__(128, 5) k_finish(Params P, Instance* __restrict__ inst, WsLayout L, char* __restrict__ ws_base, int want, const int* __restrict__ gate) {
-    if (gate && *gate == 0) return;
+__global__ void __launch_bounds__(128, 5) k_finish(Params P, Instance* __restrict__ inst, WsLayout L, char* __restrict__ ws_base, int want) {
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     Instance& I = inst[b];
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
@@ -287,11 +286,11 @@ __global__ void __launch_bounds__(128, 5) k_finish(Params P, Instance* __restric
     }
 }
 
-void launch_finish(const Params& P, Instance* inst, const WsLayout& L, char* ws, int B, int want, const int* gate, cudaStream_t stream) {
+void launch_finish(const Params& P, Instance* inst, const WsLayout& L, char* ws, int B, int want, cudaStream_t stream) {
     const size_t smem = finish_smem_bytes(L);
     // per device and context, so set on every launch (see launch_ipm)
     cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    k_finish<<<B, 128, smem, stream>>>(P, inst, L, ws, want, gate);
+    k_finish<<<B, 128, smem, stream>>>(P, inst, L, ws, want);
 }
 
 }  // namespace bgg

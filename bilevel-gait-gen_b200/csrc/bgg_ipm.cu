@@ -253,9 +253,7 @@ size_t ipm_smem_bytes(const WsLayout& L) {   // worst case for the configured ca
 }
 
 template <bool kSpill>
-__global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi, int cap_nu, int cap_rows, int want,
-                                                  const int* __restrict__ gate) {
-    if (gate && *gate == 0) return;
+__global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi, int cap_nu, int cap_rows, int want) {
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
     WsHeader* Hd = reinterpret_cast<WsHeader*>(ws + L.hdr);
@@ -795,7 +793,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
     (void)gscale;
 }
 
-void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, const int* gate, cudaStream_t stream) {
+void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, cudaStream_t stream) {
     const IpmCaps c = ipm_caps(L, nu_max, ns_max);
     const size_t smem = ipm_smem_for(L, c);
     // the opt-in is per device and context: set on every launch (a second handle on another GPU, or another host thread,
@@ -806,8 +804,8 @@ void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max,
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, c.spill ? k_ipm<true> : k_ipm<false>, 256, smem);
         fprintf(stderr, "k_ipm: dynamic smem %zu B, caps nu %d rows %d, stage_phi %d, spill %d, resident CTAs per SM %d\n", smem, c.nu, c.rows, c.stage_phi, c.spill, nblk);
     }
-    if (c.spill) k_ipm<true><<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want, gate);
-    else k_ipm<false><<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want, gate);
+    if (c.spill) k_ipm<true><<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want);
+    else k_ipm<false><<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want);
 }
 
 }  // namespace bgg

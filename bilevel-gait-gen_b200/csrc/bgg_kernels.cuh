@@ -76,16 +76,15 @@ constexpr int kPartHdr = 32;
 __host__ __device__ size_t param_partials_doubles(int N, int nu_cap);
 void launch_param_partials(const Params& P, const Instance* inst, const WsLayout& L, const char* ws, int b, int ee, int idx, int nu_cap, double* out,
                            double* ut, cudaStream_t stream);
-void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int want, const int* gate, cudaStream_t stream);
-void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, const int* gate, cudaStream_t stream);
+void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int want, cudaStream_t stream);
+void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, cudaStream_t stream);
 // max over the batch of (nu, n_samples) after launch_prepare, written to out[0..1] (device); instances larger than the caps
 // are marked for the second pass (WsHeader::pass_state = 2)
 void launch_batch_max(const WsLayout& L, char* ws, int B, int* out, int cap_nu, int cap_ns, cudaStream_t stream);
-// `want`: the pass_state an instance must have to be processed (0: first pass, 2: second pass with worst-case caps);
-// `gate`: optional device counter, zero = nothing to do for any CTA of this launch
+// `want`: the pass_state an instance must have to be processed (0: first pass, 2: second pass for the instances that outgrew the first pass's sizes)
 size_t finish_smem_bytes(const WsLayout& L);
 bool ipm_two_per_sm(const WsLayout& L, int nu_max, int ns_max);
-void launch_finish(const Params& P, Instance* inst, const WsLayout& L, char* ws, int B, int want, const int* gate, cudaStream_t stream);
+void launch_finish(const Params& P, Instance* inst, const WsLayout& L, char* ws, int B, int want, cudaStream_t stream);
 size_t ipm_smem_bytes(const WsLayout& L);
 size_t condense_smem_bytes(const WsLayout& L);
 

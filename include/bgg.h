@@ -157,7 +157,7 @@ int bgg_advance_plant(bgg_handle* h, double dt);
  * triplets in the reference's numbering -- dA (num_eq x n: dynamics | touch-down | foot start), dG (num_ineq x n: force box |
  * friction pyramid | foot box), db [num_eq]; exact zeros are not listed (utils/sparse_matrix_builder.cpp:25).  The gait-gradient
  * path (bgg_gait_gradient_batch) never forms these; this is the export for callers that want the matrices (test/mpc_test.cpp:140-236).
- * counts = [nnz dA, nnz dG, num_eq, num_ineq].  Returns BGG_OK; 1 when the instance's last solve is not Solved (the reference
+ * counts = [nnz dA, nnz dG, num_eq, num_ineq]; db must hold 12 (N + 1) + 16 entries (num_eq never exceeds that).  Returns BGG_OK; 1 when the instance's last solve is not Solved (the reference
  * returns false); a negative code otherwise (cap too small: counts holds the sizes needed). */
 int bgg_param_partials(bgg_handle* h, int b, int ee, int contact_idx, int cap, int32_t* counts, int32_t* Ar, int32_t* Ac, double* Av, int32_t* Gr,
                        int32_t* Gc, double* Gv, double* db);
