@@ -500,7 +500,10 @@ static void refresh_caps(bgg_handle::Caps& caps) { (void)caps; }
 // and those ticks took twice as long.)
 static int solve_pipeline(bgg_handle* h, bgg_handle::Caps& caps, Instance* inst, char* ws, const double* state, const double* t0, const double* ee,
                           int B, bool profile) {
-    const bool have = caps.nu > 0;
+    // Speculate only while the previous sizes are worth having: two CTAs per SM.  Beyond that (K alone fills the SM's shared memory) a
+    // horizon that has shrunk again would run a whole pass at half the occupancy it could have; there the pass waits for the exact
+    // sizes (the device idles for one host round trip, tens of microseconds in a step of a second).
+    const bool have = caps.nu > 0 && ipm_two_per_sm(h->L, caps.nu, caps.ns);
     auto run_pass = [&](int nu_cap, int ns_cap, int want, bool timed) {
         if (timed) cudaEventRecord(h->ev[1], h->stream);
         launch_condense(h->P, h->L, ws, B, nu_cap, want, h->stream);

@@ -209,13 +209,14 @@ static __device__ __forceinline__ void ipm_apply_H(const IpmCtx& c, const double
 }
 
 struct IpmCaps {          // per-launch shared-memory sizing, from the actual maxima over the batch
-    int nu, rows, ns, stage_phi, spill;
+    int nu, rows, ns, stage_phi, spill, threads;
 };
+constexpr int kRedDoubles256 = 72, kRedDoubles512 = 136;   // block_reduce_multi: 8 values per warp; chol::solve: 64
 // spill: the row vectors s, z (they live in the workspace's slack / lam output arrays from the start), rz and the foot-box
 // right-hand sides stay in L2 -- three of the six row vectors on chip instead of six
-static size_t ipm_smem_core(int N, int nu, int rows, int ns, bool spill = false) {
+static size_t ipm_smem_core(int N, int nu, int rows, int ns, bool spill = false, int red = kRedDoubles256) {
     const size_t kc = 2 * (N - 3), eb = 4 * (N - 3);
-    return 8 * (chol::doubles(nu / 8) + 6 * nu + (spill ? 3 : 6) * static_cast<size_t>(rows) + (spill ? 0 : 2 * eb * 2) + 2 * kc + 5 * kMaxEq + 72 + 2 * eb) +
+    return 8 * (chol::doubles(nu / 8) + 6 * nu + (spill ? 3 : 6) * static_cast<size_t>(rows) + (spill ? 0 : 2 * eb * 2) + 2 * kc + 5 * kMaxEq + red + 2 * eb) +
            8 * eb + sizeof(Sample) * static_cast<size_t>(ns) + sizeof(ColInfo) * static_cast<size_t>(nu) + 64;
 }
 static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max) {
@@ -233,27 +234,33 @@ static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max) {
     // if that does not cost the second CTA
     const size_t half = 112 * 1024;   // + 1 KB static + 1 KB reserved per CTA, twice, inside the SM's 228 KB
     c.spill = 0;
+    c.threads = 256;
     if (core <= half) c.stage_phi = (core + phi <= half) ? 1 : 0;
     else if (ipm_smem_core(L.N, c.nu, c.rows, c.ns, true) <= half) {
         // N = 50: 1232 rows.  Two CTAs per SM with three row vectors in L2 beat one CTA with everything on chip
         c.spill = 1;
         c.stage_phi = 0;
-    } else c.stage_phi = (core + phi <= 225 * 1024) ? 1 : 0;
+    } else {
+        // K alone leaves no room for a second CTA (nu > 136): one CTA per SM, with sixteen warps instead of eight
+        c.threads = 512;
+        c.stage_phi = (core + phi + 8 * (kRedDoubles512 - kRedDoubles256) <= 225 * 1024) ? 1 : 0;
+    }
     return c;
 }
 static size_t ipm_smem_for(const WsLayout& L, const IpmCaps& c) {
-    return ipm_smem_core(L.N, c.nu, c.rows, c.ns, c.spill != 0) + (c.stage_phi ? 8 * static_cast<size_t>(2 * (L.N - 3)) * c.nu : 0);
+    return ipm_smem_core(L.N, c.nu, c.rows, c.ns, c.spill != 0, c.threads == 512 ? kRedDoubles512 : kRedDoubles256) +
+           (c.stage_phi ? 8 * static_cast<size_t>(2 * (L.N - 3)) * c.nu : 0);
 }
 bool ipm_two_per_sm(const WsLayout& L, int nu_max, int ns_max) {   // do these maxima leave room for a second CTA on the SM?
     const IpmCaps c = ipm_caps(L, nu_max, ns_max);
     return ipm_smem_for(L, c) <= 112 * 1024;
 }
 size_t ipm_smem_bytes(const WsLayout& L) {   // worst case for the configured caps (bgg_create's feasibility check)
-    return ipm_smem_core(L.N, L.max_nu, L.max_rows, kMaxSamples);
+    return ipm_smem_core(L.N, L.max_nu, L.max_rows, kMaxSamples, false, kRedDoubles512);
 }
 
-template <bool kSpill>
-__global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi, int cap_nu, int cap_rows, int want) {
+template <bool kSpill, int kThreads>
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi, int cap_nu, int cap_rows, int want) {
     const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
     WsHeader* Hd = reinterpret_cast<WsHeader*>(ws + L.hdr);
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(256, 2) k_ipm(Params P, WsLayout L, char* __re
         if (!spill) { S.d = p; p += 2 * 8 * (N - 3); }   // right-hand sides of the foot-box rows only (force rows: see rhs_of)
         S.tkc = p; p += nkc; S.ckc = p; p += nkc;
         S.nueq = p; p += kMaxEq; S.re = p; p += kMaxEq; S.dnu = p; p += kMaxEq; S.y1 = p; p += kMaxEq; S.a3 = p; p += kMaxEq;
-        S.red = p; p += 72;   // block_reduce scratch (33) / chol::solve scratch (64)
+        S.red = p; p += (kThreads == 512 ? kRedDoubles512 : kRedDoubles256);   // block_reduce_multi scratch (8 per warp) / chol::solve scratch (64)
         S.pw = p; p += 2 * 4 * (N - 3);
         S.pcnt = reinterpret_cast<int*>(p);
         S.poff = S.pcnt + 4 * (N - 3);
@@ -798,14 +805,17 @@ void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max,
     const size_t smem = ipm_smem_for(L, c);
     // the opt-in is per device and context: set on every launch (a second handle on another GPU, or another host thread,
     // must not depend on what an earlier launch configured)
-    cudaFuncSetAttribute(c.spill ? k_ipm<true> : k_ipm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const void* fn = c.threads == 512 ? reinterpret_cast<const void*>(k_ipm<false, 512>)
+                                      : (c.spill ? reinterpret_cast<const void*>(k_ipm<true, 256>) : reinterpret_cast<const void*>(k_ipm<false, 256>));
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (getenv("BGG_DEBUG_OCC")) {
         int nblk = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, c.spill ? k_ipm<true> : k_ipm<false>, 256, smem);
-        fprintf(stderr, "k_ipm: dynamic smem %zu B, caps nu %d rows %d, stage_phi %d, spill %d, resident CTAs per SM %d\n", smem, c.nu, c.rows, c.stage_phi, c.spill, nblk);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, fn, c.threads, smem);
+        fprintf(stderr, "k_ipm: dynamic smem %zu B, caps nu %d rows %d, stage_phi %d, spill %d, threads %d, resident CTAs per SM %d\n", smem, c.nu, c.rows, c.stage_phi, c.spill, c.threads, nblk);
     }
-    if (c.spill) k_ipm<true><<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want);
-    else k_ipm<false><<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want);
+    if (c.threads == 512) k_ipm<false, 512><<<B, 512, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want);
+    else if (c.spill) k_ipm<true, 256><<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want);
+    else k_ipm<false, 256><<<B, 256, smem, stream>>>(P, L, ws, c.stage_phi, c.nu, c.rows, want);
 }
 
 }  // namespace bgg

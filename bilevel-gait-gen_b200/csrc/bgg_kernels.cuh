@@ -42,8 +42,8 @@ __device__ __noinline__ double block_reduce(double v, double* scratch) {
     return scratch[32];
 }
 
-// NS sums followed by NM maxima in one pass (one pair of barriers for all of them); scratch >= 8 (NS + NM) doubles,
-// blockDim.x <= 256.  Result broadcast to every thread in v.
+// NS sums followed by NM maxima in one pass (one pair of barriers for all of them); scratch >= (NS + NM) doubles per warp.
+// Result broadcast to every thread in v.
 template <int NS, int NM>
 __device__ __forceinline__ void block_reduce_multi(double (&v)[NS + NM], double* scratch) {   // inlined: v stays in registers
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
