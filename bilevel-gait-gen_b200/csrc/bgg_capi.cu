@@ -910,15 +910,13 @@ int bgg_param_partials(bgg_handle* h, int b, int ee, int contact_idx, int cap, i
     if (rc) return rc;
     if (sz.error) return fail(BGG_ESTATE, "the instance has no QP (k_prepare refused it)");
     if (sz.status != kSolved) return 1;   // the reference returns false (mpc_single_rigid_body.cpp:644-647)
-    int32_t nct[kNumEE * 1];
     {
         std::vector<double> t(kNumEE * kMaxContacts);
         std::vector<int32_t> ty(kNumEE * kMaxContacts), n(kNumEE);
         rc = bgg_get_contact_times(h, b, 1, t.data(), ty.data(), n.data());
         if (rc) return rc;
-        nct[0] = n[ee];
+        if (contact_idx >= n[ee]) return fail(BGG_EINVAL, "contact_idx is beyond the foot's contact times");
     }
-    if (contact_idx >= nct[0]) return fail(BGG_EINVAL, "contact_idx is beyond the foot's contact times");
     CU(cudaSetDevice(h->device));
     const int N = h->P.N, nu_cap = h->L.max_nu;
     const size_t nd = param_partials_doubles(N, nu_cap);
