@@ -46,7 +46,7 @@ def _kkt_check(qp, z, tol_eq=1e-6, tol_in=1e-6):
 def test_first_solve_matches_oracle(cfg_name):
     cfg = wl.CONFIGS[cfg_name]
     N = cfg["num_nodes"]
-    B = 12
+    B = 32 if N == 20 else 16
     states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=3)
     states[0] = cfg["srb_init"]
     ee[0] = wl.EE_NOMINAL
@@ -81,9 +81,11 @@ def test_first_solve_matches_oracle(cfg_name):
             assert _rel(sol["z"], o.prev_qp_sol()) < 1e-12
             continue
         assert st == 0, f"instance {b}: neither Solved nor PrimalInfeasible ({st}); pick inputs the solver classifies"
-        # same iteration, so the same count -- up to a step when a residual crosses its threshold within rounding, and
-        # except on the nearly degenerate instance of this batch (44 against 50 iterations; both converge)
-        assert abs(int(out["iters"][b]) - oq["iters"]) <= 2 or min(int(out["iters"][b]), oq["iters"]) >= 30
+        # same iteration, so the same count -- up to a step or two when a residual crosses its threshold within rounding; long
+        # solves at this tight tolerance (the nearly degenerate instances: 26 against 29, 44 against 50 iterations, both
+        # converge) spend their last iterations at the accuracy floor of the factorisation, where the two sides' roundings differ
+        gi, oi = int(out["iters"][b]), int(oq["iters"])
+        assert abs(gi - oi) <= max(2, int(0.15 * max(gi, oi))), (b, gi, oi)
         _kkt_check(qp, sol["qp_sol"])
         obj = lambda z: 0.5 * z @ (qp["P"] @ z) + qp["q"] @ z
         assert abs(obj(sol["qp_sol"]) - obj(oq["x"])) <= 1e-4 * max(1.0, abs(obj(oq["x"])))
