@@ -55,7 +55,7 @@ struct bgg_handle {
     };
     Caps caps_main, caps_ls;
     int last_nu_max = 0, last_ns_max = 0;   // caps the main batch's last solve was launched with (sizing of k_gradient)
-    int max_smem = 0;
+    int max_smem = 0, sm_count = 0;
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
@@ -303,6 +303,7 @@ int bgg_create(const bgg_config* cfg, const bgg_robot* robot, bgg_handle** out) 
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
     h->max_smem = max_smem;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
     if (ipm_smem_bytes(h->L) > static_cast<size_t>(max_smem) || condense_smem_bytes(h->L) > static_cast<size_t>(max_smem) ||
         finish_smem_bytes(h->L) > static_cast<size_t>(max_smem)) {
         delete h;
@@ -508,7 +509,7 @@ static int solve_pipeline(bgg_handle* h, bgg_handle::Caps& caps, Instance* inst,
         if (timed) cudaEventRecord(h->ev[1], h->stream);
         launch_condense(h->P, h->L, ws, B, nu_cap, want, h->stream);
         if (timed) cudaEventRecord(h->ev[2], h->stream);
-        launch_ipm(h->P, h->L, ws, B, nu_cap, ns_cap, want, h->stream);
+        launch_ipm(h->P, h->L, ws, B, nu_cap, ns_cap, want, h->stream, h->sm_count);
         if (timed) cudaEventRecord(h->ev[3], h->stream);
         launch_finish(h->P, inst, h->L, ws, B, want, h->stream);
         if (timed) cudaEventRecord(h->ev[4], h->stream);

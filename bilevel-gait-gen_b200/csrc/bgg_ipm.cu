@@ -219,7 +219,7 @@ static size_t ipm_smem_core(int N, int nu, int rows, int ns, bool spill = false,
     return 8 * (chol::doubles(nu / 8) + 6 * nu + (spill ? 3 : 6) * static_cast<size_t>(rows) + (spill ? 0 : 2 * eb * 2) + 2 * kc + 5 * kMaxEq + red + 2 * eb) +
            8 * eb + sizeof(Sample) * static_cast<size_t>(ns) + sizeof(ColInfo) * static_cast<size_t>(nu) + 64;
 }
-static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max) {
+static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max, bool alone = false) {
     IpmCaps c;
     c.nu = (nu_max + 7) / 8 * 8;
     if (c.nu > L.max_nu) c.nu = L.max_nu;
@@ -235,7 +235,11 @@ static IpmCaps ipm_caps(const WsLayout& L, int nu_max, int ns_max) {
     const size_t half = 112 * 1024;   // + 1 KB static + 1 KB reserved per CTA, twice, inside the SM's 228 KB
     c.spill = 0;
     c.threads = 256;
-    if (core <= half) c.stage_phi = (core + phi <= half) ? 1 : 0;
+    if (alone && core <= half) {
+        // fewer CTAs than SMs (a single robot's solve): every CTA has an SM to itself, so the room of the second CTA holds the dense
+        // position rows (1.58 -> 1.52 ms for one instance; sixteen warps on top of that are slower here: 1.67 ms)
+        c.stage_phi = (core + phi <= 225 * 1024) ? 1 : 0;
+    } else if (core <= half) c.stage_phi = (core + phi <= half) ? 1 : 0;
     else if (ipm_smem_core(L.N, c.nu, c.rows, c.ns, true) <= half) {
         // N = 50: 1232 rows.  Two CTAs per SM with three row vectors in L2 beat one CTA with everything on chip
         c.spill = 1;
@@ -800,8 +804,8 @@ __global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1) k_ipm(Param
     (void)gscale;
 }
 
-void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, cudaStream_t stream) {
-    const IpmCaps c = ipm_caps(L, nu_max, ns_max);
+void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, cudaStream_t stream, int sm_count) {
+    const IpmCaps c = ipm_caps(L, nu_max, ns_max, B <= sm_count);
     const size_t smem = ipm_smem_for(L, c);
     // the opt-in is per device and context: set on every launch (a second handle on another GPU, or another host thread,
     // must not depend on what an earlier launch configured)

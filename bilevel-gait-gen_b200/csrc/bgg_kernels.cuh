@@ -77,7 +77,7 @@ __host__ __device__ size_t param_partials_doubles(int N, int nu_cap);
 void launch_param_partials(const Params& P, const Instance* inst, const WsLayout& L, const char* ws, int b, int ee, int idx, int nu_cap, double* out,
                            double* ut, cudaStream_t stream);
 void launch_condense(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int want, cudaStream_t stream);
-void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, cudaStream_t stream);
+void launch_ipm(const Params& P, const WsLayout& L, char* ws, int B, int nu_max, int ns_max, int want, cudaStream_t stream, int sm_count = 0);
 // max over the batch of (nu, n_samples) after launch_prepare, written to out[0..1] (device); instances larger than the caps
 // are marked for the second pass (WsHeader::pass_state = 2)
 void launch_batch_max(const WsLayout& L, char* ws, int B, int* out, int cap_nu, int cap_ns, cudaStream_t stream);
