@@ -78,7 +78,7 @@ struct IpmCtx {
 // out[0..m) = C v   (v: nu-vector in shared memory); with eout != nullptr also eout[0..neq) = E v - rhs_scale e, computed by the
 // last warp while the others take the samples (no extra barrier)
 // kRowsShared: every row vector lives in shared memory (false in the spilled layout, where some are in the workspace)
-template <bool kRowsShared>
+template <bool kRowsShared, int kThreads>
 static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double* v, double* out, double* eout, double rhs_scale) {
     const Smem S = c.S;
     const int *fbase = c.fbase, *pbase = c.pbase, *nfv = c.nfv, *npv = c.npv;
@@ -86,7 +86,8 @@ static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double
     __builtin_assume(__isShared(S.smp)); __builtin_assume(__isShared(S.pw)); __builtin_assume(__isShared(S.pcnt));
     __builtin_assume(__isShared(S.poff)); __builtin_assume(__isShared(fbase)); __builtin_assume(__isShared(pbase));
     __builtin_assume(__isShared(nfv)); __builtin_assume(__isShared(npv));
-    const int tid = threadIdx.x, nth = blockDim.x;
+    const int tid = threadIdx.x;
+    constexpr int nth = kThreads;   // the launch's block size, known at compile time: constant strides
     const int nf = c.nf, ns = c.ns, ne = c.ne, nkc = c.nkc;
     const double mu_f = c.mu_f;
     l2_phi_rows_dot(S.phi, S.phi_stride, nkc, nf, smem_addr(v), smem_addr(S.tkc));   // dense position rows (csrc/bgg_l2ops.cuh)
@@ -129,13 +130,14 @@ static __device__ __forceinline__ void ipm_apply_C(const IpmCtx& c, const double
 
 // out[0..nu) += C' y   (y: m-vector; inactive rows carry y == 0); with ey != nullptr also += escale E' ey (the equality rows
 // touch position columns only: the thread that owns the column adds them).  Every output entry is owned by one thread.
-template <bool kRowsShared>
+template <bool kRowsShared, int kThreads>
 static __device__ __forceinline__ void ipm_add_Ct(const IpmCtx& c, const double* y, double* out, const double* ey, double escale) {
     const Smem S = c.S;
     if (kRowsShared) __builtin_assume(__isShared(y)); __builtin_assume(__isShared(out)); __builtin_assume(__isShared(S.ckc));
     __builtin_assume(__isShared(S.smp)); __builtin_assume(__isShared(S.pw)); __builtin_assume(__isShared(S.col));
     __builtin_assume(__isShared(S.poff));
-    const int tid = threadIdx.x, nth = blockDim.x;
+    const int tid = threadIdx.x;
+    constexpr int nth = kThreads;
     const int nu = c.nu, nf = c.nf, ns = c.ns, nkc = c.nkc;
     const double mu_f = c.mu_f;
     #pragma unroll 1
@@ -265,7 +267,8 @@ size_t ipm_smem_bytes(const WsLayout& L) {   // worst case for the configured ca
 
 template <bool kSpill, int kThreads>
 __global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1) k_ipm(Params P, WsLayout L, char* __restrict__ ws_base, int stage_phi, int cap_nu, int cap_rows, int want) {
-    const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    constexpr int nth = kThreads;   // = blockDim.x (launch_ipm)
     char* ws = ws_base + static_cast<size_t>(b) * L.stride;
     WsHeader* Hd = reinterpret_cast<WsHeader*>(ws + L.hdr);
     if (!Hd->error && Hd->pass_state != want) return;   // not this pass's instance (uniform over the CTA)
@@ -416,8 +419,8 @@ __global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1) k_ipm(Param
     IpmCtx ctx;
     ctx.S = S; ctx.Hg = Hg; ctx.eq = s_eq; ctx.fbase = s_fbase; ctx.pbase = s_pbase; ctx.nfv = s_nfv; ctx.npv = s_npv;
     ctx.N = N; ctx.nu = nu; ctx.nf = nf; ctx.ns = ns; ctx.ne = ne; ctx.neq = neq; ctx.nkc = nkc; ctx.mu_f = mu_f;
-    auto apply_C = [&](const double* v, double* out, double* eout, double rhs_scale) { PROF(10); ipm_apply_C<!kSpill>(ctx, v, out, eout, rhs_scale); PROF(6); };
-    auto add_Ct = [&](const double* y, double* out, const double* ey, double escale) { PROF(10); ipm_add_Ct<!kSpill>(ctx, y, out, ey, escale); PROF(7); };
+    auto apply_C = [&](const double* v, double* out, double* eout, double rhs_scale) { PROF(10); ipm_apply_C<!kSpill, kThreads>(ctx, v, out, eout, rhs_scale); PROF(6); };
+    auto add_Ct = [&](const double* y, double* out, const double* ey, double escale) { PROF(10); ipm_add_Ct<!kSpill, kThreads>(ctx, y, out, ey, escale); PROF(7); };
     auto apply_H = [&](const double* v, double* out, bool subtract) { PROF(10); ipm_apply_H(ctx, v, out, subtract); PROF(8); };
 
     // K = H + eps I + C' diag(wv) C + E'E/delta in 8 x 8 blocks in shared memory (csrc/bgg_kkt_mma.cuh), then chol::factor in place.
