@@ -245,6 +245,33 @@ def test_spline_evaluation_matches_the_reference_pinned_oracle():
             assert np.abs(pos[i, e] - po_).max() <= 1e-15, (t, e)
 
 
+def test_decision_vectors_come_back_the_same_through_pinned_and_pageable_buffers():
+    """bgg_download_results copies straight into a caller's page-locked buffer and through its own staging area otherwise: same bytes."""
+    import ctypes
+    cfg_name = "a1_configuration"
+    cfg = wl.CONFIGS[cfg_name]
+    B = 48
+    states, t0, ee = wl.batched_trot_inputs(cfg, B, seed=5)
+    gpu = common.make_gpu(cfg_name, B, states)
+    n_max = 12 * (cfg["num_nodes"] + 1) + 160
+    z_page = np.zeros((B, n_max))
+    z_pin = np.zeros((B, n_max))
+    rt = ctypes.CDLL("libcudart.so")
+    assert rt.cudaHostRegister(ctypes.c_void_p(z_pin.ctypes.data), ctypes.c_size_t(z_pin.nbytes), 0) == 0
+    try:
+        gpu.GetRealTimeUpdate(states, t0, ee, z_out=z_page)
+        out = gpu.download(z_out=z_pin)
+        narrow = np.zeros((B, n_max - 40))           # a row length other than the gathered one: staged path, rows cut
+        gpu.download(z_out=narrow)
+    finally:
+        rt.cudaHostUnregister(ctypes.c_void_p(z_pin.ctypes.data))
+    assert np.all(out["status"] == 0)
+    assert np.array_equal(z_pin, z_page) and np.abs(z_pin).max() > 0
+    assert np.array_equal(narrow, z_page[:, :n_max - 40])
+    n = gpu.sizes(0)["n"]
+    assert np.array_equal(z_page[0, :n], gpu.solution(0)["z"])
+
+
 def test_batch_entries_are_independent_and_deterministic():
     cfg_name = "a1_configuration"
     cfg = wl.CONFIGS[cfg_name]
