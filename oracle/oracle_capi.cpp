@@ -356,6 +356,13 @@ int orc_mpc_set_contact_times(void* h, int ee, const double* t, int n) {
     return 0;
     ORC_CATCH(-1)
 }
+// MPC::AdjustForCurrentContacts (mpc.cpp:1195-1203)
+int orc_mpc_adjust_for_contacts(void* h, double time, const int* in_contact) {
+    ORC_TRY
+    M(h).AdjustForCurrentContacts(time, {in_contact[0] != 0, in_contact[1] != 0, in_contact[2] != 0, in_contact[3] != 0});
+    return 0;
+    ORC_CATCH(-1)
+}
 // sizes: [n, m, nnzA, nnzP, num_dyn, num_force_box, num_cone, num_ee_loc, num_td, num_start, nf, np, num_eq, num_ineq]
 void orc_mpc_sizes(void* h, int* out) {
     const QpData& d = M(h).Data();

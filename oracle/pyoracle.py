@@ -498,6 +498,12 @@ class SrbMpc:
         n = self._chk(self.lib.orc_mpc_gait_gradient(self.h, _dptr(out), 64))
         return out[:n].copy() if n else None
 
+    def adjust_for_current_contacts(self, time, in_contact):
+        """MPC::AdjustForCurrentContacts (mpc.cpp:1195-1203)."""
+        self.lib.orc_mpc_adjust_for_contacts.argtypes = [C.c_void_p, C.c_double, _ip]
+        c = np.ascontiguousarray(in_contact, dtype=np.int32)
+        self._chk(self.lib.orc_mpc_adjust_for_contacts(self.h, float(time), _iptr(c)))
+
     def gait_lp(self, time, grad, solution=None):
         """(which="ref" only, after gait_gradient) GaitOptimizer::OptimizeContactTimes as the reference wrote it.  solution None: returns
         (2, A dense, lb, ub, q) -- the LP the reference built, recorded by the solver stand-in; with a solution (the LP's optimum, OSQP being

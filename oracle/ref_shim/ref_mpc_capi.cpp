@@ -311,6 +311,16 @@ int orc_mpc_set_contact_times(void* h, int ee, const double* t, int n) {
     CATCH(-1)
 }
 
+// MPC::AdjustForCurrentContacts (mpc.cpp:1195-1203), the reference's own
+int orc_mpc_adjust_for_contacts(void* h, double time, const int* in_contact) {
+    TRY
+    controller::Contact c(4);
+    for (int ee = 0; ee < 4; ee++) c.in_contact_.at(ee) = in_contact[ee] != 0;
+    M(h).AdjustForCurrentContacts(time, c);
+    return 0;
+    CATCH(-1)
+}
+
 // The derivative chain of MPCController::GaitOpt (controllers/mpc_controller.cpp:518-552), run on the reference's own
 // ClarabelInterface::SetupDerivativeCalcs / CalcDerivativeWrtMats / Vecs, MPCSingleRigidBody::ComputeParamPartialsClarabel and
 // GaitOptimizer::ComputeCostFcnDerivWrtContactTimes.  out: dH/dtheta, foot-major; returns the number of contact times,

@@ -166,3 +166,33 @@ def test_contact_time_lp_is_the_one_the_reference_builds(cfg_name):
     assert rc == 0
     want = np.concatenate(go.contact_times_for(ct, xk, step, 1.0))
     assert np.array_equal(new_times, want), np.abs(new_times - want).max()
+
+
+def test_adjust_for_current_contacts_is_the_references():
+    """MPC::AdjustForCurrentContacts (mpc.cpp:1195-1203): a swing foot reported in contact within 70 ms of its planned touch-down is
+    put in contact in the plan (EndEffectorSplines::SetToTouchdown), otherwise nothing changes.  Reference code against the
+    restatement: the contact schedules after the call and the whole next RTI step, bit for bit."""
+    cfg_name = "a1_configuration"
+    cfg = wl.CONFIGS[cfg_name]
+    init = np.asarray(cfg["srb_init"], float)
+    for early_by, expect_change in ((0.05, True), (0.15, False)):
+        r, o = _make(cfg_name, "ref", init), _make(cfg_name, "oracle", init)
+        assert r.initial_run(init, wl.EE_NOMINAL) == o.initial_run(init, wl.EE_NOMINAL) == 0
+        before = [r.contact_times(e) for e in range(4)]
+        swing = [e for e in range(4) if before[e][1][0] != po.TOUCH_DOWN][0]      # a foot that starts in swing
+        t_td = [t for t, ty in zip(*before[swing]) if ty == po.TOUCH_DOWN][0]     # its first planned touch-down
+        now = t_td - early_by
+        flags = [1 if e == swing else 0 for e in range(4)]
+        r.adjust_for_current_contacts(now, flags)
+        o.adjust_for_current_contacts(now, flags)
+        after_r = [r.contact_times(e) for e in range(4)]
+        after_o = [o.contact_times(e) for e in range(4)]
+        for e in range(4):
+            assert np.array_equal(after_r[e][0], after_o[e][0]) and np.array_equal(after_r[e][1], after_o[e][1])
+        changed = not all(np.array_equal(after_r[e][0], before[e][0]) for e in range(4))
+        assert changed == expect_change
+        ee_now = np.array([o.ee_at(e, now) for e in range(4)])
+        state = o.states()[1].copy()
+        assert r.solve(state, now, ee_now) == o.solve(state, now, ee_now)
+        _assert_same_qp_bitwise(r, o)
+        _assert_same_step_bitwise(r, o)
