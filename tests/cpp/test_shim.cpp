@@ -211,6 +211,13 @@ int main(int argc, char** argv) {
                 c.in_contact_.at(early) = true;
                 m2.AdjustForCurrentContacts(td - 0.05, c);    // 50 ms early: adjusted
                 std::printf("adjust_near %d\n", m2.GetTrajectory().GetDesiredContacts(td - 0.05).in_contact_.at(early) ? 1 : 0);
+                std::printf("adjust_near_times %.12e", td - 0.05);   // the time of the call, then the foot's contact times after it
+                const std::vector<time_v> adjusted = m2.GetTrajectory().GetContactTimes();
+                for (const auto& tv : adjusted.at(early)) std::printf(" %.12e", tv.GetTime());
+                std::printf("\nadjust_before_times");
+                const std::vector<time_v> unadjusted = before.GetContactTimes();
+                for (const auto& tv : unadjusted.at(early)) std::printf(" %.12e", tv.GetTime());
+                std::printf("\n");
                 MPCSingleRigidBody m3 = mpc;
                 m3.AdjustForCurrentContacts(td - 0.15, c);    // 150 ms early: outside the 70 ms window, unchanged
                 std::printf("adjust_far %d\n", m3.GetTrajectory().GetDesiredContacts(td - 0.15).in_contact_.at(early) ? 1 : 0);

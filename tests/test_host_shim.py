@@ -154,6 +154,19 @@ force_cost: 0.000
     assert abs(float(kv["state1_z"][0]) - o.states()[1][2]) < 1e-6
     assert abs(float(kv["force_ee1_z_t01"][0]) - o.force_at(1, 0.1)[2]) <= 1e-4 * max(1.0, abs(o.force_at(1, 0.1)[2]))
     assert abs(float(kv["ee0_x_t04"][0]) - o.ee_at(0, 0.4)[0]) < 1e-6
+    # AdjustForCurrentContacts on the oracle (itself bit-identical to the reference's, tests/test_oracle_vs_reference_mpc.py): the same
+    # contact times for the foot that was put in contact early
+    foot = int(kv["adjust_swing_foot"][0])
+    call_time, times_after = float(kv["adjust_near_times"][0]), np.array([float(v) for v in kv["adjust_near_times"][1:]])
+    times_before = np.array([float(v) for v in kv["adjust_before_times"]])
+    oa = o.clone()
+    oa.adjust_for_current_contacts(call_time, [1 if e == foot else 0 for e in range(4)])
+    moved_o = np.flatnonzero(oa.contact_times(foot)[0] != o.contact_times(foot)[0])
+    moved = np.flatnonzero(times_after != times_before)
+    # (the C++ object has been through the gait step above, its later contact times differ from the oracle's: what is compared is
+    # which contact time the call moved and where to)
+    assert len(moved) == 1 and np.array_equal(moved, moved_o)
+    assert abs(times_after[moved[0]] - oa.contact_times(foot)[0][moved[0]]) < 1e-12
     g_o = go.cost_gradient(o)
     g = np.array([float(v) for v in kv["gradient"]])
     assert np.abs(g - g_o).max() <= 1e-4 * max(1.0, np.abs(g_o).max())
